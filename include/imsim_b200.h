@@ -1,0 +1,306 @@
+/*
+ * imsim_b200.h -- C ABI of the B200-native photon-shooting hot path.
+ *
+ * This is the drop-in boundary.  Everything above it is
+ * host Python (imsim_b200/ *.py, mirroring imsim's GalSim plugin classes);
+ * everything below it is hand-written sm_100a CUDA (imsim_b200/csrc).  The
+ * signatures use only plain pointers, sizes and POD structs so that the
+ * reference can bind them with ctypes.
+ *
+ * Each entry point names the reference interface it replaces, as
+ * `imsim/<file>.py:<line>` (relative to the LSSTDESC/imSim tree) or the
+ * third-party call made from that line (GalSim / batoid are not vendored in
+ * the reference; see DESIGN.md "Oracle provenance").
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure;
+ *     b2_last_error() gives the message (thread-local).
+ *   - `where` says where the array pointers of a call live:
+ *       B2_HOST   : host memory (numpy).  The library stages the arrays
+ *                   through device scratch; copies are part of the call.
+ *       B2_DEVICE : device memory (e.g. torch.empty(..., device='cuda')).
+ *   - all photon arrays are SoA, float64, length n (GalSim PhotonArray layout).
+ *   - all calls are asynchronous on the context's stream for B2_DEVICE and
+ *     synchronous for B2_HOST.
+ */
+#ifndef IMSIM_B200_H
+#define IMSIM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_ABI_VERSION 1
+
+#define B2_HOST 0
+#define B2_DEVICE 1
+
+/* ------------------------------------------------------------------ */
+/* Telescope description (flattened batoid.Optic)                      */
+/* ------------------------------------------------------------------ */
+
+#define B2_MAX_SURFACES 24
+#define B2_MAX_MEDIA 8
+#define B2_MAX_ASPHERE_COEF 8
+#define B2_MAX_OBSC 4
+#define B2_MAX_POLY_ORDER 12 /* Poly2D extra sag: degree <= 11 */
+
+/* surface kinds (batoid.Plane/Sphere/Paraboloid/Quadric/Asphere) */
+enum { B2_SURF_PLANE = 0, B2_SURF_SPHERE = 1, B2_SURF_PARABOLOID = 2, B2_SURF_QUADRIC = 3, B2_SURF_ASPHERE = 4 };
+/* interaction kinds (batoid.Detector/Mirror/RefractiveInterface/OPDScreen) */
+enum { B2_INT_DETECTOR = 0, B2_INT_MIRROR = 1, B2_INT_REFRACT = 2, B2_INT_PASS = 3 };
+/* extra (summed) sag term: batoid.Sum([base, Zernike]) or Sum([base, Bicubic]) */
+enum { B2_EXTRA_NONE = 0, B2_EXTRA_POLY2D = 1, B2_EXTRA_BICUBIC = 2 };
+/* obscuration primitives (batoid.ObscCircle/ObscAnnulus/ObscRectangle/ObscRay) */
+enum { B2_OBSC_CIRCLE = 0, B2_OBSC_ANNULUS = 1, B2_OBSC_RECTANGLE = 2, B2_OBSC_RAY = 3 };
+/* media (batoid.ConstMedium/SellmeierMedium/SumitaMedium/Air) */
+enum { B2_MED_CONST = 0, B2_MED_SELLMEIER = 1, B2_MED_SUMITA = 2, B2_MED_AIR = 3 };
+
+typedef struct {
+    int32_t kind;   /* B2_OBSC_* */
+    int32_t negate; /* 1: batoid.ObscNegation(primitive), i.e. Clear* */
+    /* circle: p0=radius p1=x0 p2=y0
+       annulus: p0=inner p1=outer p2=x0 p3=y0
+       rectangle: p0=width p1=height p2=x0 p3=y0 p4=cos(theta) p5=sin(theta)
+       ray: p0=width p1=x0 p2=y0 p3=cos(theta) p4=sin(theta) */
+    double p[6];
+} B2Obsc;
+
+typedef struct {
+    int32_t kind; /* B2_MED_* */
+    int32_t pad;
+    /* const: p0=n
+       sellmeier: p0..2=B1..B3, p3..5=C1..C3 (um^2)
+       sumita: p0..5=A0..A5
+       air: p0=pressure[kPa] p1=temperature[K] p2=h2o_pressure[kPa] */
+    double p[6];
+} B2Medium;
+
+typedef struct {
+    int32_t surf_kind;      /* B2_SURF_* */
+    int32_t interact;       /* B2_INT_* */
+    int32_t medium_in;      /* index into B2Telescope.media */
+    int32_t medium_out;
+    int32_t n_coef;         /* asphere: number of even coefs (r^4, r^6, ...) */
+    int32_t rot_identity;   /* 1: drot is the identity (skip the 3x3 products) */
+    int32_t n_obsc;         /* obscurations OR-ed together */
+    int32_t extra_kind;     /* B2_EXTRA_* */
+    double R;               /* radius of curvature (sphere/paraboloid/quadric/asphere) */
+    double conic;
+    double coef[B2_MAX_ASPHERE_COEF];
+    /* transform from the previous interface's coordSys (or the stop surface's
+       for the first one) to this one: r' = drot^T (r - dr), v' = drot^T v
+       (batoid CoordTransform.applyForward) ; drot row-major */
+    double dr[3];
+    double drot[9];
+    B2Obsc obsc[B2_MAX_OBSC];
+    /* Poly2D extra: sag += sum_{i,j} c[i*poly_n + j] X^i Y^j with X=x*poly_scale
+       (batoid.Zernike's xy-coefficient array; scale = 1/R_outer).
+       Bicubic extra: uniform grid, see b2_telescope_set_extra(). */
+    int32_t poly_n;         /* poly order+1 (<= B2_MAX_POLY_ORDER) */
+    int32_t extra_slot;     /* slot in the context's extra table, -1 if none */
+    double poly_scale;
+} B2Surface;
+
+typedef struct {
+    int32_t n_surfaces;
+    int32_t n_media;
+    int32_t medium_stop; /* medium the rays start in (telescope.inMedium) */
+    int32_t pad;
+    B2Surface surf[B2_MAX_SURFACES];
+    B2Medium media[B2_MAX_MEDIA];
+} B2Telescope;
+
+/* ------------------------------------------------------------------ */
+/* WCS pair, detector, diffraction                                     */
+/* ------------------------------------------------------------------ */
+
+/* galsim.GSFitsWCS / FittedSIPWCS, TAN-SIP of order <= 3:
+   imsim/photon_ops.py:471-473,482-483 call xyToradec / radecToxy on two of them */
+typedef struct {
+    double crpix[2];
+    double cd[4];        /* row-major 2x2, degrees per pixel unit */
+    double ab[2][4][4];  /* ab[k][i][j] multiplies u^i v^j, identity folded in; zero if unused */
+    double ra0, dec0;    /* tangent point, radians */
+    int32_t order;       /* 0: no SIP (ab ignored); 1..3 */
+    int32_t pad;
+} B2TanSip;
+
+/* imsim/photon_ops.py:486-503 + imsim/utils.py:42-78 (constant per detector) */
+typedef struct {
+    /* (x_pix, y_pix) = A (fpx, fpy) + b with fpx = ray.y*1e3, fpy = ray.x*1e3 [mm] */
+    double A[4];
+    double b[2];
+    /* (dxdz, dydz) = Jhat (vx, vy) / vz */
+    double Jhat[4];
+} B2Detector;
+
+/* imsim/diffraction.py:32-42 (geometry), :284-415 (field rotation) */
+typedef struct {
+    int32_t enabled;          /* 0: plain RubinOptics */
+    int32_t field_rotation;   /* 0: disable_field_rotation=True */
+    int32_t n_lines, n_circles;
+    double lines[8][4];       /* nx ny d thickness */
+    double circles[4][3];     /* x y r */
+    double e_z_0[3];          /* zenith at t=0, equatorial frame */
+    double e_focal[3];        /* pointing, equatorial frame */
+    double cos_lat, sin_lat;
+    double omega;             /* earth rotation rate [rad/s] */
+} B2Diffraction;
+
+/* options of the fused optics photon-op */
+typedef struct {
+    int32_t shift_in;    /* add stamp_center before (RubinOptics.shift_photons) */
+    int32_t shift_out;   /* subtract stamp_center after (stamp_center is not None) */
+    double stamp_center[2];
+    int32_t do_focus_depth; /* galsim.FocusDepth fused as epilogue */
+    int32_t do_refraction;  /* galsim.Refraction fused as epilogue */
+    double focus_depth;     /* pixels */
+    double index_ratio;
+    uint64_t seed;          /* Philox key when gauss == NULL */
+    uint64_t photon_offset; /* global index of photon 0 (Philox counter) */
+} B2OpticsOptions;
+
+typedef struct {
+    uint64_t n_vignetted;
+    uint64_t n_failed;
+    uint64_t n_offdetector_z; /* |z| >= 1e-15 on the detector (reference asserts) */
+} B2OpticsStats;
+
+/* ------------------------------------------------------------------ */
+/* Silicon sensor                                                      */
+/* ------------------------------------------------------------------ */
+
+/* galsim.SiliconSensor.__init__ / _init_silicon arguments, already reduced
+   to what the C++ Silicon constructor receives */
+typedef struct {
+    int32_t num_vertices;   /* NumVertices per edge */
+    int32_t nx, ny;         /* PixelBoundaryNx/Ny of the vertex table (9) */
+    int32_t qdist;
+    double num_elec;        /* CollectedCharge_0_0 / strength */
+    double nrecalc;         /* nrecalc / strength ; 0 = only on recalc=True */
+    double diff_step;       /* microns, already times diffusion_factor */
+    double pixel_size;      /* microns */
+    double sensor_thickness;/* microns */
+    double treering_center[2];
+    int32_t n_treering;     /* tree-ring table points (<=2: no tree rings) */
+    int32_t n_abs;          /* absorption table points */
+    int32_t transpose;
+    int32_t pad;
+} B2SensorConfig;
+
+typedef struct {
+    double added_flux;
+    uint64_t n_polygon_tests;   /* photons that needed the full polygon test */
+    uint64_t n_neighbor_search; /* photons not in their nominal pixel */
+    uint64_t n_not_found;       /* photons resolved by the coin flip */
+    uint64_t n_boundary_1e9;    /* photons within 1e-9 px of a nominal pixel edge */
+    uint64_t n_updates;         /* boundary updates performed in this call */
+    uint64_t n_dropped_bottom;  /* zconv < 0 */
+} B2AccumStats;
+
+typedef struct b2_ctx b2_ctx;
+typedef struct b2_sensor b2_sensor;
+
+/* ---- library -------------------------------------------------------- */
+const char* b2_last_error(void);
+int b2_abi_version(void);
+/* number of kernels launched by this library since load (bench.py gpu_launches) */
+uint64_t b2_launch_count(void);
+/* sizeof() of the POD structs, for binding self-checks:
+   0 B2Telescope, 1 B2Surface, 2 B2TanSip, 3 B2Detector, 4 B2Diffraction,
+   5 B2OpticsOptions, 6 B2OpticsStats, 7 B2SensorConfig, 8 B2AccumStats, 9 B2Obsc, 10 B2Medium */
+int64_t b2_sizeof(int32_t which);
+
+/* ---- context: one per (process, detector) --------------------------- */
+int b2_ctx_create(int device, void* cuda_stream, b2_ctx** out);
+int b2_ctx_destroy(b2_ctx* ctx);
+int b2_ctx_set_stream(b2_ctx* ctx, void* cuda_stream);
+int b2_ctx_synchronize(b2_ctx* ctx);
+
+/* replaces: base['det_telescope'] (imsim/telescope_loader.py:463) as consumed by
+   imsim/photon_ops.py:108-123 */
+int b2_telescope_upload(b2_ctx* ctx, const B2Telescope* tel);
+/* extra sag tables.  poly2d: data = poly_n*poly_n coefficients.
+   bicubic: data = [x0, dx, nx, y0, dy, ny] followed by 4 grids (z, dzdx, dzdy, d2zdxdy),
+   each ny*nx row-major (batoid.Bicubic). */
+int b2_telescope_set_extra(b2_ctx* ctx, int surface_index, int extra_kind, const double* data, int64_t n);
+/* replaces: base['current_image'].wcs, base['_icrf_to_field'] (imsim/photon_ops.py:407-408) */
+int b2_wcs_upload(b2_ctx* ctx, const B2TanSip* img_wcs, const B2TanSip* icrf_to_field);
+/* replaces: camera[det_name] as used by imsim/photon_ops.py:495-500 */
+int b2_detector_upload(b2_ctx* ctx, const B2Detector* det);
+/* replaces: RubinDiffraction.__init__ (imsim/photon_ops.py:233-262) */
+int b2_diffraction_config(b2_ctx* ctx, const B2Diffraction* cfg);
+
+/* ---- photon ops ------------------------------------------------------- */
+/* XyToV.__call__ (imsim/photon_ops.py:469-475): v is 3 SoA arrays */
+int b2_xy_to_v(b2_ctx* ctx, int64_t n, const double* x, const double* y, double* vx, double* vy, double* vz, int where);
+/* XyToV.inverse (imsim/photon_ops.py:477-483) */
+int b2_v_to_xy(b2_ctx* ctx, int64_t n, const double* vx, const double* vy, const double* vz, double* x, double* y, int where);
+/* batoid Optic.trace on a RayVector in the stop surface's coordSys
+   (imsim/photon_ops.py:109-123).  All arrays in/out.  vignetted/failed: uint8. */
+int b2_trace_rays(b2_ctx* ctx, int64_t n, double* x, double* y, double* z, double* vx, double* vy, double* vz,
+                  double* t, const double* wavelength_m, uint8_t* vignetted, uint8_t* failed, int where);
+/* RubinOptics.applyTo / RubinDiffractionOptics.applyTo (imsim/photon_ops.py:81-127,203-208),
+   optionally fused with galsim.FocusDepth and galsim.Refraction
+   (config/imsim-config.yaml:304-320).  x,y,flux in/out; dxdz,dydz out.
+   gauss: one standard-normal draw per photon (injected, reference order) or NULL (Philox).
+   time_out: optional, ray time at the detector (batoid RayVector.t), may be NULL. */
+int b2_rubin_optics(b2_ctx* ctx, int64_t n, double* x, double* y, double* dxdz, double* dydz, double* flux,
+                    const double* wavelength_nm, const double* pupil_u, const double* pupil_v,
+                    const double* time, const double* gauss, double* time_out, const B2OpticsOptions* opt,
+                    int where, B2OpticsStats* stats);
+/* RubinDiffraction.applyTo (imsim/photon_ops.py:304-352): x,y in/out */
+int b2_rubin_diffraction(b2_ctx* ctx, int64_t n, double* x, double* y, const double* wavelength_nm,
+                         const double* pupil_u, const double* pupil_v, const double* time,
+                         const double* gauss, const B2OpticsOptions* opt, int where);
+/* galsim.TimeSampler + galsim.PupilAnnulusSampler (config/imsim-config.yaml:281-289), Philox */
+int b2_sample_time_pupil(b2_ctx* ctx, int64_t n, double* time, double* pupil_u, double* pupil_v,
+                         double t0, double exptime, double r_inner, double r_outer,
+                         uint64_t seed, uint64_t photon_offset, int where);
+
+/* ---- silicon sensor ---------------------------------------------------- */
+/* replaces galsim.SiliconSensor.__init__ (imsim/lsst_image.py:93-103,
+   config/imsim-config.yaml:230-235).  vertex_data: the .dat table,
+   nx*ny*(4*num_vertices+4) rows of 5 doubles.  treering_r/f/y2: tree-ring lookup
+   table (imsim/treerings.py:192-194) with the second derivatives of its natural
+   cubic spline (galsim.LookupTable default interpolant), y2 == NULL: linear.
+   abs_wave/abs_len: absorption length table, nm -> microns (linear). */
+int b2_sensor_create(b2_ctx* ctx, const B2SensorConfig* cfg, const double* vertex_data,
+                     const double* treering_r, const double* treering_f, const double* treering_y2,
+                     const double* abs_wave, const double* abs_len, b2_sensor** out);
+int b2_sensor_destroy(b2_sensor* s);
+/* bind the image the next accumulate calls add to: bounds (xmin,ymin,nx,ny),
+   dtype_bytes 4 (float32) or 8 (float64); pixels: row-major ny*nx, host or device per `where`.
+   (galsim.Image passed to SiliconSensor.accumulate, imsim/photon_pooling.py:210) */
+int b2_sensor_bind_image(b2_sensor* s, int32_t xmin, int32_t ymin, int32_t nx, int32_t ny,
+                         int32_t dtype_bytes, const void* pixels, int where);
+/* copy the current device image (target + pending delta) out */
+int b2_sensor_read_image(b2_sensor* s, void* pixels, int where);
+/* galsim.SiliconSensor.accumulate(photons, image, orig_center, resume, recalc)
+   (imsim/photon_pooling.py:210, imsim/stamp.py:562-572, imsim/flat.py:261).
+   dxdz/dydz/wavelength_nm may be NULL (not allocated in the PhotonArray).
+   rand4: injected randoms [g1[n], g2[n], u_notfound[n], u_depth[n]] or NULL (Philox). */
+int b2_sensor_accumulate(b2_sensor* s, int64_t n, const double* x, const double* y,
+                         const double* dxdz, const double* dydz, const double* wavelength_nm,
+                         const double* flux, const double* rand4, uint64_t seed, uint64_t photon_offset,
+                         int32_t orig_center_x, int32_t orig_center_y, int32_t resume, int32_t recalc,
+                         int where, B2AccumStats* stats);
+/* galsim.SiliconSensor.calculate_pixel_areas(image, orig_center, use_flux)
+   (imsim/flat.py:223).  Uses the bound image as the charge; areas: ny*nx float64. */
+int b2_sensor_pixel_areas(b2_sensor* s, int32_t orig_center_x, int32_t orig_center_y, int32_t use_flux,
+                          double* areas, int where);
+/* galsim.Sensor.accumulate (= PhotonArray.addTo), used when sensor is None
+   (imsim/photon_pooling.py:139-140,212) */
+int b2_plain_accumulate(b2_sensor* s, int64_t n, const double* x, const double* y, const double* flux,
+                        int where, double* added_flux);
+/* debug/inspection: copy boundary state of pixel (ix,iy) in image coords:
+   poly: (4*nv+4)*2 doubles in polygon order; bounds: inner[4], outer[4] (xmin,xmax,ymin,ymax) */
+int b2_sensor_get_pixel(b2_sensor* s, int32_t ix, int32_t iy, double* poly, double* bounds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMSIM_B200_H */
