@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- photons/s through optics + silicon sensor on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm (default N=1)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port, all host threads)
+
+Workload (config.workload = "C2-pooled"): one LSSTCam e2v science CCD (R22_S11, 4096 x 4004),
+SiliconSensor lsst_e2v_50_4 with brighter-fatter (strength 1) and tree rings on, bright-star
+dominated photon pool.  A step is one photon batch of the pooled pipeline
+(imsim/photon_pooling.py:141-160): TimeSampler + PupilAnnulusSampler ->
+RubinDiffractionOptics + FocusDepth + Refraction -> SiliconSensor.accumulate(resume, recalc=True),
+i.e. pixel boundaries are recomputed from the accumulated charge at every step (nrecalc = 0,
+config/imsim-config-photon-pooling.yaml:33).
+
+`value`  : photons/s with the pool already resident in HBM (CUDA events, max over ranks).
+`e2e`    : same chain through the host-facing API: pinned host arrays -> H2D -> kernels -> D2H of
+           the image and the deposited flux, every step.
+`roofline`: dominant kernel (k_rubin_optics) against HBM (algorithmic 96 B/photon) and, because
+           that kernel is FP64-pipe bound, against the measured FP64 FMA ceiling (`roofline_fp64`).
+With N > 1 every rank simulates its own detector (weak scaling, no data-path collective).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "photons/sec/GPU (optics+sensor)"
+UNIT = "photons/s"
+POOL = 1 << 25  # photons per step (33.5 M): every SoA array is 268 MB > L2 (126 MB)
+ALG_BYTES_TRACE = 96.0  # read x,y,wl,u,v,t,flux (56 B) + write x,y,dxdz,dydz,flux (40 B)
+ALG_FLOP_TRACE = 4000.0  # SURVEY 8d estimate of the reference's FP64 op count per photon (3.8-5.6 k)
+DETECTORS = ["R22_S11", "R21_S11", "R23_S11", "R12_S11", "R32_S11", "R22_S00", "R22_S22", "R11_S11"]
+
+
+def dist_info():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons, power = [], [], set(), []
+        for s in self.samples:
+            f = [t.strip() for t in s.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def sensor_inputs():
+    import helpers
+
+    cfg, dat = helpers.sensor_model("lsst_e2v_50_4")
+    tr = helpers.tree_ring_table("R22_S11")
+    aw, al = helpers.absorption()
+    return cfg, dat, tr, (aw, al)
+
+
+def cpu_baseline(n_sample, threads, det_name="R22_S11", seed=0):
+    """Time the CPU oracle (restatement of the reference path, kind='port') on a bounded sample
+    of the same workload: optics (+diffraction, FocusDepth, Refraction) then sensor (BF + tree rings)."""
+    import helpers
+    from imsim_b200 import _abi
+    from imsim_b200.synthetic import make_detector_setup, synthetic_photons
+    from oracle import oracle as orc
+
+    orc.set_threads(threads)
+    su = make_detector_setup(helpers.oracle_tracer(), det_name, rot_tel_pos=np.radians(60.0))
+    dif = helpers.default_diffraction()
+    cfg, dat, tr, (aw, al) = sensor_inputs()
+    rng = np.random.default_rng(seed)
+    x, y, wl, flux = synthetic_photons(n_sample, kind="stars", seed=seed)
+    u_r = np.sqrt(rng.uniform(2.558**2, 4.18**2, n_sample))
+    ph = rng.uniform(0, 2 * np.pi, n_sample)
+    pu, pv = u_r * np.cos(ph), u_r * np.sin(ph)
+    t = rng.uniform(0, 30, n_sample)
+    gauss = rng.standard_normal(n_sample)
+    rand4 = np.vstack([rng.standard_normal(n_sample), rng.standard_normal(n_sample), rng.uniform(size=n_sample),
+                       rng.uniform(size=n_sample)])
+    opt = _abi.B2OpticsOptions()
+    opt.do_refraction, opt.index_ratio = 1, 3.9
+    pod = helpers.sensor_pod(cfg, nrecalc=0, treering=tr, n_abs=len(aw))
+    sens = orc.Sensor(pod, dat, tr[1].x, tr[1].f, True, aw, al)
+    img = np.zeros((4004, 4096), np.float32)
+    sens.bind_image(img, 0, 0)
+    tel = su.telescope.flatten()
+    # untimed: boundary initialisation of the full CCD (set-up, done once per image)
+    sens.accumulate(x[:10], y[:10], flux[:10], rand4[:, :10].copy())
+    t0 = time.perf_counter()
+    out = orc.rubin_optics(*tel, su.img_wcs.to_pod(), su.icrf_to_field.to_pod(), su.detector.to_pod(), dif, opt, x, y,
+                           flux, wl, pu, pv, t, gauss)
+    t1 = time.perf_counter()
+    sens.accumulate(out["x"], out["y"], out["flux"], rand4, dxdz=out["dxdz"], dydz=out["dydz"], wavelength=wl,
+                    resume=True, recalc=False)
+    t2 = time.perf_counter()
+    return {"value": n_sample / (t2 - t0), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d photons of the C2-pooled workload: oracle optics %.2f s + sensor %.2f s (boundary "
+                      "recalculation of the full CCD excluded)" % (n_sample, t1 - t0, t2 - t1),
+            "optics_photons_per_s": n_sample / (t1 - t0), "sensor_photons_per_s": n_sample / (t2 - t1)}
+
+
+def run_reference(args):
+    """--impl reference: the CPU arm.  The reference itself (imSim over GalSim/batoid C++) cannot be
+    installed offline (no wheels for galsim/batoid/lsst.* in /opt/wheelhouse), so
+    this times the oracle restatement of its path with every host thread."""
+    rank, world, _ = dist_info()
+    if rank != 0:
+        return 0
+    from oracle import oracle as orc
+
+    threads = orc.max_threads()
+    n = args.ref_sample
+    vals = []
+    for _ in range(args.warmup):
+        cpu_baseline(min(n, 200000), threads)
+    for k in range(args.steps):
+        vals.append(cpu_baseline(n, threads, seed=k))
+    v = float(np.mean([c["value"] for c in vals]))
+    ms = n / v * 1e3
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(n, note="bounded sample per step on host cores"),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": vals[-1]["sample"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(pool, note=""):
+    return {"workload": "C2-pooled: single e2v CCD R22_S11 4096x4004, SiliconSensor lsst_e2v_50_4 brighter-fatter "
+                        "(strength 1, boundaries recomputed every step = photon batch) + tree rings, bright-star "
+                        "dominated pool (1000 stars, 5 mag range, sigma 1.5 px), RubinDiffractionOptics + "
+                        "FocusDepth + Refraction, r band",
+            "photons_per_step": pool, "detector": "R22_S11 (+7 neighbours for N>1, one per rank)",
+            "l2_policy": "inputs larger than L2 (each SoA array %d MB)" % (pool * 8 // 2**20), "note": note}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pool", type=int, default=POOL)
+    ap.add_argument("--ref-sample", type=int, default=2_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    import helpers
+    from imsim_b200 import OpticsContext, _abi, launch_count
+    from imsim_b200.photon_pooling import DevicePhotons, PhotonPool, PinnedPhotons
+    from imsim_b200.sensor import Image, SiliconSensor
+    from imsim_b200.synthetic import gpu_tracer, make_detector_setup, synthetic_photons
+
+    rank, world, local = dist_info()
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    W, K, P = max(args.warmup, 3), args.steps, args.pool
+
+    # ---- per-rank detector set-up (what telescope_loader / batoid_wcs hand to the ops) ----
+    det_name = DETECTORS[rank % len(DETECTORS)]
+    stream = torch.cuda.current_stream()
+    ctx = OpticsContext(device=local, stream=stream)
+    su = make_detector_setup(gpu_tracer(ctx), det_name, rot_tel_pos=np.radians(60.0))
+    ctx.set_telescope(su.telescope)
+    ctx.set_wcs(su.img_wcs, su.icrf_to_field)
+    ctx.set_detector(su.detector)
+    ctx.set_diffraction(helpers.default_diffraction())
+    cfg, dat, tr, abs_tab = sensor_inputs()
+    sensor = SiliconSensor(config=cfg, vertex_data=dat, nrecalc=0, strength=1.0, rng=1234 + rank,
+                           treering_func=tr[1], treering_center=tr[0], absorption_table=abs_tab, context=ctx)
+    image = Image(np.zeros((su.detector.ny, su.detector.nx), np.float32), 0, 0)
+    pool = PhotonPool(ctx, sensor, exptime=30.0, focus_depth=0.0, index_ratio=3.9, seed=99 + rank)
+
+    # ---- synthetic pool: generated once on the host, resident in HBM before timing ----
+    hx, hy, hwl, hflux = synthetic_photons(P, su.detector.nx, su.detector.ny, seed=rank, kind="stars")
+    pinned = PinnedPhotons(P)
+    pinned.x[:], pinned.y[:], pinned.wavelength[:], pinned.flux[:] = hx, hy, hwl, hflux
+    src = DevicePhotons(P, device=dev)
+    src.upload(pinned)
+    torch.cuda.synchronize()
+    work = [DevicePhotons(P, device=dev) for _ in range(2)]
+
+    def refill(dp):
+        for f in ("x", "y", "wavelength", "flux"):
+            getattr(dp, f).copy_(getattr(src, f))
+
+    # first call binds + initialises the image state (untimed set-up, once per image)
+    refill(work[0])
+    pool.process(work[0], image, resume=False, recalc=False)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps -------------------------------------------------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for i in range(W):
+        refill(work[i % 2])
+        pool.process(work[i % 2], image, resume=True, recalc=True)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = launch_count()
+    step_ms = []
+    t_region0 = time.perf_counter()
+    for i in range(K):
+        dp = work[i % 2]
+        refill(dp)  # untimed input restore (the ops work in place); events bracket only the path
+        ev[i][0].record()
+        pool.ctx.sample_time_pupil(dp.time, dp.pupil_u, dp.pupil_v, pool.t0, pool.exptime, pool.r_inner,
+                                   pool.r_outer, pool.seed, pool.offset)
+        pool.opt.photon_offset = pool.offset
+        kev[i][0].record()
+        ctx.rubin_optics(dp.x, dp.y, dp.dxdz, dp.dydz, dp.flux, dp.wavelength, dp.pupil_u, dp.pupil_v, dp.time,
+                         options=pool.opt, want_stats=False)
+        kev[i][1].record()
+        dp._has.update(pupil_u=True, pupil_v=True, time=True, dxdz=True, dydz=True)
+        pool.offset += P
+        sensor.accumulate(dp, image, resume=True, recalc=True, sync_image=False, want_stats=False)
+        ev[i][1].record()
+    barrier()
+    launches = launch_count() - l0
+    clk = clocks.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    trace_ms = [a.elapsed_time(b) for a, b in kev]
+    total_ms = float(np.sum(step_ms))
+    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    total_ms_max = float(tt.item())
+    value = world * P * K / (total_ms_max * 1e-3)
+
+    # ---- end-to-end steps: host pinned -> H2D -> path -> D2H(image + deposited flux) ----
+    e2e_K = max(2, min(K, 4))
+    barrier()
+    e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(e2e_K)]
+    h2d = d2h = 0
+    for i in range(e2e_K + 1):  # one warm-up pass
+        dp = work[i % 2]
+        if i > 0:
+            e_ev[i - 1][0].record()
+        h2d = dp.upload(pinned)
+        pool.process(dp, image, resume=True, recalc=True, sample=True, want_stats=True)
+        sensor.read_image(image)
+        d2h = image.array.nbytes + 8 + 56
+        if i > 0:
+            e_ev[i - 1][1].record()
+    barrier()
+    e_ms = float(np.sum([a.elapsed_time(b) for a, b in e_ev]))
+    et = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    e2e_value = world * P * e2e_K / (float(et.item()) * 1e-3)
+
+    # ---- roofline of the dominant kernel + CPU baseline (rank 0 only) -------------------
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        fp64_peak = ctx.fma_peak(True)
+        fp32_peak = ctx.fma_peak(False)
+        tr_ms = float(np.mean(trace_ms))
+        ach_gbs = ALG_BYTES_TRACE * P / (tr_ms * 1e-3) / 1e9
+        ach_tf = ALG_FLOP_TRACE * P / (tr_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(P),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_K},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"kernel": "k_rubin_optics", "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": tr_ms, "share_of_step": tr_ms * K / total_ms,
+                         "note": "kernel is FP64-pipe bound, see roofline_fp64"},
+            "roofline_fp64": {"kernel": "k_rubin_optics", "bound": "fp64 fma pipe", "achieved": ach_tf,
+                              "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+                              "flop_per_photon_algorithmic": ALG_FLOP_TRACE,
+                              "peak_source": "b2_fma_peak measured in this run", "fp32_peak": fp32_peak},
+            "breakdown_ms": {"step": total_ms / K, "trace": tr_ms, "sampler+accumulate+boundary_update":
+                             total_ms / K - tr_ms},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_sample, 1)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,149 @@
+"""Per-detector device context: telescope + WCS pair + detector geometry +
+diffraction set-up uploaded once, then any number of photon-op calls.
+
+Wraps ``b2_ctx`` of include/imsim_b200.h.  PyTorch only supplies the stream and
+device buffers; all arithmetic is in csrc/*.cu.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _abi, _lib
+from .detector import DetectorGeometry
+from .telescope import Telescope
+from .wcs import TanSipWCS
+
+
+def _stream_handle(stream) -> Optional[int]:
+    if stream is None:
+        return None
+    if hasattr(stream, "cuda_stream"):  # torch.cuda.Stream
+        return int(stream.cuda_stream)
+    return int(stream)
+
+
+class OpticsContext:
+    def __init__(self, device: int = 0, stream=None):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.device = int(device)
+        _lib.check(self._lib.b2_ctx_create(self.device, _stream_handle(stream), C.byref(self._h)))
+        self.telescope = None
+        self._keep = []
+
+    # -- uploads ----------------------------------------------------------
+    def set_stream(self, stream):
+        _lib.check(self._lib.b2_ctx_set_stream(self._h, _stream_handle(stream)))
+
+    def set_telescope(self, tel):
+        """``tel``: a :class:`Telescope` or an already flattened ``(B2Telescope, extras)``."""
+        pod, extras = tel.flatten() if isinstance(tel, Telescope) else tel
+        _lib.check(self._lib.b2_telescope_upload(self._h, C.byref(pod)))
+        for i, e in enumerate(extras or []):
+            if e is None:
+                continue
+            kind, arr = e
+            arr = np.ascontiguousarray(arr, dtype=np.float64)
+            _lib.check(self._lib.b2_telescope_set_extra(self._h, i, kind, arr.ctypes.data, arr.size))
+        self.telescope = tel
+
+    def set_wcs(self, img_wcs, icrf_to_field):
+        a = img_wcs.to_pod() if isinstance(img_wcs, TanSipWCS) else img_wcs
+        b = icrf_to_field.to_pod() if isinstance(icrf_to_field, TanSipWCS) else icrf_to_field
+        _lib.check(self._lib.b2_wcs_upload(self._h, C.byref(a), C.byref(b)))
+
+    def set_detector(self, det):
+        d = det.to_pod() if isinstance(det, DetectorGeometry) else det
+        _lib.check(self._lib.b2_detector_upload(self._h, C.byref(d)))
+
+    def set_diffraction(self, cfg: Optional[_abi.B2Diffraction]):
+        if cfg is None:
+            cfg = _abi.B2Diffraction()
+        _lib.check(self._lib.b2_diffraction_config(self._h, C.byref(cfg)))
+
+    def synchronize(self):
+        _lib.check(self._lib.b2_ctx_synchronize(self._h))
+
+    def fma_peak(self, fp64=True) -> float:
+        """Measured non-tensor FMA ceiling in TFLOP/s (roofline denominator of the trace kernel)."""
+        out = C.c_double(0.0)
+        _lib.check(self._lib.b2_fma_peak(self._h, int(bool(fp64)), C.byref(out)))
+        return out.value
+
+    # -- photon ops ---------------------------------------------------------
+    def xy_to_v(self, x, y, out=None):
+        where = _lib.where_of(x)
+        n = x.shape[0]
+        if out is None:
+            out = tuple(_empty_like(x) for _ in range(3))
+        _lib.check(self._lib.b2_xy_to_v(self._h, n, _lib.ptr(x), _lib.ptr(y), _lib.ptr(out[0]), _lib.ptr(out[1]),
+                                        _lib.ptr(out[2]), where))
+        return out
+
+    def v_to_xy(self, vx, vy, vz, out=None):
+        where = _lib.where_of(vx)
+        n = vx.shape[0]
+        if out is None:
+            out = tuple(_empty_like(vx) for _ in range(2))
+        _lib.check(self._lib.b2_v_to_xy(self._h, n, _lib.ptr(vx), _lib.ptr(vy), _lib.ptr(vz), _lib.ptr(out[0]),
+                                        _lib.ptr(out[1]), where))
+        return out
+
+    def trace_rays(self, x, y, z, vx, vy, vz, t, wavelength_m, vignetted, failed):
+        """In-place ``batoid.Optic.trace`` of rays given in the stop surface's frame."""
+        where = _lib.where_of(x)
+        _lib.check(self._lib.b2_trace_rays(self._h, x.shape[0], _lib.ptr(x), _lib.ptr(y), _lib.ptr(z), _lib.ptr(vx),
+                                           _lib.ptr(vy), _lib.ptr(vz), _lib.ptr(t), _lib.ptr(wavelength_m),
+                                           _lib.ptr(vignetted, np.uint8), _lib.ptr(failed, np.uint8), where))
+
+    def rubin_optics(self, x, y, dxdz, dydz, flux, wavelength, pupil_u, pupil_v, time, gauss=None, time_out=None,
+                     options: Optional[_abi.B2OpticsOptions] = None, want_stats=True):
+        where = _lib.where_of(x)
+        opt = options if options is not None else _abi.B2OpticsOptions()
+        stats = _abi.B2OpticsStats() if want_stats else None
+        _lib.check(self._lib.b2_rubin_optics(
+            self._h, x.shape[0], _lib.ptr(x), _lib.ptr(y), _lib.ptr(dxdz), _lib.ptr(dydz), _lib.ptr(flux),
+            _lib.ptr(wavelength), _lib.ptr(pupil_u), _lib.ptr(pupil_v), _lib.ptr(time), _lib.ptr(gauss),
+            _lib.ptr(time_out), C.byref(opt), where, C.byref(stats) if want_stats else None))
+        return stats
+
+    def rubin_diffraction(self, x, y, wavelength, pupil_u, pupil_v, time, gauss=None,
+                          options: Optional[_abi.B2OpticsOptions] = None):
+        where = _lib.where_of(x)
+        opt = options if options is not None else _abi.B2OpticsOptions()
+        _lib.check(self._lib.b2_rubin_diffraction(
+            self._h, x.shape[0], _lib.ptr(x), _lib.ptr(y), _lib.ptr(wavelength), _lib.ptr(pupil_u),
+            _lib.ptr(pupil_v), _lib.ptr(time), _lib.ptr(gauss), C.byref(opt), where))
+
+    def sample_time_pupil(self, time, pupil_u, pupil_v, t0, exptime, r_inner, r_outer, seed, photon_offset=0):
+        ref = time if time is not None else pupil_u
+        where = _lib.where_of(ref)
+        _lib.check(self._lib.b2_sample_time_pupil(self._h, ref.shape[0], _lib.ptr(time), _lib.ptr(pupil_u),
+                                                  _lib.ptr(pupil_v), t0, exptime, r_inner, r_outer, seed,
+                                                  photon_offset, where))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            self._lib.b2_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _empty_like(a):
+    if _lib._is_torch(a):
+        import torch
+
+        return torch.empty_like(a)
+    return np.empty_like(a)

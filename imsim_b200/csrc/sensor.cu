@@ -1,0 +1,1044 @@
+// sensor.cu -- silicon sensor kernels (sm_100a): conversion depth, diffusion,
+// tree-ring + brighter-fatter distorted pixel polygons, charge deposition,
+// boundary updates at the nrecalc cadence, pixel areas.
+//
+// Replaces galsim.SiliconSensor.accumulate / calculate_pixel_areas as called from
+// imsim/photon_pooling.py:195-225, imsim/stamp.py:562-572, imsim/flat.py:220-264.
+//
+// Device layout (per bound image of nx x ny pixels, nv vertices per pixel edge):
+//   H  float2 [(ny+1)][nx][nv+2]      bottom edge of pixel (x,y): BL corner, nv points, BR corner,
+//                                     in the owning pixel's frame (y ~ 0); corners live here only
+//   V  float2 [ny][(nx+1)][nv]        left edge of pixel (x,y), bottom -> top (x ~ 0)
+//   inner/outer double4 [ny][nx]      bounding boxes used for the fast accept / reject
+//   delta double [ny][nx]             charge deposited since the last boundary update
+//   target T [ny][nx]                 the image (float32 or float64)
+// A pixel's polygon is 3 contiguous segments: H[y][x][0..nv+2), H[y+1][x][0..nv+2)
+// and V[y][x][0..2nv) (its own left edge followed by the right neighbour's).
+#include "b2_common.cuh"
+
+#define PI_D 3.14159265358979323846
+#define B2_MAX_NV 32
+
+struct DevSensor {
+    int nv, nx9, ny9, qdist;
+    int xmin, ymin, nx, ny;
+    int ntr, nabs, tr_spline, pad;
+    double diff_step, pixel_size, thickness;
+    double trc[2];
+    double tr_max;
+    const double *tr_r, *tr_f, *tr_y2;
+    const double *abs_w, *abs_l;
+    const float2 *KH, *KV;
+    float2 *H, *V;
+    double *inner, *outer;
+    double* delta;
+    void* target;
+    int dtype_bytes, pad2;
+    double frac[B2_MAX_NV];  // (tan(theta_k)+1)/2, k = 0..nv-1, double (GalSim _emptypoly)
+};
+
+struct b2_sensor {
+    b2_ctx* ctx = nullptr;
+    B2SensorConfig cfg;
+    DevSensor d;
+    std::vector<void*> owned;        // tables
+    std::vector<void*> image_owned;  // per-image state
+    bool bound = false, initialized = false;
+    double accum_flux = 0.0;
+    uint8_t* changed = nullptr;
+    unsigned long long* dstats = nullptr;  // device counters
+    double* dadded = nullptr;
+    Scratch cum;  // cumulative flux scratch
+};
+
+enum { ST_POLY = 0, ST_NEIGH = 1, ST_NOTFOUND = 2, ST_B9 = 3, ST_DROP = 4, ST_N = 8 };
+
+// ------------------------------------------------------------------ device helpers
+__device__ __forceinline__ size_t Hidx(const DevSensor& s, int x, int y) {
+    return ((size_t)y * s.nx + x) * (s.nv + 2);
+}
+__device__ __forceinline__ size_t Vidx(const DevSensor& s, int x, int y) {
+    return ((size_t)y * (s.nx + 1) + x) * s.nv;
+}
+
+__device__ __forceinline__ int table_index(int n, const double* __restrict__ x, double a) {
+    if (a <= __ldg(x)) return 1;
+    if (a >= __ldg(x + n - 1)) return n - 1;
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(x + mid) <= a) lo = mid; else hi = mid;
+    }
+    return hi;
+}
+
+// GalSim Table.cpp linear / spline interpolation; explicit _rn ops: no FMA contraction,
+// so the values match the host (non-FMA) evaluation bit for bit
+__device__ __forceinline__ double table_linear(int n, const double* __restrict__ x, const double* __restrict__ f, double a) {
+    a = fmin(fmax(a, __ldg(x)), __ldg(x + n - 1));
+    int i = table_index(n, x, a);
+    double xi = __ldg(x + i), xm = __ldg(x + i - 1);
+    double ax = __ddiv_rn(__dsub_rn(xi, a), __dsub_rn(xi, xm));
+    double bx = __dsub_rn(1.0, ax);
+    return __dadd_rn(__dmul_rn(__ldg(f + i), bx), __dmul_rn(__ldg(f + i - 1), ax));
+}
+
+__device__ __forceinline__ double table_spline(int n, const double* __restrict__ x, const double* __restrict__ f,
+                                               const double* __restrict__ y2, double a) {
+    int i = table_index(n, x, a);
+    double xi = __ldg(x + i), xm = __ldg(x + i - 1);
+    double h = __dsub_rn(xi, xm);
+    double aa = __dsub_rn(xi, a);
+    double bb = __dsub_rn(h, aa);
+    double t1 = __dadd_rn(__dmul_rn(aa, __ldg(f + i - 1)), __dmul_rn(bb, __ldg(f + i)));
+    double t2 = __dadd_rn(__dmul_rn(__dadd_rn(aa, h), __ldg(y2 + i - 1)), __dmul_rn(__dadd_rn(bb, h), __ldg(y2 + i)));
+    double t3 = __dmul_rn(__dmul_rn(__dmul_rn(1. / 6., aa), bb), t2);
+    return __ddiv_rn(__dsub_rn(t1, t3), h);
+}
+
+// walk the polygon of pixel (ax, ay) counter-clockwise starting at the BL corner and
+// call f(n_is, px, py, ex, ey) with the stored point (pixel frame) and the undistorted one
+template <typename F>
+__device__ __forceinline__ void walk_polygon(const DevSensor& s, int ax, int ay, F&& f) {
+    const int nv = s.nv;
+    const float2* hb = s.H + Hidx(s, ax, ay);
+    const float2* ht = s.H + Hidx(s, ax, ay + 1);
+    const float2* vl = s.V + Vidx(s, ax, ay);
+    const float2* vr = vl + nv;
+    // bottom edge: BL corner, nv points, BR corner (all in this pixel's frame)
+    {
+        float2 p = hb[0];
+        f((double)p.x, (double)p.y, 0.0, 0.0);
+    }
+    for (int k = 0; k < nv; ++k) {
+        float2 p = hb[k + 1];
+        f((double)p.x, (double)p.y, s.frac[k], 0.0);
+    }
+    {
+        float2 p = hb[nv + 1];
+        f((double)p.x, (double)p.y, 1.0, 0.0);
+    }
+    for (int k = 0; k < nv; ++k) {
+        float2 p = vr[k];
+        f((double)p.x + 1.0, (double)p.y, 1.0, s.frac[k]);
+    }
+    {
+        float2 p = ht[nv + 1];
+        f((double)p.x, (double)p.y + 1.0, 1.0, 1.0);
+    }
+    for (int k = nv - 1; k >= 0; --k) {
+        float2 p = ht[k + 1];
+        f((double)p.x, (double)p.y + 1.0, s.frac[k], 1.0);
+    }
+    {
+        float2 p = ht[0];
+        f((double)p.x, (double)p.y + 1.0, 0.0, 1.0);
+    }
+    for (int k = nv - 1; k >= 0; --k) {
+        float2 p = vl[k];
+        f((double)p.x, (double)p.y, 0.0, s.frac[k]);
+    }
+}
+
+// Silicon::insidePixel.  ix, iy: image coordinates.  Returns inside; sets *off_edge like GalSim.
+__device__ __forceinline__ bool inside_pixel(const DevSensor& s, int ix, int iy, double x, double y, double zconv,
+                                             bool* off_edge, unsigned& npoly) {
+    int ax = ix - s.xmin, ay = iy - s.ymin;
+    if (ax < 0 || ax >= s.nx || ay < 0 || ay >= s.ny) {
+        if (off_edge) *off_edge = true;
+        return false;
+    }
+    size_t k = ((size_t)ay * s.nx + ax) * 4;
+    const double4 in = *reinterpret_cast<const double4*>(s.inner + k);  // xmin xmax ymin ymax
+    bool inside;
+    if (x >= in.x && x <= in.y && y >= in.z && y <= in.w) {
+        inside = true;
+    } else {
+        const double4 out = *reinterpret_cast<const double4*>(s.outer + k);
+        if (!(x >= out.x && x <= out.y && y >= out.z && y <= out.w)) {
+            inside = false;
+        } else {
+            const double zfactor = tanh(zconv / 12.0);
+            // Polygon::contains crossing test over consecutive vertices
+            bool in_poly = false;
+            double x1 = 0.0, y1 = 0.0, xf = 0.0, yf = 0.0;
+            bool first = true;
+            auto edge = [&](double xa, double ya, double xb, double yb) {
+                if (y > fmin(ya, yb)) {
+                    if (y <= fmax(ya, yb)) {
+                        if (x <= fmax(xa, xb)) {
+                            double xinters = 0.0;
+                            bool have = (ya != yb);
+                            if (have) xinters = __dadd_rn(__ddiv_rn(__dmul_rn(__dsub_rn(y, ya), __dsub_rn(xb, xa)), __dsub_rn(yb, ya)), xa);
+                            // GalSim keeps the previous xinters when ya == yb; with y > min and
+                            // y <= max that case is impossible (min == max), so it is never read
+                            if ((xa == xb) || (x <= xinters)) in_poly = !in_poly;
+                        }
+                    }
+                }
+            };
+            walk_polygon(s, ax, ay, [&](double px, double py, double ex, double ey) {
+                double qx = __dadd_rn(ex, __dmul_rn(__dsub_rn(px, ex), zfactor));
+                double qy = __dadd_rn(ey, __dmul_rn(__dsub_rn(py, ey), zfactor));
+                if (first) {
+                    xf = qx; yf = qy;
+                    first = false;
+                } else {
+                    edge(x1, y1, qx, qy);
+                }
+                x1 = qx; y1 = qy;
+            });
+            edge(x1, y1, xf, yf);
+            inside = in_poly;
+            npoly++;
+        }
+    }
+    if (!inside && off_edge) {
+        *off_edge = false;
+        if (ax == 0 && x < in.x) *off_edge = true;
+        if (ax == s.nx - 1 && x > in.y) *off_edge = true;
+        if (ay == 0 && y < in.z) *off_edge = true;
+        if (ay == s.ny - 1 && y > in.w) *off_edge = true;
+    }
+    return inside;
+}
+
+__constant__ int c_xoff[9] = {0, 1, 1, 0, -1, -1, -1, 0, 1};
+__constant__ int c_yoff[9] = {0, 0, 1, 1, 1, 0, -1, -1, -1};
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned v) {
+    return (unsigned long long)__reduce_add_sync(0xffffffffu, v);
+}
+
+// ------------------------------------------------------------------ accumulate
+// Silicon::accumulate over photons [i1, i2)
+__global__ void __launch_bounds__(256)
+k_accumulate(const __grid_constant__ DevSensor s, int64_t i1, int64_t i2, int64_t ntot,
+             const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ pdxdz,
+             const double* __restrict__ pdydz, const double* __restrict__ pwl, const double* __restrict__ pflux,
+             const double* __restrict__ rand4, uint64_t seed, uint64_t offset, unsigned long long* __restrict__ stats,
+             double* __restrict__ added) {
+    int64_t i = i1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = i < i2;
+    unsigned npoly = 0, nneigh = 0, nnf = 0, nb9 = 0, ndrop = 0;
+    double my_added = 0.0;
+    if (active) {
+        double g1, g2, unf, udep;
+        if (rand4) {
+            g1 = rand4[i];
+            g2 = rand4[ntot + i];
+            unf = rand4[2 * ntot + i];
+            udep = rand4[3 * ntot + i];
+        } else {
+            uint32_t r[4], q[4];
+            philox4(seed, offset + (uint64_t)i, 3u, r);
+            philox4(seed, offset + (uint64_t)i, 4u, q);
+            double u1 = u01(r[0], r[1]), u2 = u01(r[2], r[3]);
+            double sn, cs;
+            sincospi(2.0 * u2, &sn, &cs);
+            double rad = sqrt(-2.0 * log(u1));
+            g1 = rad * cs;
+            g2 = rad * sn;
+            unf = u01(q[0], q[1]);
+            udep = u01(q[2], q[3]);
+        }
+        const double T = s.thickness;
+        const double invPixelSize = 1. / s.pixel_size;
+        const double diffStep_pixel_z = s.diff_step / (T * s.pixel_size);
+        double x0 = px[i], y0 = py[i];
+        // calculateConversionDepth
+        double dz;
+        double a = 0.0, b = 0.0;
+        if (pdxdz) {
+            a = pdxdz[i];
+            b = pdydz[i];
+        }
+        if (pwl) {
+            double abs_length = table_linear(s.nabs, s.abs_w, s.abs_l, pwl[i]);
+            double si_length = __dmul_rn(-abs_length, log(__dsub_rn(1.0, udep)));
+            if (pdxdz) {
+                double nrm = sqrt(__dadd_rn(__dadd_rn(1.0, __dmul_rn(a, a)), __dmul_rn(b, b)));
+                dz = fmin(T - 1.0, __ddiv_rn(si_length, nrm));
+            } else {
+                dz = si_length;
+            }
+        } else {
+            dz = 1.0;
+        }
+        if (pdxdz) {
+            double dz_pixel = __dmul_rn(dz, invPixelSize);
+            x0 = __dadd_rn(x0, __dmul_rn(a, dz_pixel));
+            y0 = __dadd_rn(y0, __dmul_rn(b, dz_pixel));
+        }
+        double zconv = __dsub_rn(T, dz);
+        if (zconv < 0.0) {
+            ndrop = 1;
+        } else {
+            if (s.diff_step != 0.) {
+                double diffStep = fmax(0.0, __dmul_rn(diffStep_pixel_z, sqrt(__dmul_rn(zconv, T))));
+                x0 = __dadd_rn(x0, __dmul_rn(diffStep, g1));
+                y0 = __dadd_rn(y0, __dmul_rn(diffStep, g2));
+            }
+            int ix = (int)floor(x0 + 0.5);
+            int iy = (int)floor(y0 + 0.5);
+            double x = __dadd_rn(__dsub_rn(x0, (double)ix), 0.5);
+            double y = __dadd_rn(__dsub_rn(y0, (double)iy), 0.5);
+            if (fabs(x) < 1e-9 || fabs(x - 1.0) < 1e-9 || fabs(y) < 1e-9 || fabs(y - 1.0) < 1e-9) nb9 = 1;
+            bool off_edge = false;
+            bool found = inside_pixel(s, ix, iy, x, y, zconv, &off_edge, npoly);
+            bool drop = (!found && off_edge);
+            if (!drop) {
+                int step = 0;
+                if (!found) {
+                    nneigh = 1;
+                    if ((x > y) && (x > 1.0 - y)) step = 1;
+                    else if ((x > y) && (x < 1.0 - y)) step = 7;
+                    else if ((x < y) && (x > 1.0 - y)) step = 3;
+                    else step = 5;
+                    int nn = step;
+                    for (int m = 1; m < 9; ++m) {
+                        int ix_off = ix + c_xoff[nn], iy_off = iy + c_yoff[nn];
+                        double x_off = x - c_xoff[nn], y_off = y - c_yoff[nn];
+                        if (inside_pixel(s, ix_off, iy_off, x_off, y_off, zconv, nullptr, npoly)) {
+                            ix = ix_off;
+                            iy = iy_off;
+                            found = true;
+                            break;
+                        }
+                        nn = ((nn - 1) + step) % 8 + 1;
+                    }
+                }
+                if (!found) {
+                    nnf = 1;
+                    int nn = (unf > 0.5) ? 0 : step;
+                    ix += c_xoff[nn];
+                    iy += c_yoff[nn];
+                }
+                int ax = ix - s.xmin, ay = iy - s.ymin;
+                if (ax >= 0 && ax < s.nx && ay >= 0 && ay < s.ny) {
+                    double flux = pflux[i];
+                    atomicAdd(&s.delta[(size_t)ay * s.nx + ax], flux);
+                    my_added = flux;
+                }
+            }
+        }
+    }
+    // warp-aggregated statistics
+    unsigned long long w0 = warp_sum(npoly), w1 = warp_sum(nneigh), w2 = warp_sum(nnf), w3 = warp_sum(nb9),
+                       w4 = warp_sum(ndrop);
+    double wa = my_added;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wa += __shfl_xor_sync(0xffffffffu, wa, o);
+    if ((threadIdx.x & 31) == 0) {
+        if (w0) atomicAdd(&stats[ST_POLY], w0);
+        if (w1) atomicAdd(&stats[ST_NEIGH], w1);
+        if (w2) atomicAdd(&stats[ST_NOTFOUND], w2);
+        if (w3) atomicAdd(&stats[ST_B9], w3);
+        if (w4) atomicAdd(&stats[ST_DROP], w4);
+        if (wa != 0.0) atomicAdd(added, wa);
+    }
+}
+
+// galsim.Sensor.accumulate = PhotonArray.addTo
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_plain_accumulate(const __grid_constant__ DevSensor s, int64_t n, const double* __restrict__ px,
+                   const double* __restrict__ py, const double* __restrict__ pflux, double* __restrict__ added) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double my = 0.0;
+    if (i < n) {
+        int ax = (int)floor(px[i] + 0.5) - s.xmin;
+        int ay = (int)floor(py[i] + 0.5) - s.ymin;
+        if (ax >= 0 && ax < s.nx && ay >= 0 && ay < s.ny) {
+            double f = pflux[i];
+            atomicAdd(&s.delta[(size_t)ay * s.nx + ax], f);
+            my = f;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my += __shfl_xor_sync(0xffffffffu, my, o);
+    if ((threadIdx.x & 31) == 0 && my != 0.0) atomicAdd(added, my);
+}
+
+// ------------------------------------------------------------------ boundaries
+__device__ __forceinline__ void treering_point(const DevSensor& s, float2& pt, int i, int j, int ocx, int ocy) {
+    double tx = (double)i + (double)pt.x - s.trc[0] + (double)ocx;
+    double ty = (double)j + (double)pt.y - s.trc[1] + (double)ocy;
+    double r = sqrt(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)));
+    if (r > 0 && r < s.tr_max) {
+        double shift = s.tr_spline ? table_spline(s.ntr, s.tr_r, s.tr_f, s.tr_y2, r) : table_linear(s.ntr, s.tr_r, s.tr_f, r);
+        double dx = __ddiv_rn(__dmul_rn(shift, tx), r);
+        double dy = __ddiv_rn(__dmul_rn(shift, ty), r);
+        pt.x = (float)((double)pt.x + dx);
+        pt.y = (float)((double)pt.y + dy);
+    }
+}
+
+// undistorted boundaries + tree rings: one thread per (x, y) slot, x in [0,nx], y in [0,ny]
+__global__ void __launch_bounds__(256)
+k_init_boundaries(const __grid_constant__ DevSensor s, int ocx, int ocy) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x > s.nx) return;
+    const int nv = s.nv;
+    const bool tr = s.ntr > 2;
+    if (x < s.nx) {
+        float2* h = s.H + Hidx(s, x, y);
+        for (int k = 0; k <= nv + 1; ++k) {
+            float2 p;
+            p.x = (k == 0) ? 0.f : (k == nv + 1 ? 1.f : (float)s.frac[k - 1]);
+            p.y = 0.f;
+            if (tr) treering_point(s, p, s.xmin + x, s.ymin + y, ocx, ocy);
+            h[k] = p;
+        }
+    }
+    if (y < s.ny) {
+        float2* v = s.V + Vidx(s, x, y);
+        for (int k = 0; k < nv; ++k) {
+            float2 p;
+            p.x = 0.f;
+            p.y = (float)s.frac[k];
+            if (tr) treering_point(s, p, s.xmin + x, s.ymin + y, ocx, ocy);
+            v[k] = p;
+        }
+    }
+}
+
+// Silicon::updatePixelDistortions: charge-weighted sum of the per-electron kernels.
+// One thread per (x, y) slot; CHARGE_T: the delta image (double) or the target image.
+template <typename CT>
+__global__ void __launch_bounds__(128)
+k_update_distortions(const __grid_constant__ DevSensor s, const CT* __restrict__ charge, uint8_t* __restrict__ changed) {
+    extern __shared__ float2 sK[];  // KH then KV
+    const int nv = s.nv;
+    const int nKH = s.nx9 * s.ny9 * (nv + 2), nKV = s.nx9 * s.ny9 * nv;
+    for (int k = threadIdx.x; k < nKH; k += blockDim.x) sK[k] = s.KH[k];
+    for (int k = threadIdx.x; k < nKV; k += blockDim.x) sK[nKH + k] = s.KV[k];
+    __syncthreads();
+    const float2* KH = sK;
+    const float2* KV = sK + nKH;
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x > s.nx) return;
+    const int q = s.qdist, nx = s.nx, ny = s.ny;
+    const int cxk = (s.nx9 - 1) / 2, cyk = (s.ny9 - 1) / 2;
+    // horizontal slot
+    if (x < nx) {
+        int i1 = max(x - q, 0), i2 = min(x + q, nx - 1);
+        int j1 = max(y - (q + 1), 0), j2 = min(y + q, ny - 1);
+        int kmax = nv + 1;
+        float2* h = s.H + Hidx(s, x, y);
+        bool change = false;
+        for (int j = j1; j <= j2; ++j)
+            for (int i = i1; i <= i2; ++i) {
+                double c = (double)charge[(size_t)j * nx + i];
+                if (c == 0.0) continue;
+                change = true;
+                const float2* kh = KH + ((y - j + cyk) * s.nx9 + (x - i + cxk)) * (nv + 2);
+                for (int k = 0; k <= kmax; ++k) {
+                    float2 p = h[k];
+                    float2 d = kh[k];
+                    p.x = (float)__dadd_rn((double)p.x, __dmul_rn((double)d.x, c));
+                    p.y = (float)__dadd_rn((double)p.y, __dmul_rn((double)d.y, c));
+                    h[k] = p;
+                }
+            }
+        if (change) {
+            for (int dy = -1; dy <= 0; ++dy) {
+                int pyy = y + dy;
+                if (pyy >= 0 && pyy < ny) changed[(size_t)pyy * nx + x] = 1;
+            }
+        }
+    }
+    if (y < ny) {
+        int i1 = max(x - (q + 1), 0), i2 = min(x + q, nx - 1);
+        int j1 = max(y - q, 0), j2 = min(y + q, ny - 1);
+        float2* v = s.V + Vidx(s, x, y);
+        bool change = false;
+        for (int j = j1; j <= j2; ++j)
+            for (int i = i1; i <= i2; ++i) {
+                double c = (double)charge[(size_t)j * nx + i];
+                if (c == 0.0) continue;
+                change = true;
+                const float2* kv = KV + ((y - j + cyk) * s.nx9 + (x - i + cxk)) * nv;
+                for (int k = 0; k < nv; ++k) {
+                    float2 p = v[k];
+                    float2 d = kv[k];
+                    p.x = (float)__dadd_rn((double)p.x, __dmul_rn((double)d.x, c));
+                    p.y = (float)__dadd_rn((double)p.y, __dmul_rn((double)d.y, c));
+                    v[k] = p;
+                }
+            }
+        if (change) {
+            for (int dx = -1; dx <= 0; ++dx) {
+                int pxx = x + dx;
+                if (pxx >= 0 && pxx < nx) changed[(size_t)y * nx + pxx] = 1;
+            }
+        }
+    }
+}
+
+// Silicon::updatePixelBounds for every pixel (all = 1) or the flagged ones
+__global__ void __launch_bounds__(256)
+k_update_bounds(const __grid_constant__ DevSensor s, const uint8_t* __restrict__ changed, int all) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= s.nx) return;
+    size_t pix = (size_t)y * s.nx + x;
+    if (!all && !changed[pix]) return;
+    double oxmin = INFINITY, oxmax = -INFINITY, oymin = INFINITY, oymax = -INFINITY;
+    walk_polygon(s, x, y, [&](double px, double py, double, double) {
+        oxmin = fmin(oxmin, px);
+        oxmax = fmax(oxmax, px);
+        oymin = fmin(oymin, py);
+        oymax = fmax(oymax, py);
+    });
+    double cx = (oxmin + oxmax) / 2.0, cy = (oymin + oymax) / 2.0;
+    double ixmin = oxmin, ixmax = oxmax, iymin = oymin, iymax = oymax;
+    walk_polygon(s, x, y, [&](double px, double py, double, double) {
+        if (px - cx >= fabs(py - cy) && px < ixmax) ixmax = px;
+        if (px - cx <= -fabs(py - cy) && px > ixmin) ixmin = px;
+        if (py - cy >= fabs(px - cx) && py < iymax) iymax = py;
+        if (py - cy <= -fabs(px - cx) && py > iymin) iymin = py;
+    });
+    *reinterpret_cast<double4*>(s.outer + pix * 4) = make_double4(oxmin, oxmax, oymin, oymax);
+    *reinterpret_cast<double4*>(s.inner + pix * 4) = make_double4(ixmin, ixmax, iymin, iymax);
+}
+
+// target (+/-)= delta, optionally clearing delta (Silicon::addDelta / subtractDelta / update)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_add_delta(T* __restrict__ target, double* __restrict__ delta, size_t n, double sign, int clear) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double d = delta[i];
+    if (d != 0.0) {
+        target[i] = (T)__dadd_rn((double)target[i], __dmul_rn(sign, d));
+        if (clear) delta[i] = 0.0;
+    }
+}
+
+// Silicon::pixelArea (shoelace) for every pixel
+__global__ void __launch_bounds__(256)
+k_pixel_areas(const __grid_constant__ DevSensor s, double* __restrict__ areas) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= s.nx) return;
+    // GalSim starts at polygon vertex 0 (mid left edge); the sum is cyclic, but to keep the
+    // same rounding sequence start there as well: collect the walk (which starts at BL) and rotate
+    const int nv = s.nv;
+    const int npoly = 4 * nv + 4;
+    const int start = npoly - nv / 2;  // walk index of polygon vertex 0
+    double area = 0.0;
+    // two passes over the walk: [start, npoly) then [0, start], chaining consecutive vertices
+    double x1 = 0, y1 = 0, fx = 0, fy = 0;
+    bool have = false;
+    for (int pass = 0; pass < 2; ++pass) {
+        int idx = 0;
+        walk_polygon(s, x, y, [&](double px, double py, double, double) {
+            bool use = (pass == 0) ? (idx >= start) : (idx < start);
+            if (use) {
+                if (!have) {
+                    fx = px; fy = py;
+                    have = true;
+                } else {
+                    area = __dadd_rn(area, __dmul_rn(x1, py));
+                    area = __dsub_rn(area, __dmul_rn(px, y1));
+                }
+                x1 = px; y1 = py;
+            }
+            idx++;
+        });
+    }
+    area = __dadd_rn(area, __dmul_rn(x1, fy));
+    area = __dsub_rn(area, __dmul_rn(fx, y1));
+    areas[(size_t)y * s.nx + x] = fabs(area) / 2.0;
+}
+
+// inclusive prefix sum of flux, single block (chunk boundaries for nrecalc > 0); the
+// running total is carried in double like the reference's host loop
+__global__ void k_find_chunks(const double* __restrict__ flux, int64_t n, double accum0, double nrecalc,
+                              int64_t* __restrict__ bounds, int max_bounds, int* __restrict__ nb, double* accum_out) {
+    // serial scan by one thread per launch is too slow for large n; use a block-wide
+    // sequential-by-tile scan: 1024 threads, each tile of 1024 photons scanned in shared memory
+    __shared__ double tile[1024];
+    __shared__ double carry;
+    __shared__ int count;
+    if (threadIdx.x == 0) {
+        carry = accum0;
+        count = 0;
+    }
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += 1024) {
+        int64_t i = base + threadIdx.x;
+        tile[threadIdx.x] = (i < n) ? flux[i] : 0.0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // exact sequential semantics (order of additions = photon order)
+            double acc = carry;
+            int64_t lim = (n - base < 1024) ? (n - base) : 1024;
+            for (int k = 0; k < lim; ++k) {
+                acc += tile[k];
+                if (acc >= nrecalc) {
+                    if (count < max_bounds) bounds[count] = base + k + 1;
+                    count++;
+                    acc = 0.0;
+                }
+            }
+            carry = acc;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        *nb = count;
+        *accum_out = carry;
+    }
+}
+
+// ------------------------------------------------------------------ host side
+static inline dim3 grid2(int nxslots, int ny, int bs) { return dim3((nxslots + bs - 1) / bs, ny, 1); }
+
+template <typename T>
+static int dev_upload(b2_ctx* ctx, std::vector<void*>& owned, const T* src, size_t n, const T** out) {
+    void* p = nullptr;
+    B2_CUDA(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+    owned.push_back(p);
+    if (n) B2_CUDA(cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *out = (const T*)p;
+    return 0;
+}
+
+static void spline_y2_host(int n, const double* x, const double* f, std::vector<double>& y2) {
+    y2.assign(n, 0.0);
+    if (n < 3) return;
+    std::vector<double> cp(n, 0.0), dp(n, 0.0);
+    for (int i = 1; i < n - 1; ++i) {
+        double h0 = x[i] - x[i - 1], h1 = x[i + 1] - x[i];
+        double b = 2.0 * (h0 + h1);
+        double rhs = 6.0 * ((f[i + 1] - f[i]) / h1 - (f[i] - f[i - 1]) / h0);
+        double m = b - h0 * cp[i - 1];
+        cp[i] = h1 / m;
+        dp[i] = (rhs - h0 * dp[i - 1]) / m;
+    }
+    for (int i = n - 2; i >= 1; --i) y2[i] = dp[i] - cp[i] * y2[i + 1];
+}
+
+extern "C" int b2_sensor_create(b2_ctx* ctx, const B2SensorConfig* cfg, const double* vertex_data,
+                                const double* tr_r, const double* tr_f, const double* tr_y2, const double* abs_w,
+                                const double* abs_l, b2_sensor** out) {
+    B2_REQUIRE(ctx && cfg && vertex_data && out, "b2_sensor_create: null argument");
+    B2_REQUIRE(cfg->num_vertices >= 2 && cfg->num_vertices <= B2_MAX_NV && cfg->num_vertices % 2 == 0,
+               "b2_sensor_create: num_vertices must be even and <= 32");
+    B2_REQUIRE(cfg->nx >= 2 * cfg->qdist + 3 && cfg->ny >= 2 * cfg->qdist + 3,
+               "b2_sensor_create: vertex table smaller than 2*qdist+3");
+    B2_REQUIRE(!cfg->transpose, "b2_sensor_create: transpose=True is not supported yet");
+    B2_REQUIRE(cfg->n_treering <= 2 || (tr_r && tr_f), "b2_sensor_create: tree-ring table missing");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    b2_sensor* s = new b2_sensor();
+    s->ctx = ctx;
+    s->cfg = *cfg;
+    DevSensor& d = s->d;
+    memset(&d, 0, sizeof(d));
+    const int nv = d.nv = cfg->num_vertices;
+    d.nx9 = cfg->nx;
+    d.ny9 = cfg->ny;
+    d.qdist = cfg->qdist;
+    d.diff_step = cfg->diff_step;
+    d.pixel_size = cfg->pixel_size;
+    d.thickness = cfg->sensor_thickness;
+    d.trc[0] = cfg->treering_center[0];
+    d.trc[1] = cfg->treering_center[1];
+    // undistorted edge points (GalSim buildEmptyPoly)
+    {
+        double theta0 = -PI_D / 4.0, dtheta = PI_D / (2.0 * (nv + 1.0));
+        for (int k = 0; k < nv; ++k) d.frac[k] = (tan(theta0 + (k + 1.0) * dtheta) + 1.0) / 2.0;
+    }
+    // polygon order of the .dat file -> undistorted positions
+    const int npoly = 4 * nv + 4;
+    std::vector<double> ex(npoly), ey(npoly);
+    {
+        int n = 0;
+        for (int k = nv / 2 - 1; k >= 0; --k) { ex[n] = 0.0; ey[n] = d.frac[k]; n++; }
+        ex[n] = 0.0; ey[n] = 0.0; n++;
+        for (int k = 0; k < nv; ++k) { ex[n] = d.frac[k]; ey[n] = 0.0; n++; }
+        ex[n] = 1.0; ey[n] = 0.0; n++;
+        for (int k = 0; k < nv; ++k) { ex[n] = 1.0; ey[n] = d.frac[k]; n++; }
+        ex[n] = 1.0; ey[n] = 1.0; n++;
+        for (int k = nv - 1; k >= 0; --k) { ex[n] = d.frac[k]; ey[n] = 1.0; n++; }
+        ex[n] = 0.0; ey[n] = 1.0; n++;
+        for (int k = nv - 1; k >= nv / 2; --k) { ex[n] = 0.0; ey[n] = d.frac[k]; n++; }
+    }
+    const int nx9 = cfg->nx, ny9 = cfg->ny;
+    std::vector<float2> KH((size_t)nx9 * ny9 * (nv + 2)), KV((size_t)nx9 * ny9 * nv);
+    for (int i = 0; i < nx9; ++i)
+        for (int j = 0; j < ny9; ++j)
+            for (int n = 0; n < npoly; ++n) {
+                const double* row = vertex_data + 5 * (((size_t)i * ny9 + j) * npoly + n);
+                double pxv = (row[3] - row[0]) / cfg->pixel_size + 0.5;
+                double pyv = (row[4] - row[1]) / cfg->pixel_size + 0.5;
+                float2 dd;
+                dd.x = (float)((pxv - ex[n]) / cfg->num_elec);
+                dd.y = (float)((pyv - ey[n]) / cfg->num_elec);
+                if (n >= nv / 2 && n <= nv / 2 + nv + 1) KH[((size_t)j * nx9 + i) * (nv + 2) + (n - nv / 2)] = dd;
+                else if (n < nv / 2) KV[((size_t)j * nx9 + i) * nv + (nv / 2 - 1 - n)] = dd;
+                else if (n >= 7 * nv / 2 + 4) KV[((size_t)j * nx9 + i) * nv + (nv - 1 - (n - (7 * nv / 2 + 4)))] = dd;
+            }
+    if (dev_upload(ctx, s->owned, KH.data(), KH.size(), &d.KH)) return 1;
+    if (dev_upload(ctx, s->owned, KV.data(), KV.size(), &d.KV)) return 1;
+    d.ntr = cfg->n_treering;
+    if (d.ntr > 2) {
+        if (dev_upload(ctx, s->owned, tr_r, (size_t)d.ntr, &d.tr_r)) return 1;
+        if (dev_upload(ctx, s->owned, tr_f, (size_t)d.ntr, &d.tr_f)) return 1;
+        d.tr_max = tr_r[d.ntr - 1];
+        if (tr_y2) {
+            if (dev_upload(ctx, s->owned, tr_y2, (size_t)d.ntr, &d.tr_y2)) return 1;
+            d.tr_spline = 1;
+        }
+    }
+    d.nabs = cfg->n_abs;
+    if (d.nabs > 0) {
+        B2_REQUIRE(abs_w && abs_l, "b2_sensor_create: absorption table missing");
+        if (dev_upload(ctx, s->owned, abs_w, (size_t)d.nabs, &d.abs_w)) return 1;
+        if (dev_upload(ctx, s->owned, abs_l, (size_t)d.nabs, &d.abs_l)) return 1;
+    }
+    void* p = nullptr;
+    B2_CUDA(cudaMalloc(&p, ST_N * sizeof(unsigned long long) + 64));
+    s->owned.push_back(p);
+    s->dstats = (unsigned long long*)p;
+    s->dadded = (double*)((char*)p + ST_N * sizeof(unsigned long long));
+    B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = s;
+    return 0;
+}
+
+static void free_list(std::vector<void*>& v) {
+    for (void* p : v) cudaFree(p);
+    v.clear();
+}
+
+extern "C" int b2_sensor_destroy(b2_sensor* s) {
+    if (!s) return 0;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    free_list(s->image_owned);
+    free_list(s->owned);
+    if (s->cum.ptr) cudaFree(s->cum.ptr);
+    delete s;
+    return 0;
+}
+
+extern "C" int b2_sensor_bind_image(b2_sensor* s, int32_t xmin, int32_t ymin, int32_t nx, int32_t ny,
+                                    int32_t dtype_bytes, const void* pixels, int where) {
+    B2_REQUIRE(s, "b2_sensor_bind_image: null sensor");
+    B2_REQUIRE(nx > 0 && ny > 0, "b2_sensor_bind_image: empty image");
+    B2_REQUIRE(dtype_bytes == 4 || dtype_bytes == 8, "b2_sensor_bind_image: image must be float32 or float64");
+    b2_ctx* ctx = s->ctx;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    DevSensor& d = s->d;
+    bool same = s->bound && d.nx == nx && d.ny == ny && d.dtype_bytes == dtype_bytes;
+    if (!same) {
+        B2_CUDA(cudaStreamSynchronize(ctx->stream));
+        free_list(s->image_owned);
+        const int nv = d.nv;
+        size_t nH = (size_t)(ny + 1) * nx * (nv + 2), nV = (size_t)ny * (nx + 1) * nv + nv;
+        size_t npix = (size_t)nx * ny;
+        void* p;
+        B2_CUDA(cudaMalloc(&p, nH * sizeof(float2))); s->image_owned.push_back(p); d.H = (float2*)p;
+        B2_CUDA(cudaMalloc(&p, nV * sizeof(float2))); s->image_owned.push_back(p); d.V = (float2*)p;
+        B2_CUDA(cudaMalloc(&p, npix * 4 * sizeof(double))); s->image_owned.push_back(p); d.inner = (double*)p;
+        B2_CUDA(cudaMalloc(&p, npix * 4 * sizeof(double))); s->image_owned.push_back(p); d.outer = (double*)p;
+        B2_CUDA(cudaMalloc(&p, npix * sizeof(double))); s->image_owned.push_back(p); d.delta = (double*)p;
+        B2_CUDA(cudaMalloc(&p, npix * dtype_bytes)); s->image_owned.push_back(p); d.target = p;
+        B2_CUDA(cudaMalloc(&p, npix)); s->image_owned.push_back(p); s->changed = (uint8_t*)p;
+    }
+    d.xmin = xmin; d.ymin = ymin; d.nx = nx; d.ny = ny; d.dtype_bytes = dtype_bytes;
+    size_t bytes = (size_t)nx * ny * dtype_bytes;
+    if (pixels)
+        B2_CUDA(cudaMemcpyAsync(d.target, pixels, bytes, where == B2_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+    else
+        B2_CUDA(cudaMemsetAsync(d.target, 0, bytes, ctx->stream));
+    B2_CUDA(cudaMemsetAsync(d.delta, 0, (size_t)nx * ny * sizeof(double), ctx->stream));
+    if (where == B2_HOST) B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    s->bound = true;
+    s->initialized = false;
+    s->accum_flux = 0.0;
+    return 0;
+}
+
+extern "C" int b2_sensor_read_image(b2_sensor* s, void* pixels, int where) {
+    B2_REQUIRE(s && s->bound && pixels, "b2_sensor_read_image: no image bound");
+    b2_ctx* ctx = s->ctx;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    size_t bytes = (size_t)s->d.nx * s->d.ny * s->d.dtype_bytes;
+    B2_CUDA(cudaMemcpyAsync(pixels, s->d.target, bytes, where == B2_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
+    if (where == B2_HOST) B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int launch_add_delta(b2_sensor* s, double sign, int clear) {
+    DevSensor& d = s->d;
+    size_t n = (size_t)d.nx * d.ny;
+    int nb = (int)((n + 255) / 256);
+    if (d.dtype_bytes == 4) k_add_delta<float><<<nb, 256, 0, s->ctx->stream>>>((float*)d.target, d.delta, n, sign, clear);
+    else k_add_delta<double><<<nb, 256, 0, s->ctx->stream>>>((double*)d.target, d.delta, n, sign, clear);
+    B2_CHECK_LAUNCH();
+    return 0;
+}
+
+// charge_from_target: distortions from the bound image (initialize) or from delta (update)
+static int launch_update_distortions(b2_sensor* s, bool from_target) {
+    DevSensor& d = s->d;
+    b2_ctx* ctx = s->ctx;
+    B2_CUDA(cudaMemsetAsync(s->changed, 0, (size_t)d.nx * d.ny, ctx->stream));
+    size_t smem = ((size_t)d.nx9 * d.ny9 * (2 * d.nv + 2)) * sizeof(float2);
+    dim3 g = grid2(d.nx + 1, d.ny + 1, 128);
+    if (!from_target) {
+        if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(k_update_distortions<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_update_distortions<double><<<g, 128, smem, ctx->stream>>>(d, d.delta, s->changed);
+    } else if (d.dtype_bytes == 4) {
+        if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(k_update_distortions<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_update_distortions<float><<<g, 128, smem, ctx->stream>>>(d, (const float*)d.target, s->changed);
+    } else {
+        if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(k_update_distortions<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_update_distortions<double><<<g, 128, smem, ctx->stream>>>(d, (const double*)d.target, s->changed);
+    }
+    B2_CHECK_LAUNCH();
+    return 0;
+}
+
+static int launch_bounds_update(b2_sensor* s, int all) {
+    DevSensor& d = s->d;
+    k_update_bounds<<<grid2(d.nx, d.ny, 256), 256, 0, s->ctx->stream>>>(d, s->changed, all);
+    B2_CHECK_LAUNCH();
+    return 0;
+}
+
+// Silicon::update
+static int sensor_update(b2_sensor* s) {
+    if (launch_update_distortions(s, false)) return 1;
+    if (launch_bounds_update(s, 0)) return 1;
+    if (launch_add_delta(s, 1.0, 1)) return 1;
+    return 0;
+}
+
+static int init_boundaries(b2_sensor* s, int ocx, int ocy) {
+    DevSensor& d = s->d;
+    k_init_boundaries<<<grid2(d.nx + 1, d.ny + 1, 256), 256, 0, s->ctx->stream>>>(d, ocx, ocy);
+    B2_CHECK_LAUNCH();
+    return 0;
+}
+
+// Silicon::initialize
+static int sensor_initialize(b2_sensor* s, int ocx, int ocy) {
+    DevSensor& d = s->d;
+    if (init_boundaries(s, ocx, ocy)) return 1;
+    if (launch_update_distortions(s, true)) return 1;
+    if (launch_bounds_update(s, 1)) return 1;
+    B2_CUDA(cudaMemsetAsync(d.delta, 0, (size_t)d.nx * d.ny * sizeof(double), s->ctx->stream));
+    s->accum_flux = 0.0;
+    s->initialized = true;
+    return 0;
+}
+
+extern "C" int b2_sensor_accumulate(b2_sensor* s, int64_t n, const double* x, const double* y, const double* dxdz,
+                                    const double* dydz, const double* wl, const double* flux, const double* rand4,
+                                    uint64_t seed, uint64_t offset, int32_t ocx, int32_t ocy, int32_t resume,
+                                    int32_t recalc, int where, B2AccumStats* stats) {
+    B2_REQUIRE(s && s->bound, "b2_sensor_accumulate: no image bound");
+    B2_REQUIRE(n == 0 || (x && y && flux), "b2_sensor_accumulate: null photon array");
+    B2_REQUIRE((dxdz == nullptr) == (dydz == nullptr), "b2_sensor_accumulate: dxdz and dydz go together");
+    B2_REQUIRE(!wl || s->d.nabs > 0, "b2_sensor_accumulate: wavelengths given but the sensor has no absorption table");
+    // galsim/sensor.py: resume=True needs the image of the previous call
+    B2_REQUIRE(!resume || s->initialized, "b2_sensor_accumulate: resume=True but there was no previous accumulate on this image");
+    b2_ctx* ctx = s->ctx;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    DevSensor& d = s->d;
+    cudaStream_t st = ctx->stream;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    B2_CUDA(cudaMemsetAsync(s->dstats, 0, ST_N * sizeof(unsigned long long) + 64, st));
+    uint64_t n_updates = 0;
+    if (!resume) {
+        if (sensor_initialize(s, ocx, ocy)) return 1;
+    } else {
+        if (launch_add_delta(s, -1.0, 0)) return 1;  // subtractDelta
+        if (recalc) {
+            if (sensor_update(s)) return 1;
+            s->accum_flux = 0.0;
+            n_updates++;
+        }
+    }
+    // stage host photons
+    const double *dx = x, *dy = y, *da = dxdz, *db = dydz, *dw = wl, *df = flux, *dr = rand4;
+    if (where == B2_HOST && n > 0) {
+        Stager sg{ctx};
+        size_t narr = 3 + (dxdz ? 2 : 0) + (wl ? 1 : 0) + (rand4 ? 4 : 0);
+        if (sg.init(narr * pad256(n * 8))) return 1;
+        double* t;
+        t = sg.take<double>(n); H2D(t, x, n); dx = t;
+        t = sg.take<double>(n); H2D(t, y, n); dy = t;
+        t = sg.take<double>(n); H2D(t, flux, n); df = t;
+        if (dxdz) {
+            t = sg.take<double>(n); H2D(t, dxdz, n); da = t;
+            t = sg.take<double>(n); H2D(t, dydz, n); db = t;
+        }
+        if (wl) { t = sg.take<double>(n); H2D(t, wl, n); dw = t; }
+        if (rand4) {
+            // keep the [4][n] layout contiguous
+            t = (double*)(sg.base + sg.off);
+            sg.off += pad256((size_t)4 * n * 8);
+            H2D(t, rand4, 4 * n);
+            dr = t;
+        }
+    }
+    // chunk boundaries (photon order) at the nrecalc cadence
+    std::vector<int64_t> bounds;
+    double nrecalc = s->cfg.nrecalc;
+    if (nrecalc > 0 && n > 0) {
+        const int max_bounds = 1 << 20;
+        if (b2_scratch_reserve(ctx, s->cum, (size_t)max_bounds * 8 + 64)) return 1;
+        int64_t* dbounds = (int64_t*)s->cum.ptr;
+        int* dnb = (int*)((char*)s->cum.ptr + (size_t)max_bounds * 8);
+        double* dacc = (double*)((char*)s->cum.ptr + (size_t)max_bounds * 8 + 8);
+        k_find_chunks<<<1, 1024, 0, st>>>(df, n, s->accum_flux, nrecalc, dbounds, max_bounds, dnb, dacc);
+        B2_CHECK_LAUNCH();
+        int nb = 0;
+        double acc = 0.0;
+        B2_CUDA(cudaMemcpyAsync(&nb, dnb, sizeof(int), cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaMemcpyAsync(&acc, dacc, sizeof(double), cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaStreamSynchronize(st));
+        B2_REQUIRE(nb <= max_bounds, "b2_sensor_accumulate: more than 2^20 boundary updates in one call");
+        bounds.resize(nb);
+        if (nb) {
+            B2_CUDA(cudaMemcpyAsync(bounds.data(), dbounds, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
+            B2_CUDA(cudaStreamSynchronize(st));
+        }
+        s->accum_flux = acc;
+    }
+    int64_t i1 = 0;
+    size_t ib = 0;
+    while (i1 < n) {
+        int64_t i2 = (ib < bounds.size()) ? bounds[ib] : n;
+        bool hit = ib < bounds.size();
+        int64_t cnt = i2 - i1;
+        if (cnt > 0) {
+            k_accumulate<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d, i1, i2, n, dx, dy, da, db, dw, df, dr, seed,
+                                                                         offset, s->dstats, s->dadded);
+            B2_CHECK_LAUNCH();
+        }
+        if (hit) {
+            if (sensor_update(s)) return 1;
+            n_updates++;
+            ib++;
+        }
+        i1 = i2;
+    }
+    if (launch_add_delta(s, 1.0, 0)) return 1;  // addDelta (pending charge stays in delta)
+    if (stats || where == B2_HOST) {
+        unsigned long long h[ST_N];
+        double added = 0.0;
+        B2_CUDA(cudaMemcpyAsync(h, s->dstats, sizeof(h), cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaMemcpyAsync(&added, s->dadded, sizeof(double), cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaStreamSynchronize(st));
+        if (stats) {
+            stats->added_flux = added;
+            stats->n_polygon_tests = h[ST_POLY];
+            stats->n_neighbor_search = h[ST_NEIGH];
+            stats->n_not_found = h[ST_NOTFOUND];
+            stats->n_boundary_1e9 = h[ST_B9];
+            stats->n_dropped_bottom = h[ST_DROP];
+            stats->n_updates = n_updates;
+        }
+    }
+    return 0;
+}
+
+extern "C" int b2_plain_accumulate(b2_sensor* s, int64_t n, const double* x, const double* y, const double* flux,
+                                   int where, double* added_flux) {
+    B2_REQUIRE(s && s->bound, "b2_plain_accumulate: no image bound");
+    b2_ctx* ctx = s->ctx;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevSensor& d = s->d;
+    B2_CUDA(cudaMemsetAsync(s->dadded, 0, sizeof(double), st));
+    B2_CUDA(cudaMemsetAsync(d.delta, 0, (size_t)d.nx * d.ny * sizeof(double), st));
+    s->initialized = false;
+    if (n > 0) {
+        const double *dx = x, *dy = y, *df = flux;
+        if (where == B2_HOST) {
+            Stager sg{ctx};
+            if (sg.init(3 * pad256(n * 8))) return 1;
+            double* t;
+            t = sg.take<double>(n); H2D(t, x, n); dx = t;
+            t = sg.take<double>(n); H2D(t, y, n); dy = t;
+            t = sg.take<double>(n); H2D(t, flux, n); df = t;
+        }
+        if (d.dtype_bytes == 4) k_plain_accumulate<float><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, n, dx, dy, df, s->dadded);
+        else k_plain_accumulate<double><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, n, dx, dy, df, s->dadded);
+        B2_CHECK_LAUNCH();
+        if (launch_add_delta(s, 1.0, 1)) return 1;
+    }
+    if (added_flux) {
+        B2_CUDA(cudaMemcpyAsync(added_flux, s->dadded, sizeof(double), cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+extern "C" int b2_sensor_pixel_areas(b2_sensor* s, int32_t ocx, int32_t ocy, int32_t use_flux, double* areas, int where) {
+    B2_REQUIRE(s && s->bound && areas, "b2_sensor_pixel_areas: no image bound");
+    b2_ctx* ctx = s->ctx;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    DevSensor& d = s->d;
+    if (init_boundaries(s, ocx, ocy)) return 1;
+    if (use_flux && launch_update_distortions(s, true)) return 1;
+    s->initialized = false;
+    size_t npix = (size_t)d.nx * d.ny;
+    double* dareas = areas;
+    if (where == B2_HOST) {
+        if (b2_scratch_reserve(ctx, ctx->scratch, npix * 8)) return 1;
+        dareas = (double*)ctx->scratch.ptr;
+    }
+    k_pixel_areas<<<grid2(d.nx, d.ny, 256), 256, 0, ctx->stream>>>(d, dareas);
+    B2_CHECK_LAUNCH();
+    if (where == B2_HOST) {
+        B2_CUDA(cudaMemcpyAsync(areas, dareas, npix * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+__global__ void k_get_pixel(const __grid_constant__ DevSensor s, int ax, int ay, double* poly, double* bounds) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int nv = s.nv, npoly = 4 * nv + 4;
+    const int start = npoly - nv / 2;  // walk index of polygon vertex 0
+    int idx = 0;
+    walk_polygon(s, ax, ay, [&](double px, double py, double, double) {
+        int n = (idx - start + npoly) % npoly;
+        poly[2 * n] = px;
+        poly[2 * n + 1] = py;
+        idx++;
+    });
+    size_t k = ((size_t)ay * s.nx + ax) * 4;
+    for (int j = 0; j < 4; ++j) {
+        bounds[j] = s.inner[k + j];
+        bounds[4 + j] = s.outer[k + j];
+    }
+}
+
+extern "C" int b2_sensor_get_pixel(b2_sensor* s, int32_t ix, int32_t iy, double* poly, double* bounds) {
+    B2_REQUIRE(s && s->bound, "b2_sensor_get_pixel: no image bound");
+    b2_ctx* ctx = s->ctx;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    DevSensor& d = s->d;
+    int ax = ix - d.xmin, ay = iy - d.ymin;
+    B2_REQUIRE(ax >= 0 && ax < d.nx && ay >= 0 && ay < d.ny, "b2_sensor_get_pixel: pixel outside the image");
+    int npoly = 4 * d.nv + 4;
+    if (b2_scratch_reserve(ctx, ctx->scratch, (size_t)(2 * npoly + 8) * 8)) return 1;
+    double* dp = (double*)ctx->scratch.ptr;
+    k_get_pixel<<<1, 32, 0, ctx->stream>>>(d, ax, ay, dp, dp + 2 * npoly);
+    B2_CHECK_LAUNCH();
+    B2_CUDA(cudaMemcpyAsync(poly, dp, (size_t)2 * npoly * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    B2_CUDA(cudaMemcpyAsync(bounds, dp + 2 * npoly, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}

@@ -1,0 +1,283 @@
+"""Photon pooling on the B200 (mirror of imsim/photon_pooling.py).
+
+Two layers:
+
+* the batching algebra of ``LSST_PhotonPoolingImageBuilder`` --
+  ``partition_objects``, ``make_batches``, ``make_photon_batches``,
+  ``make_photon_subbatches``, ``merge_photon_arrays``, ``accumulate_photons``
+  (imsim/photon_pooling.py:177-386) -- reproduced exactly as static methods of
+  the same class name, so the reference's tests/test_photon_pooling.py reads the
+  same against this module;
+
+* :class:`PhotonPool`, the device-resident replacement for the hot loop of
+  ``buildImage`` (imsim/photon_pooling.py:141-160): the merged pool is copied to
+  HBM once, TimeSampler + PupilAnnulusSampler, RubinDiffractionOptics, FocusDepth,
+  Refraction run as two kernels on it and ``SiliconSensor.accumulate`` consumes the
+  device arrays directly; the image stays on the device until a checkpoint or the
+  end of ``buildImage`` asks for it.
+"""
+from __future__ import annotations
+
+import dataclasses
+import itertools
+import warnings
+from dataclasses import dataclass
+from enum import Enum, auto
+from typing import List, Optional
+
+import numpy as np
+
+from . import _abi, _lib
+from .photon_array import PhotonArray
+
+
+class ProcessingMode(Enum):
+    """imsim/stamp.py:17-20"""
+    FFT = auto()
+    PHOT = auto()
+    FAINT = auto()
+
+
+@dataclass
+class ObjectInfo:
+    """Per-object cache of the rendering decision (imsim/stamp.py:23-34)."""
+    index: int
+    phot_flux: float
+    mode: ProcessingMode
+
+
+def _uniform_deviate(config, base, logger):
+    """``galsim.UniformDeviate(GetRNG(config, base, logger, "LSST_Silicon"))`` when GalSim is
+    present; otherwise a numpy generator seeded from ``base['rng']`` / ``base['random_seed']``."""
+    try:
+        import galsim  # noqa: PLC0415
+
+        rng = galsim.config.GetRNG(config, base, logger, "LSST_Silicon")
+        return galsim.UniformDeviate(rng)
+    except ImportError:
+        rng = (base or {}).get('rng', None)
+        if callable(rng):
+            return rng
+        gen = np.random.default_rng((base or {}).get('random_seed', None) if rng is None else rng)
+        return gen.random
+
+
+class LSST_PhotonPoolingImageBuilder:
+    """Pools photons from all objects in ``nbatch`` batches; photons from faint
+    objects only appear in one of the batches randomly.  Static batching helpers
+    of the reference builder (the GalSim-facing ``setup`` / ``buildImage`` live in
+    galsim_plugin.py because they need the GalSim config machinery)."""
+
+    @staticmethod
+    def merge_photon_arrays(stamps):
+        """Merge the photon arrays of a list of stamps into one PhotonArray
+        (imsim/photon_pooling.py:177-192)."""
+        n_tot = sum(len(stamp.photons) for stamp in stamps)
+        cls = type(stamps[0].photons) if stamps else PhotonArray
+        merged = cls(n_tot)
+        start = 0
+        for stamp in stamps:
+            merged.copyFrom(stamp.photons, slice(start, start + stamp.photons.size()))
+            start += len(stamp.photons)
+        return merged
+
+    @staticmethod
+    def accumulate_photons(photons, image, sensor, resume=False, recalc=True):
+        """Accumulate a photon array onto a sensor (imsim/photon_pooling.py:195-225)."""
+        from .sensor import Image, SiliconSensor  # noqa: PLC0415
+
+        if image.dtype in (np.float32, np.float64):
+            if isinstance(sensor, SiliconSensor):
+                sensor.accumulate(photons, image, resume=resume, recalc=recalc)
+            else:
+                sensor.accumulate(photons, image, resume=resume)
+        else:
+            # integer image: work in a temporary float64 image; resume / recalc do nothing
+            if resume:
+                warnings.warn("Sensor is not a float. Using temporary ImageD and ignoring resume = True for "
+                              "photon accumulation.")
+            if not recalc:
+                warnings.warn("Sensor is not a float. Using temporary ImageD and ignoring recalc = False for "
+                              "photon accumulation.")
+            b = image.bounds
+            im1 = Image(np.zeros(image.array.shape, dtype=np.float64), int(b.xmin), int(b.ymin))
+            sensor.accumulate(photons, im1)
+            image.array[:, :] += im1.array.astype(image.array.dtype)
+
+    @staticmethod
+    def make_batches(objects, nbatch: int):
+        """Yield ``nbatch`` batches of objects; early batches get the remainder
+        (imsim/photon_pooling.py:227-247)."""
+        base_per_batch = len(objects) // nbatch
+        per_batch_remainder = len(objects) % nbatch
+        o_iter = iter(objects)
+        for i in range(nbatch):
+            nobj_per_batch = base_per_batch + 1 if i < per_batch_remainder else base_per_batch
+            yield [obj for _, obj in zip(range(nobj_per_batch), o_iter)]
+
+    @staticmethod
+    def make_photon_batches(config, base, logger, phot_objects: List[ObjectInfo],
+                            faint_objects: List[ObjectInfo], nbatch: int):
+        """``nbatch`` copies of the bright objects at ``(f(i+1))//nbatch - (f i)//nbatch`` of
+        their flux, faint objects whole into a random batch (imsim/photon_pooling.py:278-313)."""
+        if not phot_objects and not faint_objects:
+            return []
+        batches = [
+            [dataclasses.replace(obj, phot_flux=(obj.phot_flux * (i + 1)) // nbatch - (obj.phot_flux * i) // nbatch)
+             for obj in phot_objects]
+            for i in range(nbatch)]
+        ud = _uniform_deviate(config, base, logger)
+        for obj in faint_objects:
+            batch_index = int(ud() * nbatch)
+            batches[batch_index].append(obj)
+        return batches
+
+    @staticmethod
+    def make_photon_subbatches(batch, nsubbatch):
+        """Split a batch into ``nsubbatch`` nearly equal consecutive sub-batches
+        (imsim/photon_pooling.py:315-331)."""
+        nobj = len(batch)
+        nobj_per_subbatch, nobj_extra = divmod(nobj, nsubbatch)
+        section_sizes = nobj_extra * [nobj_per_subbatch + 1] + (nsubbatch - nobj_extra) * [nobj_per_subbatch]
+        section_indices = [0] + list(itertools.accumulate(section_sizes))
+        return [batch[section_indices[i]:section_indices[i + 1]] for i in range(nsubbatch)]
+
+    @staticmethod
+    def stamp_bounds(stamp, full_image_bounds):
+        """Overlap of a stamp with the full image or None (imsim/photon_pooling.py:333-353)."""
+        if stamp is None:
+            return None
+        bounds = stamp.bounds & full_image_bounds
+        if not bounds.isDefined():
+            return None
+        return bounds
+
+    @staticmethod
+    def partition_objects(objects, nbatch):
+        """Split objects into (FFT, PHOT, FAINT); PHOT objects with fewer photons than
+        batches are drawn like FAINT ones (imsim/photon_pooling.py:355-386)."""
+        objects_by_mode = {ProcessingMode.FFT: [], ProcessingMode.PHOT: [], ProcessingMode.FAINT: []}
+        for obj in objects:
+            if obj.phot_flux < nbatch and obj.mode == ProcessingMode.PHOT:
+                mode = ProcessingMode.FAINT
+            else:
+                mode = obj.mode
+            objects_by_mode[mode].append(obj)
+        return (objects_by_mode[ProcessingMode.FFT], objects_by_mode[ProcessingMode.PHOT],
+                objects_by_mode[ProcessingMode.FAINT])
+
+
+# ---------------------------------------------------------------------------
+# device-resident pool
+# ---------------------------------------------------------------------------
+class DevicePhotons:
+    """SoA photon pool in HBM (float64 CUDA tensors); same field names and
+    predicates as ``PhotonArray`` so the sensor and the ops take either."""
+
+    FIELDS = ("x", "y", "flux", "dxdz", "dydz", "wavelength", "pupil_u", "pupil_v", "time")
+
+    def __init__(self, n: int, device="cuda:0", fields=FIELDS):
+        import torch  # device buffers only
+
+        self.n = int(n)
+        self.device = torch.device(device)
+        # one allocation, 9 rows: every field is a contiguous 8n-byte row
+        self.buf = torch.empty((len(self.FIELDS), self.n), dtype=torch.float64, device=self.device)
+        self._has = {f: (f in fields) for f in self.FIELDS}
+        for k, f in enumerate(self.FIELDS):
+            setattr(self, f, self.buf[k])
+
+    def size(self):
+        return self.n
+
+    def __len__(self):
+        return self.n
+
+    def hasAllocatedAngles(self):
+        return self._has["dxdz"] and self._has["dydz"]
+
+    def hasAllocatedWavelengths(self):
+        return self._has["wavelength"]
+
+    def hasAllocatedPupil(self):
+        return self._has["pupil_u"] and self._has["pupil_v"]
+
+    def hasAllocatedTimes(self):
+        return self._has["time"]
+
+    def upload(self, host: "PinnedPhotons", fields=("x", "y", "flux", "wavelength"), stream=None):
+        """Host (pinned) -> device copy of the given fields; returns bytes copied."""
+        import torch
+
+        nbytes = 0
+        with torch.cuda.stream(stream) if stream is not None else _nullctx():
+            for f in fields:
+                k = self.FIELDS.index(f)
+                self.buf[k].copy_(host.buf[k, : self.n], non_blocking=True)
+                nbytes += self.n * 8
+        return nbytes
+
+
+class PinnedPhotons:
+    """Pinned host staging buffer with the DevicePhotons layout (numpy views)."""
+
+    def __init__(self, n: int):
+        import torch
+
+        self.n = int(n)
+        self.buf = torch.empty((len(DevicePhotons.FIELDS), self.n), dtype=torch.float64).pin_memory()
+        self.np = self.buf.numpy()
+        for k, f in enumerate(DevicePhotons.FIELDS):
+            setattr(self, f, self.np[k])
+
+
+class _nullctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+class PhotonPool:
+    """Device-resident replacement of the pooled hot loop
+    (imsim/photon_pooling.py:141-160) for one detector.
+
+    ``process(photons)`` applies, on HBM-resident arrays,
+      TimeSampler + PupilAnnulusSampler      (config/imsim-config.yaml:281-289)
+      RubinDiffractionOptics + FocusDepth + Refraction   (:297-320, one kernel)
+      SiliconSensor.accumulate(resume, recalc)           (photon_pooling.py:159)
+    PhotonDCR is not part of the kernel chain yet (it needs the per-object sky
+    position; in the pooled pipeline the reference applies it with a stale one,
+    SURVEY.md Q2) -- callers that need it apply it to x, y before ``process``.
+    """
+
+    def __init__(self, ctx, sensor, exptime=30.0, t0=0.0, r_inner=2.558, r_outer=4.18, focus_depth=0.0,
+                 index_ratio=3.9, seed=1):
+        self.ctx = ctx
+        self.sensor = sensor
+        self.exptime, self.t0 = float(exptime), float(t0)
+        self.r_inner, self.r_outer = float(r_inner), float(r_outer)
+        self.seed = int(seed)
+        self.offset = 0
+        self.opt = _abi.B2OpticsOptions()
+        self.opt.do_focus_depth = int(focus_depth != 0.0)
+        self.opt.focus_depth = float(focus_depth)
+        self.opt.do_refraction = 1
+        self.opt.index_ratio = float(index_ratio)
+        self.opt.seed = self.seed
+
+    def process(self, dp: DevicePhotons, image, resume: bool, recalc: bool, sample=True, want_stats=False):
+        """Run the chain on a device pool and accumulate onto the sensor's bound image."""
+        if sample:
+            self.ctx.sample_time_pupil(dp.time, dp.pupil_u, dp.pupil_v, self.t0, self.exptime, self.r_inner,
+                                       self.r_outer, self.seed, self.offset)
+            dp._has.update(pupil_u=True, pupil_v=True, time=True)
+        self.opt.photon_offset = self.offset
+        stats = self.ctx.rubin_optics(dp.x, dp.y, dp.dxdz, dp.dydz, dp.flux, dp.wavelength, dp.pupil_u, dp.pupil_v,
+                                      dp.time, options=self.opt, want_stats=want_stats)
+        dp._has.update(dxdz=True, dydz=True)
+        self.offset += dp.n
+        added = self.sensor.accumulate(dp, image, resume=resume, recalc=recalc, sync_image=False,
+                                       want_stats=want_stats)
+        return added, stats

@@ -219,6 +219,10 @@ int b2_ctx_create(int device, void* cuda_stream, b2_ctx** out);
 int b2_ctx_destroy(b2_ctx* ctx);
 int b2_ctx_set_stream(b2_ctx* ctx, void* cuda_stream);
 int b2_ctx_synchronize(b2_ctx* ctx);
+/* measurement aid: register-resident FMA chains on every SM; returns the achieved
+   non-tensor FMA rate (fp64 != 0: double, else float) in TFLOP/s.  The roofline
+   denominator of the compute-bound trace kernel (MEASURED_PEAKS.json has none). */
+int b2_fma_peak(b2_ctx* ctx, int32_t fp64, double* tflops);
 
 /* replaces: base['det_telescope'] (imsim/telescope_loader.py:463) as consumed by
    imsim/photon_ops.py:108-123 */

@@ -272,3 +272,11 @@ def plain_accumulate(image, x, y, flux, xmin=0, ymin=0):
     return lib().orc_plain_accumulate(C.c_int(xmin), C.c_int(ymin), C.c_int(nx), C.c_int(ny),
                                       C.c_int(image.dtype.itemsize), image.ctypes.data_as(C.c_void_p),
                                       C.c_int64(x.size), px, py, pf)
+
+
+def set_threads(n: int):
+    lib().orc_set_threads(C.c_int(int(n)))
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())

@@ -23,6 +23,9 @@
 #include <string.h>
 
 #include "../include/imsim_b200.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define PI 3.14159265358979323846
 
@@ -36,7 +39,9 @@ typedef struct {
     int npoly; /* 4*nv+4 */
     double* emptypoly; /* npoly*2 */
     /* per-electron distortion kernels of the nx9*ny9 neighbourhood:
-       KH[(ky*nx9+kx)*(nv+1)+k]: BL corner (k=0) + bottom-edge points of kernel pixel (kx,ky)
+       KH[(ky*nx9+kx)*(nv+2)+k]: bottom edge of kernel pixel (kx,ky): BL corner (k=0), nv
+                                 points, BR corner (k=nv+1) -- corners belong to the
+                                 horizontal arrays, one pair per pixel
        KV[(ky*nx9+kx)*nv+k]: left-edge points, bottom -> top */
     f2* KH;
     f2* KV;
@@ -49,8 +54,9 @@ typedef struct {
     int xmin, ymin, nx, ny, dtype_bytes;
     void* target; /* caller's pixel buffer, row-major ny*nx */
     double* delta;
-    /* boundary state: H[(y*(nx+1)+x)*(nv+1)+k], y in [0,ny], x in [0,nx];
-                       V[(y*(nx+1)+x)*nv+k],     y in [0,ny), x in [0,nx] */
+    /* boundary state: H[(y*nx+x)*(nv+2)+k],     y in [0,ny], x in [0,nx): bottom edge of pixel
+                                                 (x,y) with both its corners, pixel frame;
+                       V[(y*(nx+1)+x)*nv+k],     y in [0,ny), x in [0,nx]: left edge of pixel (x,y) */
     f2* H;
     f2* V;
     double* inner; /* nx*ny*4: xmin xmax ymin ymax */
@@ -146,7 +152,7 @@ OrcSensor* orc_sensor_create(const B2SensorConfig* cfg, const double* vertex_dat
     s->emptypoly = (double*)malloc(sizeof(double) * 2 * s->npoly);
     build_emptypoly(nv, s->emptypoly);
     int nx9 = cfg->nx, ny9 = cfg->ny;
-    s->KH = (f2*)calloc((size_t)nx9 * ny9 * (nv + 1), sizeof(f2));
+    s->KH = (f2*)calloc((size_t)nx9 * ny9 * (nv + 2), sizeof(f2));
     s->KV = (f2*)calloc((size_t)nx9 * ny9 * nv, sizeof(f2));
     /* .dat rows: pixel index x-major (i = index/(ny*npoly)), then j, then vertex n.
        Per-electron displacement of vertex n of neighbour pixel (i,j) caused by
@@ -161,9 +167,9 @@ OrcSensor* orc_sensor_create(const B2SensorConfig* cfg, const double* vertex_dat
                 f2 d;
                 d.x = (float)((px - s->emptypoly[2 * n]) / cfg->num_elec);
                 d.y = (float)((py - s->emptypoly[2 * n + 1]) / cfg->num_elec);
-                /* own bottom edge (+BL corner) and own left edge of each kernel pixel */
-                if (n >= nv / 2 && n <= nv / 2 + nv) {
-                    s->KH[((size_t)j * nx9 + i) * (nv + 1) + (n - nv / 2)] = d;
+                /* own bottom edge (with both corners) and own left edge of each kernel pixel */
+                if (n >= nv / 2 && n <= nv / 2 + nv + 1) {
+                    s->KH[((size_t)j * nx9 + i) * (nv + 2) + (n - nv / 2)] = d;
                 } else if (n < nv / 2) {
                     s->KV[((size_t)j * nx9 + i) * nv + (nv / 2 - 1 - n)] = d;
                 } else if (n >= 7 * nv / 2 + 4) {
@@ -222,7 +228,7 @@ static inline double tget(const OrcSensor* s, int x, int y) {
     return s->dtype_bytes == 4 ? (double)((float*)s->target)[k] : ((double*)s->target)[k];
 }
 
-static inline f2* Hp(const OrcSensor* s, int x, int y) { return s->H + ((size_t)y * (s->nx + 1) + x) * (s->nv + 1); }
+static inline f2* Hp(const OrcSensor* s, int x, int y) { return s->H + ((size_t)y * s->nx + x) * (s->nv + 2); }
 static inline f2* Vp(const OrcSensor* s, int x, int y) { return s->V + ((size_t)y * (s->nx + 1) + x) * s->nv; }
 
 /* polygon of pixel (x,y) (array indices) in polygon order, pixel-local coords */
@@ -232,14 +238,10 @@ static void pixel_poly(const OrcSensor* s, int x, int y, double* p) {
     const f2* vr = Vp(s, x + 1, y);
     const f2* hb = Hp(s, x, y);
     const f2* ht = Hp(s, x, y + 1);
-    const f2* cbr = Hp(s, x + 1, y);
-    const f2* ctr = Hp(s, x + 1, y + 1);
     for (int k = nv / 2 - 1; k >= 0; --k) { p[2 * n] = vl[k].x; p[2 * n + 1] = vl[k].y; n++; }
-    for (int k = 0; k <= nv; ++k) { p[2 * n] = hb[k].x; p[2 * n + 1] = hb[k].y; n++; }
-    p[2 * n] = (double)cbr[0].x + 1.0; p[2 * n + 1] = cbr[0].y; n++;
+    for (int k = 0; k <= nv + 1; ++k) { p[2 * n] = hb[k].x; p[2 * n + 1] = hb[k].y; n++; }
     for (int k = 0; k < nv; ++k) { p[2 * n] = (double)vr[k].x + 1.0; p[2 * n + 1] = vr[k].y; n++; }
-    p[2 * n] = (double)ctr[0].x + 1.0; p[2 * n + 1] = (double)ctr[0].y + 1.0; n++;
-    for (int k = nv; k >= 0; --k) { p[2 * n] = ht[k].x; p[2 * n + 1] = (double)ht[k].y + 1.0; n++; }
+    for (int k = nv + 1; k >= 0; --k) { p[2 * n] = ht[k].x; p[2 * n + 1] = (double)ht[k].y + 1.0; n++; }
     for (int k = nv - 1; k >= nv / 2; --k) { p[2 * n] = vl[k].x; p[2 * n + 1] = vl[k].y; n++; }
 }
 
@@ -286,7 +288,7 @@ static void treering_point(const OrcSensor* s, f2* pt, int i, int j, int ocx, in
 
 static void init_boundaries(OrcSensor* s, int ocx, int ocy) {
     int nx = s->nx, ny = s->ny, nv = s->nv;
-    size_t nH = (size_t)(ny + 1) * (nx + 1) * (nv + 1), nV = (size_t)ny * (nx + 1) * nv;
+    size_t nH = (size_t)(ny + 1) * nx * (nv + 2), nV = (size_t)ny * (nx + 1) * nv;
     if (!s->H) {
         s->H = (f2*)malloc(nH * sizeof(f2));
         s->V = (f2*)malloc((nV ? nV : 1) * sizeof(f2));
@@ -296,9 +298,12 @@ static void init_boundaries(OrcSensor* s, int ocx, int ocy) {
     }
     for (int y = 0; y <= ny; ++y)
         for (int x = 0; x <= nx; ++x) {
-            f2* h = Hp(s, x, y);
-            h[0].x = 0.f; h[0].y = 0.f;
-            for (int k = 0; k < nv; ++k) { h[k + 1].x = (float)edge_frac(nv, k); h[k + 1].y = 0.f; }
+            if (x < nx) {
+                f2* h = Hp(s, x, y);
+                h[0].x = 0.f; h[0].y = 0.f;
+                for (int k = 0; k < nv; ++k) { h[k + 1].x = (float)edge_frac(nv, k); h[k + 1].y = 0.f; }
+                h[nv + 1].x = 1.f; h[nv + 1].y = 0.f;
+            }
             if (y < ny) {
                 f2* v = Vp(s, x, y);
                 for (int k = 0; k < nv; ++k) { v[k].x = 0.f; v[k].y = (float)edge_frac(nv, k); }
@@ -307,10 +312,10 @@ static void init_boundaries(OrcSensor* s, int ocx, int ocy) {
     if (s->ntr > 2) {
         for (int y = 0; y <= ny; ++y)
             for (int x = 0; x <= nx; ++x) {
-                f2* h = Hp(s, x, y);
-                /* points past the last column exist only as the corner */
-                int kmax = (x < nx) ? nv : 0;
-                for (int k = 0; k <= kmax; ++k) treering_point(s, &h[k], s->xmin + x, s->ymin + y, ocx, ocy);
+                if (x < nx) {
+                    f2* h = Hp(s, x, y);
+                    for (int k = 0; k <= nv + 1; ++k) treering_point(s, &h[k], s->xmin + x, s->ymin + y, ocx, ocy);
+                }
                 if (y < ny) {
                     f2* v = Vp(s, x, y);
                     for (int k = 0; k < nv; ++k) treering_point(s, &v[k], s->xmin + x, s->ymin + y, ocx, ocy);
@@ -329,10 +334,10 @@ static void update_distortions(OrcSensor* s, const double* qd /* delta or NULL -
     /* horizontal rows */
 #pragma omp parallel for schedule(dynamic, 4)
     for (int y = 0; y <= ny; ++y)
-        for (int x = 0; x <= nx; ++x) {
+        for (int x = 0; x < nx; ++x) {
             int i1 = x - q < 0 ? 0 : x - q, i2 = x + q > nx - 1 ? nx - 1 : x + q;
             int j1 = y - (q + 1) < 0 ? 0 : y - (q + 1), j2 = y + q > ny - 1 ? ny - 1 : y + q;
-            int kmax = (x < nx) ? nv : 0;
+            int kmax = nv + 1;
             f2* h = Hp(s, x, y);
             int change = 0;
             for (int j = j1; j <= j2; ++j)
@@ -340,18 +345,17 @@ static void update_distortions(OrcSensor* s, const double* qd /* delta or NULL -
                     double charge = qd ? qd[(size_t)j * nx + i] : tget(s, i, j);
                     if (charge == 0.0) continue;
                     change = 1;
-                    const f2* kh = s->KH + ((size_t)(y - j + cyk) * nx9 + (x - i + cxk)) * (nv + 1);
+                    const f2* kh = s->KH + ((size_t)(y - j + cyk) * nx9 + (x - i + cxk)) * (nv + 2);
                     for (int k = 0; k <= kmax; ++k) {
                         h[k].x = (float)((double)h[k].x + (double)kh[k].x * charge);
                         h[k].y = (float)((double)h[k].y + (double)kh[k].y * charge);
                     }
                 }
             if (change) {
-                for (int dy = -1; dy <= 0; ++dy)
-                    for (int dx = -1; dx <= 0; ++dx) {
-                        int px = x + dx, py = y + dy;
-                        if (px >= 0 && px < nx && py >= 0 && py < ny) changed[(size_t)py * nx + px] = 1;
-                    }
+                for (int dy = -1; dy <= 0; ++dy) {
+                    int py = y + dy;
+                    if (py >= 0 && py < ny) changed[(size_t)py * nx + x] = 1;
+                }
             }
         }
     /* vertical columns */
@@ -492,6 +496,8 @@ static double accumulate_chunk(OrcSensor* s, int64_t i1, int64_t i2, const doubl
     const double* g2 = rand4 + n;
     const double* unf = rand4 + 2 * n;
     const double* udep = rand4 + 3 * n;
+    /* photons of one chunk are independent (GalSim's loop is "#pragma omp parallel for" too) */
+#pragma omp parallel for schedule(static) reduction(+ : added, npt, nns, nnf, nb9, ndrop)
     for (int64_t i = i1; i < i2; ++i) {
         double x0 = px[i], y0 = py[i];
         /* calculateConversionDepth */
@@ -558,6 +564,7 @@ static double accumulate_chunk(OrcSensor* s, int64_t i1, int64_t i2, const doubl
         int ax = ix - s->xmin, ay = iy - s->ymin;
         if (ax >= 0 && ax < s->nx && ay >= 0 && ay < s->ny) {
             double flux = pflux[i];
+#pragma omp atomic
             s->delta[(size_t)ay * s->nx + ax] += flux;
             added += flux;
         }
@@ -660,4 +667,18 @@ void orc_sensor_get_pixel(OrcSensor* s, int ix, int iy, double* poly, double* bo
     size_t k = ((size_t)ay * s->nx + ax) * 4;
     memcpy(bounds, s->inner + k, 4 * sizeof(double));
     memcpy(bounds + 4, s->outer + k, 4 * sizeof(double));
+}
+
+/* thread control for the CPU-baseline timings */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#endif
+}
+int orc_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
 }

@@ -1,0 +1,237 @@
+"""Parity of the CUDA optics path (through the C ABI) against the CPU oracle on
+identical inputs with injected random draws.
+
+Tolerances (BASELINE.json north_star): ray-traced positions, directions and
+times agree to 1e-10 relative in FP64 mode; vignetting flags identical.
+"""
+import numpy as np
+import pytest
+
+import helpers
+from imsim_b200 import _abi
+from imsim_b200.telescope import paraboloid_test_telescope, rubin_like
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def _ctx(setup=None, dif=None):
+    from imsim_b200 import OpticsContext
+
+    ctx = OpticsContext(device=0)
+    if setup is not None:
+        ctx.set_telescope(setup.telescope)
+        ctx.set_wcs(setup.img_wcs, setup.icrf_to_field)
+        ctx.set_detector(setup.detector)
+    ctx.set_diffraction(dif)
+    return ctx
+
+
+def _close(a, b, scale=None, rtol=RTOL):
+    a, b = np.asarray(a), np.asarray(b)
+    s = np.maximum(np.abs(b), 1e-300) if scale is None else scale
+    err = np.max(np.abs(a - b) / s)
+    assert err < rtol, "max relative error %.3e" % err
+    return err
+
+
+def test_xy_to_v_and_inverse_match_oracle():
+    from oracle import oracle as orc
+
+    su = helpers.oracle_setup()
+    ctx = _ctx(su)
+    rng = np.random.default_rng(3)
+    x = rng.uniform(0, 4096, 20000)
+    y = rng.uniform(0, 4004, 20000)
+    vx, vy, vz = ctx.xy_to_v(x, y)
+    ox, oy, oz = orc.xy_to_v(su.img_wcs.to_pod(), su.icrf_to_field.to_pod(), x, y)
+    # direction cosines: absolute 1e-12 on O(0.03) components is far below 1e-10 relative of the pixel position
+    np.testing.assert_allclose(vx, ox, rtol=0, atol=2e-14)
+    np.testing.assert_allclose(vy, oy, rtol=0, atol=2e-14)
+    np.testing.assert_allclose(vz, oz, rtol=1e-14)
+    # XyToV.inverse o XyToV = id (tests/test_photon_ops.py:429-446)
+    x2, y2 = ctx.v_to_xy(vx, vy, vz)
+    np.testing.assert_allclose(x2, x, rtol=0, atol=4e-7)  # 1e-10 relative of 4000 px
+    np.testing.assert_allclose(y2, y, rtol=0, atol=4e-7)
+    ox2, oy2 = orc.v_to_xy(su.img_wcs.to_pod(), su.icrf_to_field.to_pod(), vx, vy, vz)
+    np.testing.assert_allclose(x2, ox2, rtol=0, atol=4e-7)
+    np.testing.assert_allclose(y2, oy2, rtol=0, atol=4e-7)
+
+
+@pytest.mark.parametrize("rot", [0.0, np.radians(60.0)])
+def test_trace_rays_matches_oracle(rot):
+    from oracle import oracle as orc
+
+    tel = rubin_like("r", rot_tel_pos=rot)
+    ctx = _ctx()
+    ctx.set_telescope(tel)
+    rng = np.random.default_rng(5)
+    n = 50000
+    r = np.sqrt(rng.uniform(2.3**2, 4.3**2, n))  # includes vignetted rays
+    ph = rng.uniform(0, 2 * np.pi, n)
+    x, y, z = r * np.cos(ph), r * np.sin(ph), np.zeros(n)
+    thx, thy = rng.uniform(-0.031, 0.031, n), rng.uniform(-0.031, 0.031, n)
+    wl = rng.uniform(320e-9, 1050e-9, n)
+    g = 1 / np.sqrt(1 + thx**2 + thy**2)
+    nair = tel.in_medium.n(wl)
+    vx, vy, vz = thx * g / nair, thy * g / nair, -g / nair
+    t = np.zeros(n)
+    bt, ex = tel.flatten()
+    ref = orc.trace_rays(bt, ex, x, y, z, vx, vy, vz, t, wl)
+    arrs = [np.ascontiguousarray(a.copy()) for a in (x, y, z, vx, vy, vz, t, wl)]
+    vig = np.zeros(n, np.uint8)
+    fail = np.zeros(n, np.uint8)
+    ctx.trace_rays(*arrs, vig, fail)
+    assert np.array_equal(vig, ref[7]), "vignetting flags differ for %d rays" % np.sum(vig != ref[7])
+    assert np.array_equal(fail, ref[8])
+    ok = fail == 0
+    # positions on the focal plane are O(0.3 m); compare relative to the focal-plane scale
+    _close(arrs[0][ok], ref[0][ok], scale=0.3)
+    _close(arrs[1][ok], ref[1][ok], scale=0.3)
+    assert np.abs(arrs[2][ok]).max() < 1e-15  # on the detector plane (photon_ops.py:494)
+    for k in (3, 4, 5):
+        _close(arrs[k][ok], ref[k][ok], scale=1.0)
+    _close(arrs[6][ok], ref[6][ok])  # time of flight
+
+
+def test_paraboloid_focus_exact():
+    tel = paraboloid_test_telescope(10.0)
+    ctx = _ctx()
+    ctx.set_telescope(tel)
+    rng = np.random.default_rng(0)
+    n = 4096
+    x, y = rng.uniform(-3, 3, n), rng.uniform(-3, 3, n)
+    z, vx, vy, vz, t = np.zeros(n), np.zeros(n), np.zeros(n), -np.ones(n), np.zeros(n)
+    vig, fail = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    ctx.trace_rays(x, y, z, vx, vy, vz, t, np.full(n, 500e-9), vig, fail)
+    assert np.abs(x).max() < 1e-14 and np.abs(y).max() < 1e-14
+    assert np.ptp(t) < 1e-13 and abs(t[0] - 30.0) < 1e-13  # equal optical path (Fermat)
+
+
+@pytest.mark.parametrize("mode", ["optics", "diffraction_optics", "diffraction_optics_norot"])
+def test_rubin_optics_matches_oracle(mode):
+    from oracle import oracle as orc
+
+    su = helpers.oracle_setup()
+    dif = None if mode == "optics" else helpers.default_diffraction(field_rotation=(mode == "diffraction_optics"))
+    ctx = _ctx(su, dif)
+    p = helpers.test_photon_arrays(n=100000, t=12.0, center=(809.5, 3432.5))
+    rng = np.random.default_rng(11)
+    p["time"] = rng.uniform(0, 30, p["x"].size)
+    p["wavelength"] = rng.uniform(540, 700, p["x"].size)
+    gauss = rng.standard_normal(p["x"].size)
+    opt = _abi.B2OpticsOptions()
+    ref = orc.rubin_optics(*su.telescope.flatten(), su.img_wcs.to_pod(), su.icrf_to_field.to_pod(),
+                           su.detector.to_pod(), dif, opt, p["x"], p["y"], p["flux"], p["wavelength"], p["pupil_u"],
+                           p["pupil_v"], p["time"], gauss, want_time=True)
+    x, y, flux = p["x"].copy(), p["y"].copy(), p["flux"].copy()
+    dxdz, dydz, tout = np.empty_like(x), np.empty_like(x), np.empty_like(x)
+    stats = ctx.rubin_optics(x, y, dxdz, dydz, flux, p["wavelength"], p["pupil_u"], p["pupil_v"], p["time"],
+                             gauss=gauss, time_out=tout, options=opt)
+    assert np.array_equal(flux, ref["flux"])  # vignetting identical
+    assert stats.n_vignetted == ref["stats"].n_vignetted and stats.n_failed == 0 and stats.n_offdetector_z == 0
+    ok = flux > 0
+    assert ok.mean() > 0.9
+    _close(x[ok], ref["x"][ok], scale=4000.0)
+    _close(y[ok], ref["y"][ok], scale=4000.0)
+    _close(dxdz[ok], ref["dxdz"][ok], scale=1.0)
+    _close(dydz[ok], ref["dydz"][ok], scale=1.0)
+    _close(tout[ok], ref["time_out"][ok])
+    # photons land where the WCS says (within the PSF + diffraction spikes): tests/test_photon_ops.py:173-196
+    if mode == "optics":
+        assert np.abs(x[ok] - p["x"][ok]).max() < 20 and np.abs(y[ok] - p["y"][ok]).max() < 20
+
+
+def test_fused_focus_depth_and_refraction():
+    from oracle import oracle as orc
+
+    su = helpers.oracle_setup()
+    ctx = _ctx(su, None)
+    p = helpers.test_photon_arrays(n=20000, center=(2000.0, 2000.0))
+    opt = _abi.B2OpticsOptions()
+    opt.do_focus_depth, opt.focus_depth = 1, -0.6
+    opt.do_refraction, opt.index_ratio = 1, 3.9
+    opt.shift_in, opt.shift_out = 1, 1
+    opt.stamp_center[0], opt.stamp_center[1] = 12.0, -7.0
+    ref = orc.rubin_optics(*su.telescope.flatten(), su.img_wcs.to_pod(), su.icrf_to_field.to_pod(),
+                           su.detector.to_pod(), None, opt, p["x"], p["y"], p["flux"], p["wavelength"], p["pupil_u"],
+                           p["pupil_v"], p["time"])
+    x, y, flux = p["x"].copy(), p["y"].copy(), p["flux"].copy()
+    dxdz, dydz = np.empty_like(x), np.empty_like(x)
+    ctx.rubin_optics(x, y, dxdz, dydz, flux, p["wavelength"], p["pupil_u"], p["pupil_v"], p["time"], options=opt)
+    ok = flux > 0
+    _close(x[ok], ref["x"][ok], scale=4000.0)
+    _close(dxdz[ok], ref["dxdz"][ok], scale=1.0)
+    # Refraction shrinks the slopes by ~1/3.9
+    assert np.abs(dxdz[ok]).max() < 0.15
+
+
+def test_rubin_diffraction_matches_oracle_and_modular_equals_combined():
+    """RubinDiffraction.applyTo parity, and the reference's own invariant
+    (tests/test_photon_ops.py:281-318): combined op == diffraction then optics, 6 decimals."""
+    from oracle import oracle as orc
+
+    su = helpers.oracle_setup()
+    dif = helpers.default_diffraction()
+    ctx = _ctx(su, dif)
+    p = helpers.test_photon_arrays(n=30000, t=3.0, center=(1500.0, 2500.0))
+    gauss = np.random.default_rng(42).standard_normal(p["x"].size)
+    opt = _abi.B2OpticsOptions()
+    rx, ry = orc.rubin_diffraction(su.telescope.flatten()[0], su.img_wcs.to_pod(), su.icrf_to_field.to_pod(), dif,
+                                   opt, p["x"], p["y"], p["wavelength"], p["pupil_u"], p["pupil_v"], p["time"], gauss)
+    x, y = p["x"].copy(), p["y"].copy()
+    ctx.rubin_diffraction(x, y, p["wavelength"], p["pupil_u"], p["pupil_v"], p["time"], gauss=gauss, options=opt)
+    _close(x, rx, scale=4000.0)
+    _close(y, ry, scale=4000.0)
+    # modular: diffraction (above) then plain optics
+    ctx2 = _ctx(su, None)
+    flux = p["flux"].copy()
+    dxdz, dydz = np.empty_like(x), np.empty_like(x)
+    ctx2.rubin_optics(x, y, dxdz, dydz, flux, p["wavelength"], p["pupil_u"], p["pupil_v"], p["time"], options=opt)
+    # combined
+    xc, yc, fc = p["x"].copy(), p["y"].copy(), p["flux"].copy()
+    ac, bc = np.empty_like(x), np.empty_like(x)
+    ctx.rubin_optics(xc, yc, ac, bc, fc, p["wavelength"], p["pupil_u"], p["pupil_v"], p["time"], gauss=gauss,
+                     options=opt)
+    ok = (fc > 0) & (flux > 0)
+    np.testing.assert_array_almost_equal(xc[ok], x[ok], decimal=6)
+    np.testing.assert_array_almost_equal(yc[ok], y[ok], decimal=6)
+    np.testing.assert_array_almost_equal(ac[ok], dxdz[ok], decimal=6)
+
+
+def test_zernike_and_bicubic_perturbations():
+    from oracle import oracle as orc
+
+    rng = np.random.default_rng(9)
+    poly = np.zeros((5, 5))
+    poly[2, 0], poly[0, 2], poly[1, 1], poly[3, 1], poly[0, 4] = 3e-7, -2e-7, 1e-7, 4e-8, -3e-8
+    tel = rubin_like("r").with_surface_perturbation("M1", poly=poly, poly_scale=1 / 4.18)
+    xs = np.linspace(-1.8, 1.8, 41)
+    X, Y = np.meshgrid(xs, xs)
+    bic = dict(xs=xs, ys=xs, zs=1e-7 * np.cos(2 * X) * np.sin(Y), dzdxs=-2e-7 * np.sin(2 * X) * np.sin(Y),
+               dzdys=1e-7 * np.cos(2 * X) * np.cos(Y), d2zdxdys=-2e-7 * np.sin(2 * X) * np.cos(Y))
+    tel = tel.with_surface_perturbation("M2", bicubic=bic)
+    ctx = _ctx()
+    ctx.set_telescope(tel)
+    n = 20000
+    r = np.sqrt(rng.uniform(2.6**2, 4.1**2, n))
+    ph = rng.uniform(0, 2 * np.pi, n)
+    x, y, z = r * np.cos(ph), r * np.sin(ph), np.zeros(n)
+    thx, thy = rng.uniform(-0.02, 0.02, n), rng.uniform(-0.02, 0.02, n)
+    wl = np.full(n, 622e-9)
+    g = 1 / np.sqrt(1 + thx**2 + thy**2)
+    nair = tel.in_medium.n(wl)
+    vx, vy, vz, t = thx * g / nair, thy * g / nair, -g / nair, np.zeros(n)
+    bt, ex = tel.flatten()
+    ref = orc.trace_rays(bt, ex, x, y, z, vx, vy, vz, t, wl)
+    base = orc.trace_rays(*rubin_like("r").flatten(), x, y, z, vx, vy, vz, t, wl)
+    arrs = [np.ascontiguousarray(a.copy()) for a in (x, y, z, vx, vy, vz, t, wl)]
+    vig, fail = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    ctx.trace_rays(*arrs, vig, fail)
+    ok = (fail == 0) & (ref[8] == 0)
+    assert ok.mean() > 0.99
+    _close(arrs[0][ok], ref[0][ok], scale=0.3)
+    _close(arrs[1][ok], ref[1][ok], scale=0.3)
+    # and the perturbation does something (microns on the focal plane)
+    assert np.abs(ref[0][ok] - base[0][ok]).max() > 1e-7

@@ -1,0 +1,178 @@
+"""Pin the CPU oracle against everything the reference's own tests and sources
+fix for this path:
+
+  * imsim/diffraction.py itself (imported standalone when the golden file was made),
+  * tests/test_diffraction.py known answers,
+  * tests/test_tree_rings.py:16-38 known answers,
+  * tests/test_photon_ops.py:668-691 ray->pixel golden vector,
+  * doc/validation/diffusion.rst diffusion-step formula evaluated on the sensor cfgs.
+"""
+import numpy as np
+import pytest
+
+import helpers
+from imsim_b200 import _abi
+from imsim_b200.detector import lsstcam_like
+from imsim_b200.diffraction import RUBIN_SPIDER_GEOMETRY, diffraction_config, e_equatorial
+from imsim_b200.sensor import calculate_diff_step
+from imsim_b200.treerings import RadialTable, TreeRingRadialFunction, natural_spline_y2
+from oracle import oracle as orc
+
+
+def test_diffraction_matches_reference_module_no_rotation():
+    g = helpers.golden("diffraction.npz")
+    cfg = diffraction_config(disable_field_rotation=True)
+    v = g["v"]
+    vx, vy, vz = orc.diffraction(cfg, g["pos"][:, 0], g["pos"][:, 1], g["t"], g["wl"], g["gauss"], v[:, 0], v[:, 1],
+                                 v[:, 2])
+    ref = g["v_norot"]
+    np.testing.assert_allclose(np.c_[vx, vy, vz], ref, rtol=0, atol=2e-16)
+
+
+def test_diffraction_matches_reference_module_field_rotation():
+    g = helpers.golden("diffraction.npz")
+    cfg = diffraction_config(latitude=float(g["lat"]), altitude=float(g["alt"]), azimuth=float(g["az"]))
+    np.testing.assert_allclose(np.array(cfg.e_focal[:]), g["e_equatorial"], rtol=0, atol=1e-16)
+    assert cfg.omega == float(g["omega"])
+    v = g["v"]
+    vx, vy, vz = orc.diffraction(cfg, g["pos"][:, 0], g["pos"][:, 1], g["t"], g["wl"], g["gauss"], v[:, 0], v[:, 1],
+                                 v[:, 2])
+    # einsum vs scalar evaluation order: a few ulp
+    np.testing.assert_allclose(np.c_[vx, vy, vz], g["v_rot"], rtol=0, atol=1e-15)
+    # the kick preserves |v| (apply_delta_v)
+    np.testing.assert_allclose(np.sqrt(vx**2 + vy**2 + vz**2), np.linalg.norm(v, axis=1), rtol=1e-15)
+
+
+def test_geometry_table_is_the_reference_one():
+    g = helpers.golden("diffraction.npz")
+    np.testing.assert_array_equal(RUBIN_SPIDER_GEOMETRY.thick_lines, g["lines"])
+    np.testing.assert_array_equal(RUBIN_SPIDER_GEOMETRY.circles, g["circles"])
+
+
+def _kick_distance(px, py, wl=500e-9, gauss=1.0):
+    """recover the distance the oracle used from the kick size (v along -z, unit speed)"""
+    cfg = diffraction_config(disable_field_rotation=True)
+    vx, vy, vz = orc.diffraction(cfg, [px], [py], [0.0], [wl], [gauss], [0.0], [0.0], [-1.0])
+    tan_phi = np.hypot(vx[0], vy[0]) / -vz[0]
+    phi = tan_phi  # d_tan_phi = gauss * phi*
+    k = 2 * np.pi / wl
+    return 1.0 / (2 * k * np.tan(phi)), (vx[0], vy[0])
+
+
+def test_directed_dist_known_answers():
+    # tests/test_diffraction.py:8-81 style known answers on the Rubin geometry:
+    # a point just inside the outer circle is closest to it, normal points to the centre
+    d, (kx, ky) = _kick_distance(4.0, 0.0)
+    assert d == pytest.approx(0.18, rel=1e-9)
+    assert kx < 0 and abs(ky) < 1e-18  # n = (centre - p)/|.| = (-1, 0)
+    # a point near a vane: |n.p - d| - w
+    s = 1 / np.sqrt(2.0)
+    p = np.array([3.0, -3.0 + 0.4 / s + 0.05 / s])  # 0.05 off the centre line of vane n=(s,s), d=0.4
+    d, (kx, ky) = _kick_distance(*p)
+    assert d == pytest.approx(0.05 - 0.025, rel=1e-9)
+    assert kx == pytest.approx(ky, rel=1e-12)  # along the stored line normal
+
+
+def test_field_rotation_matrix_golden():
+    g = helpers.golden("diffraction.npz")
+    # rotation angles of the golden matrices are tiny over 30 s but non-zero; check orthonormality
+    R = g["rotm"]
+    np.testing.assert_allclose(R[:, 0, 0] ** 2 + R[:, 0, 1] ** 2, 1.0, atol=1e-12)
+    assert np.abs(R[:, 0, 1]).max() > 1e-5
+
+
+def test_tree_ring_known_answers():
+    g = helpers.golden("tree_rings.npz")
+    for i, det in enumerate(("R22_S11", "R34_S22")):
+        block = helpers.tree_ring_block(det, "tree_ring_parameters_19mar18.txt")
+        f = TreeRingRadialFunction(block)
+        # oracle restatement == host class == known answer (tests/test_tree_rings.py:19)
+        val_o = orc.treering_func(f.A, f.B, f.cfreqs, f.cphases, f.sfreqs, f.sphases, [float(g["known_r"])])[0]
+        assert val_o == pytest.approx(float(g["known_values"][i]), abs=5e-7)
+        assert float(f(float(g["known_r"]))) == pytest.approx(val_o, rel=1e-13)
+        items = block[1].split()
+        assert (float(items[4]), float(items[5])) == pytest.approx(tuple(g["known_centers"][i]), abs=0.05)
+        # the tabulated (spline) function the sensor uses agrees to 6 decimals as the reference test demands
+        tab = RadialTable.from_func(f, 0.0, 8000.0, 2667)
+        assert float(tab(float(g["known_r"]))) == pytest.approx(float(g["known_values"][i]), abs=5e-7)
+
+
+def test_spline_matches_oracle_and_scipy():
+    from scipy.interpolate import CubicSpline
+
+    (cx, cy), tab = helpers.tree_ring_table()
+    y2 = orc.spline_y2(tab.x, tab.f)
+    np.testing.assert_allclose(natural_spline_y2(tab.x, tab.f), y2, rtol=0, atol=0)
+    cs = CubicSpline(tab.x, tab.f, bc_type="natural")
+    r = np.random.default_rng(1).uniform(1, 7999, 500)
+    np.testing.assert_allclose([orc.table_spline(tab.x, tab.f, y2, a) for a in r], cs(r), rtol=1e-9, atol=1e-15)
+    np.testing.assert_allclose(tab(r), cs(r), rtol=1e-9, atol=1e-15)
+
+
+def test_ray_to_pixel_golden_vector():
+    """tests/test_photon_ops.py:668-691 through the oracle's applyTo epilogue: a
+    'telescope' that is only a detector plane leaves the rays untouched."""
+    from imsim_b200.telescope import CoordSys, Interface, Surface, Telescope, VACUUM
+
+    I = np.eye(3)
+    tel = Telescope(stop=CoordSys(np.zeros(3), I.copy()),
+                    items=[Interface("D", Surface("plane"), "detector", CoordSys(np.zeros(3), I.copy()), VACUUM,
+                                     VACUUM, [])], in_medium=VACUUM)
+    bt, ex = tel.flatten()
+    det = lsstcam_like("R22_S11")
+    # the host mirror first
+    from imsim_b200.photon_array import PhotonArray
+    from imsim_b200.photon_ops import ray_vector_to_photon_array
+
+    class RV:
+        x = np.array([1.0, 2.0]); y = np.array([-1.0, 3.0]); z = np.zeros(2)
+        vx = np.array([0.0, 0.25]); vy = np.array([0.0, 0.5]); vz = np.array([-1.0, -1.0])
+        vignetted = np.zeros(2, bool)
+
+    pa = PhotonArray(2, flux=np.ones(2))
+    ray_vector_to_photon_array(RV, det, pa)
+    np.testing.assert_array_almost_equal(pa.x, np.array([-97952.5, 302047.5]))
+    np.testing.assert_array_almost_equal(pa.y, np.array([102001.5, 202001.5]))
+    np.testing.assert_array_almost_equal(pa.dxdz, np.array([0.0, -0.5]))
+    np.testing.assert_array_almost_equal(pa.dydz, np.array([0.0, -0.25]))
+    np.testing.assert_array_almost_equal(pa.flux, np.ones(2))
+    # and the oracle's trace + epilogue on the same rays
+    out = orc.trace_rays(bt, ex, RV.x, RV.y, RV.z, RV.vx, RV.vy, RV.vz, np.zeros(2), 577.6e-9)
+    pod = det.to_pod()
+    fpx, fpy = out[1] * 1e3, out[0] * 1e3
+    x = pod.A[0] * fpx + pod.A[1] * fpy + pod.b[0]
+    y = pod.A[2] * fpx + pod.A[3] * fpy + pod.b[1]
+    np.testing.assert_array_almost_equal(x, np.array([-97952.5, 302047.5]))
+    np.testing.assert_array_almost_equal(y, np.array([102001.5, 202001.5]))
+    np.testing.assert_array_almost_equal(np.array(pod.Jhat[:]).reshape(2, 2), [[0, 1], [1, 0]])
+
+
+def test_diff_step_values():
+    # doc/validation/diffusion.rst formula on the reference cfgs (ITL 4.429, E2V 4.379 um)
+    cfg, _ = helpers.sensor_model("lsst_itl_50_4")
+    assert calculate_diff_step(cfg) == pytest.approx(4.429, abs=2e-3)
+    cfg, _ = helpers.sensor_model("lsst_e2v_50_4")
+    assert calculate_diff_step(cfg) == pytest.approx(4.379, abs=2e-3)
+
+
+def test_sensor_table_layout():
+    # the .dat layout the oracle assumes: x-major pixel order, 15..95 um centres, polygon order by angle
+    cfg, dat = helpers.sensor_model("lsst_itl_50_4")
+    nv = cfg["NumVertices"]
+    npoly = 4 * nv + 4
+    assert dat.shape == (81 * npoly, 5)
+    assert tuple(dat[0, :2]) == (15.0, 15.0) and tuple(dat[npoly, :2]) == (15.0, 25.0)
+    pod = helpers.sensor_pod(cfg)
+    s = orc.Sensor(pod, dat)
+    img = np.zeros((12, 12), np.float32)
+    s.bind_image(img)
+    rng = np.random.default_rng(0)
+    s.accumulate([5.0], [5.0], [0.0], np.zeros(4))  # initialise boundaries
+    poly, bounds = s.get_pixel(5, 5)
+    # undistorted polygon = unit square, vertices in .dat order
+    th = np.arctan2(poly[:, 1] - 0.5, poly[:, 0] - 0.5)
+    assert np.all(np.diff(th) > 0)  # increasing from just past -pi
+    th_file = dat[:npoly, 2]
+    th_file = np.where(th_file > np.pi, th_file - 2 * np.pi, th_file)
+    np.testing.assert_allclose(th, th_file, atol=2e-3)
+    np.testing.assert_allclose(bounds, [0, 1, 0, 1, 0, 1, 0, 1], atol=1e-7)
