@@ -219,6 +219,10 @@ class Telescope:
             # batoid CoordTransform(source=prev, dest=this)
             dr = prev.rot.T @ (it.coord_sys.origin - prev.origin)
             drot = prev.rot.T @ it.coord_sys.rot
+            # consecutive interfaces of a rigidly rotated group (the camera behind the rotator)
+            # share their frame: snap round-off (|.| < 4 ulp) to the exact identity
+            if np.abs(drot - np.eye(3)).max() < 1e-15:
+                drot = np.eye(3)
             s.rot_identity = int(np.array_equal(drot, np.eye(3)))
             for k in range(3):
                 s.dr[k] = dr[k]

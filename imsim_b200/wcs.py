@@ -79,9 +79,24 @@ def fit_tan_sip(x, y, ra, dec, order=3, center=None) -> TanSipWCS:
     cy, *_ = np.linalg.lstsq(A, eta, rcond=None)
     M = np.array([[cx[0], cx[1]], [cy[0], cy[1]]])
     crpix = -np.linalg.solve(M, np.array([cx[2], cy[2]]))
-    u, v = x - crpix[0], y - crpix[1]
     if order <= 1:
         return TanSipWCS(crpix=crpix, cd=M, center=center, order=0)
+    # refine crpix: it is where the full polynomial (not its affine part) vanishes, so that the
+    # final fit needs no constant term
+    all_terms = [(i, j) for i in range(order + 1) for j in range(order + 1 - i)]
+    for _ in range(6):
+        u, v = x - crpix[0], y - crpix[1]
+        s = max(np.abs(u).max(), np.abs(v).max())
+        D = np.column_stack([(u / s) ** i * (v / s) ** j for i, j in all_terms])
+        px, *_ = np.linalg.lstsq(D, xi, rcond=None)
+        py, *_ = np.linalg.lstsq(D, eta, rcond=None)
+        c = {t: (a, b_) for t, a, b_ in zip(all_terms, px, py)}
+        J = np.array([[c[(1, 0)][0], c[(0, 1)][0]], [c[(1, 0)][1], c[(0, 1)][1]]]) / s
+        step = -np.linalg.solve(J, np.array(c[(0, 0)]))
+        crpix = crpix + step
+        if np.abs(step).max() < 1e-13 * s:
+            break
+    u, v = x - crpix[0], y - crpix[1]
     # polynomial without constant term, scaled for conditioning
     s = max(np.abs(u).max(), np.abs(v).max())
     us, vs = u / s, v / s

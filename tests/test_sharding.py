@@ -1,0 +1,61 @@
+"""Multi-GPU host logic on CPU: LPT detector sharding and the gloo metadata gather (world_size 2)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from imsim_b200.detector import lsstcam_science_detectors
+from imsim_b200.sharding import gather_visit_metadata, lpt_partition
+
+
+def test_lpt_partition_covers_every_detector_once():
+    dets = lsstcam_science_detectors()
+    rng = np.random.default_rng(0)
+    costs = {d: float(c) for d, c in zip(dets, rng.lognormal(18, 0.7, len(dets)))}
+    for n in (1, 2, 4, 8):
+        shards = lpt_partition(costs, n)
+        flat = [d for s in shards for d in s]
+        assert sorted(flat) == sorted(dets)
+        loads = [sum(costs[d] for d in s) for s in shards]
+        assert max(loads) <= min(loads) + max(costs.values())  # LPT bound
+        assert max(len(s) for s in shards) <= -(-len(dets) // n) + 6
+    assert lpt_partition(costs, 8) == lpt_partition(dict(reversed(list(costs.items()))), 8)  # deterministic
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dets = lsstcam_science_detectors()[:10]
+    costs = {d: 1.0 + i for i, d in enumerate(dets)}
+    mine = lpt_partition(costs, world)[rank]
+    local = [{"det_name": d, "photons": int(costs[d] * 1000), "rank": rank} for d in mine]
+    allrec = gather_visit_metadata(local)
+    dist.destroy_process_group()
+    q.put((rank, [r["det_name"] for r in allrec], sum(r["photons"] for r in allrec)))
+
+
+def test_gloo_metadata_gather_world_size_2():
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    dets = sorted(lsstcam_science_detectors()[:10])
+    for rank, names, total in res:
+        assert names == dets
+        assert total == sum(int((1.0 + i) * 1000) for i in range(10))
