@@ -46,6 +46,8 @@ struct b2_sensor {
     bool bound = false, initialized = false;
     double accum_flux = 0.0;
     uint8_t* changed = nullptr;
+    uint8_t* tiles = nullptr;  // charge occupancy per 32x32 tile
+    int tnx = 0, tny = 0;
     unsigned long long* dstats = nullptr;  // device counters
     double* dadded = nullptr;
     Scratch cum;  // cumulative flux scratch
@@ -404,13 +406,47 @@ k_init_boundaries(const __grid_constant__ DevSensor s, int ocx, int ocy) {
     }
 }
 
+// Charge occupancy per 32x32-pixel tile: lets the boundary update skip the (usually large) part
+// of the CCD that received no charge since the last update.
+#define B2_TILE 32
+template <typename CT>
+__global__ void __launch_bounds__(256)
+k_charge_tiles(const CT* __restrict__ charge, int nx, int ny, int tnx, uint8_t* __restrict__ tiles) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    bool nz = (x < nx) && (charge[(size_t)y * nx + x] != (CT)0);
+    // one store per warp that saw charge (a warp spans one tile row segment)
+    unsigned any = __ballot_sync(0xffffffffu, nz);
+    if (any && (threadIdx.x & 31) == 0) tiles[(y / B2_TILE) * tnx + (x / B2_TILE)] = 1;
+}
+
+// true if any tile overlapping pixels [xa, xb] x [ya, yb] holds charge (uniform per block)
+__device__ __forceinline__ bool tiles_any(const uint8_t* __restrict__ tiles, int tnx, int tny, int xa, int xb, int ya,
+                                          int yb, int nx, int ny) {
+    xa = max(xa, 0); ya = max(ya, 0);
+    xb = min(xb, nx - 1); yb = min(yb, ny - 1);
+    if (xa > xb || ya > yb) return false;
+    for (int ty = ya / B2_TILE; ty <= yb / B2_TILE; ++ty)
+        for (int tx = xa / B2_TILE; tx <= xb / B2_TILE; ++tx)
+            if (tiles[ty * tnx + tx]) return true;
+    return false;
+}
+
 // Silicon::updatePixelDistortions: charge-weighted sum of the per-electron kernels.
 // One thread per (x, y) slot; CHARGE_T: the delta image (double) or the target image.
 template <typename CT>
 __global__ void __launch_bounds__(128)
-k_update_distortions(const __grid_constant__ DevSensor s, const CT* __restrict__ charge, uint8_t* __restrict__ changed) {
+k_update_distortions(const __grid_constant__ DevSensor s, const CT* __restrict__ charge, uint8_t* __restrict__ changed,
+                     const uint8_t* __restrict__ tiles, int tnx, int tny) {
     extern __shared__ float2 sK[];  // KH then KV
     const int nv = s.nv;
+    {
+        // block-uniform early exit: no charge within reach of this strip of slots
+        int xs = blockIdx.x * blockDim.x, ys = blockIdx.y;
+        if (!tiles_any(tiles, tnx, tny, xs - s.qdist - 1, xs + (int)blockDim.x - 1 + s.qdist, ys - s.qdist - 1,
+                       ys + s.qdist, s.nx, s.ny))
+            return;
+    }
     const int nKH = s.nx9 * s.ny9 * (nv + 2), nKV = s.nx9 * s.ny9 * nv;
     for (int k = threadIdx.x; k < nKH; k += blockDim.x) sK[k] = s.KH[k];
     for (int k = threadIdx.x; k < nKV; k += blockDim.x) sK[nKH + k] = s.KV[k];
@@ -480,9 +516,16 @@ k_update_distortions(const __grid_constant__ DevSensor s, const CT* __restrict__
 
 // Silicon::updatePixelBounds for every pixel (all = 1) or the flagged ones
 __global__ void __launch_bounds__(256)
-k_update_bounds(const __grid_constant__ DevSensor s, const uint8_t* __restrict__ changed, int all) {
+k_update_bounds(const __grid_constant__ DevSensor s, const uint8_t* __restrict__ changed, int all,
+                const uint8_t* __restrict__ tiles, int tnx, int tny) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y;
+    if (!all) {
+        int xs = blockIdx.x * blockDim.x;
+        if (!tiles_any(tiles, tnx, tny, xs - s.qdist - 2, xs + (int)blockDim.x + s.qdist + 1, y - s.qdist - 2,
+                       y + s.qdist + 1, s.nx, s.ny))
+            return;
+    }
     if (x >= s.nx) return;
     size_t pix = (size_t)y * s.nx + x;
     if (!all && !changed[pix]) return;
@@ -750,6 +793,9 @@ extern "C" int b2_sensor_bind_image(b2_sensor* s, int32_t xmin, int32_t ymin, in
         B2_CUDA(cudaMalloc(&p, npix * sizeof(double))); s->image_owned.push_back(p); d.delta = (double*)p;
         B2_CUDA(cudaMalloc(&p, npix * dtype_bytes)); s->image_owned.push_back(p); d.target = p;
         B2_CUDA(cudaMalloc(&p, npix)); s->image_owned.push_back(p); s->changed = (uint8_t*)p;
+        s->tnx = (nx + B2_TILE - 1) / B2_TILE;
+        s->tny = (ny + B2_TILE - 1) / B2_TILE;
+        B2_CUDA(cudaMalloc(&p, (size_t)s->tnx * s->tny)); s->image_owned.push_back(p); s->tiles = (uint8_t*)p;
     }
     d.xmin = xmin; d.ymin = ymin; d.nx = nx; d.ny = ny; d.dtype_bytes = dtype_bytes;
     size_t bytes = (size_t)nx * ny * dtype_bytes;
@@ -789,18 +835,27 @@ static int launch_add_delta(b2_sensor* s, double sign, int clear) {
 static int launch_update_distortions(b2_sensor* s, bool from_target) {
     DevSensor& d = s->d;
     b2_ctx* ctx = s->ctx;
-    B2_CUDA(cudaMemsetAsync(s->changed, 0, (size_t)d.nx * d.ny, ctx->stream));
+    cudaStream_t st = ctx->stream;
+    B2_CUDA(cudaMemsetAsync(s->changed, 0, (size_t)d.nx * d.ny, st));
+    B2_CUDA(cudaMemsetAsync(s->tiles, 0, (size_t)s->tnx * s->tny, st));
+    dim3 gt = grid2(d.nx, d.ny, 256);
     size_t smem = ((size_t)d.nx9 * d.ny9 * (2 * d.nv + 2)) * sizeof(float2);
     dim3 g = grid2(d.nx + 1, d.ny + 1, 128);
     if (!from_target) {
+        k_charge_tiles<double><<<gt, 256, 0, st>>>(d.delta, d.nx, d.ny, s->tnx, s->tiles);
+        B2_CHECK_LAUNCH();
         if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(k_update_distortions<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_update_distortions<double><<<g, 128, smem, ctx->stream>>>(d, d.delta, s->changed);
+        k_update_distortions<double><<<g, 128, smem, st>>>(d, d.delta, s->changed, s->tiles, s->tnx, s->tny);
     } else if (d.dtype_bytes == 4) {
+        k_charge_tiles<float><<<gt, 256, 0, st>>>((const float*)d.target, d.nx, d.ny, s->tnx, s->tiles);
+        B2_CHECK_LAUNCH();
         if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(k_update_distortions<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_update_distortions<float><<<g, 128, smem, ctx->stream>>>(d, (const float*)d.target, s->changed);
+        k_update_distortions<float><<<g, 128, smem, st>>>(d, (const float*)d.target, s->changed, s->tiles, s->tnx, s->tny);
     } else {
+        k_charge_tiles<double><<<gt, 256, 0, st>>>((const double*)d.target, d.nx, d.ny, s->tnx, s->tiles);
+        B2_CHECK_LAUNCH();
         if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(k_update_distortions<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_update_distortions<double><<<g, 128, smem, ctx->stream>>>(d, (const double*)d.target, s->changed);
+        k_update_distortions<double><<<g, 128, smem, st>>>(d, (const double*)d.target, s->changed, s->tiles, s->tnx, s->tny);
     }
     B2_CHECK_LAUNCH();
     return 0;
@@ -808,7 +863,7 @@ static int launch_update_distortions(b2_sensor* s, bool from_target) {
 
 static int launch_bounds_update(b2_sensor* s, int all) {
     DevSensor& d = s->d;
-    k_update_bounds<<<grid2(d.nx, d.ny, 256), 256, 0, s->ctx->stream>>>(d, s->changed, all);
+    k_update_bounds<<<grid2(d.nx, d.ny, 256), 256, 0, s->ctx->stream>>>(d, s->changed, all, s->tiles, s->tnx, s->tny);
     B2_CHECK_LAUNCH();
     return 0;
 }
