@@ -201,7 +201,12 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=2_000_000)
     ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-timing", action="store_true",
+                    help="diagnostic: bracket every kernel with CUDA events (B2_TIMING=1) and print the breakdown "
+                         "to stderr; adds event overhead, do not quote `value` from such a run")
     args = ap.parse_args()
+    if args.kernel_timing:
+        os.environ["B2_TIMING"] = "1"
     if args.impl == "reference":
         return run_reference(args)
 
@@ -267,6 +272,10 @@ def main():
         refill(work[i % 2])
         pool.process(work[i % 2], image, resume=True, recalc=True)
     barrier()
+    if args.kernel_timing:
+        from imsim_b200._lib import timing_report
+
+        timing_report()  # drop warm-up launches
     clocks = ClockSampler(local)
     clocks.start()
     l0 = launch_count()
@@ -290,6 +299,9 @@ def main():
     barrier()
     launches = launch_count() - l0
     clk = clocks.stop()
+    if args.kernel_timing and rank == 0:
+        rep = timing_report()
+        sys.stderr.write("per-step kernel ms: " + json.dumps({k: round(v[1] / K, 4) for k, v in rep.items()}) + "\n")
     step_ms = [a.elapsed_time(b) for a, b in ev]
     trace_ms = [a.elapsed_time(b) for a, b in kev]
     total_ms = float(np.sum(step_ms))

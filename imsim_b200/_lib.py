@@ -71,6 +71,7 @@ _SIGNATURES = {
     "b2_ctx_set_stream": (C.c_int, [vp, vp]),
     "b2_ctx_synchronize": (C.c_int, [vp]),
     "b2_fma_peak": (C.c_int, [vp, C.c_int32, dp]),
+    "b2_timing_report": (C.c_int, [C.c_char_p, C.c_int64]),
     "b2_telescope_upload": (C.c_int, [vp, C.POINTER(_abi.B2Telescope)]),
     "b2_telescope_set_extra": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int64]),
     "b2_wcs_upload": (C.c_int, [vp, C.POINTER(_abi.B2TanSip), C.POINTER(_abi.B2TanSip)]),
@@ -129,6 +130,15 @@ def check(rc: int):
 
 def launch_count() -> int:
     return int(load().b2_launch_count())
+
+
+def timing_report() -> dict:
+    """Per-kernel device times {name: [launches, total_ms]} since the last call (needs B2_TIMING=1)."""
+    import json
+
+    buf = C.create_string_buffer(1 << 16)
+    check(load().b2_timing_report(buf, len(buf)))
+    return json.loads(buf.value.decode())
 
 
 # ---- pointer helpers -----------------------------------------------------

@@ -1,4 +1,8 @@
 // abi.cu -- context management and library-level entry points of libimsim_b200.so
+#include <cstdlib>
+#include <map>
+#include <mutex>
+
 #include "b2_common.cuh"
 
 thread_local std::string g_b2_error;
@@ -78,5 +82,70 @@ extern "C" int b2_ctx_synchronize(b2_ctx* ctx) {
     B2_REQUIRE(ctx, "null context");
     B2_CUDA(cudaSetDevice(ctx->device));
     B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------- per-kernel timing (B2_TIMING=1)
+namespace {
+struct TimedLaunch {
+    const char* name;
+    cudaEvent_t e0, e1;
+};
+std::vector<TimedLaunch> g_timed;
+std::mutex g_timed_mu;
+}  // namespace
+
+bool b2_timing_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("B2_TIMING");
+        on = (e && e[0] == '1') ? 1 : 0;
+    }
+    return on == 1;
+}
+
+void b2_timing_begin(const char* name, cudaStream_t st) {
+    TimedLaunch t;
+    t.name = name;
+    cudaEventCreate(&t.e0);
+    cudaEventCreate(&t.e1);
+    cudaEventRecord(t.e0, st);
+    std::lock_guard<std::mutex> lk(g_timed_mu);
+    g_timed.push_back(t);
+}
+
+void b2_timing_end(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_timed_mu);
+    cudaEventRecord(g_timed.back().e1, st);
+}
+
+// JSON {"kernel": [count, total_ms], ...} of everything timed since the last report; clears the log
+extern "C" int b2_timing_report(char* buf, int64_t cap) {
+    B2_REQUIRE(buf && cap > 2, "b2_timing_report: bad buffer");
+    std::lock_guard<std::mutex> lk(g_timed_mu);
+    std::map<std::string, std::pair<long, double>> agg;
+    for (auto& t : g_timed) {
+        cudaEventSynchronize(t.e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t.e0, t.e1);
+        auto& a = agg[t.name];
+        a.first++;
+        a.second += ms;
+        cudaEventDestroy(t.e0);
+        cudaEventDestroy(t.e1);
+    }
+    g_timed.clear();
+    std::string out = "{";
+    bool first = true;
+    for (auto& kv : agg) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s\"%s\": [%ld, %.6f]", first ? "" : ", ", kv.first.c_str(), kv.second.first,
+                 kv.second.second);
+        out += line;
+        first = false;
+    }
+    out += "}";
+    B2_REQUIRE((int64_t)out.size() + 1 <= cap, "b2_timing_report: buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
     return 0;
 }

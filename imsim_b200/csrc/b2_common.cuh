@@ -40,6 +40,23 @@ static inline int b2_fail(const char* fmt, const char* a = "", const char* b = "
         B2_CUDA(cudaGetLastError());              \
     } while (0)
 
+// Optional per-kernel device timing (B2_TIMING=1): cudaEvents around each launch on the launching
+// stream, resolved lazily by b2_timing_report().  Off by default: no events, no overhead.
+bool b2_timing_enabled();
+void b2_timing_begin(const char* name, cudaStream_t st);
+void b2_timing_end(cudaStream_t st);
+struct B2TimedScope {
+    cudaStream_t st;
+    bool on;
+    B2TimedScope(const char* name, cudaStream_t s) : st(s), on(b2_timing_enabled()) {
+        if (on) b2_timing_begin(name, st);
+    }
+    ~B2TimedScope() {
+        if (on) b2_timing_end(st);
+    }
+};
+#define B2_TIMED(name, stream) B2TimedScope _b2_timed_scope(name, stream)
+
 #define B2_REQUIRE(cond, msg)             \
     do {                                  \
         if (!(cond)) return b2_fail("%s", msg); \
@@ -74,6 +91,9 @@ struct DevSurf {
     int poly_n, pad;
     double poly_scale;
     const double* extra;  // device pointer (poly coefficients or bicubic block)
+    // fast path for the usual single centred Clear{Circle,Annulus}: vignetted unless in2 <= r^2 < out2
+    int simple_clear, pad2;
+    double clr_in2, clr_out2;
 };
 
 #define B2_DEV_MAX_SURF 16

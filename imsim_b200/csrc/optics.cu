@@ -8,6 +8,8 @@
 //
 // Replaces (per photon): imsim/photon_ops.py:81-148,274-302,454-503 and the
 // batoid / GalSim C++ those lines call; see include/imsim_b200.h.
+#include <cstdlib>
+
 #include "b2_common.cuh"
 
 #define PI_D 3.14159265358979323846
@@ -340,21 +342,31 @@ __device__ __forceinline__ void bicubic_eval(const double* blk, double x, double
     fx = h1(yf, gx0, gx1, gd0 * dy, gd1 * dy) / dx;
 }
 
-// even-asphere polynomial P(r^2) = sum coef[k] r^(4+2k) and dP/d(r^2), plus the summed
-// extra term E(x, y) with its gradient: everything on the surface that is not the base conic
+// even-asphere polynomial P(r^2) = sum coef[k] r^(4+2k) with dP/d(r^2) and d2P/d(r^2)^2, plus the
+// summed extra term E(x, y) with its gradient: everything on the surface that is not the base conic
 __device__ __forceinline__ void departure(const DevSurf& s, double x, double y, double r2, double& P, double& dP,
-                                          double& E, double& Ex, double& Ey) {
-    P = 0.0;
-    dP = 0.0;
+                                          double& ddP, double& E, double& Ex, double& Ey) {
+    P = dP = ddP = 0.0;
     if (s.kind == B2_SURF_ASPHERE) {
-        // Horner from the highest coefficient: P = r2^2 (c0 + r2 (c1 + ...)), dP = d/d(r2)
-        double h = 0.0, dh = 0.0;
-        for (int k = s.n_coef - 1; k >= 0; --k) {
-            dh = dh * r2 + h;
-            h = h * r2 + s.coef[k];
+        // P = r2^2 h(r2); Horner for h, h', h'' from the highest coefficient
+        double h = 0.0, dh = 0.0, ddh = 0.0;
+        if (s.n_coef <= 4) {  // the usual case, fully unrolled (unused coefficients are zero)
+#pragma unroll
+            for (int k = 3; k >= 0; --k) {
+                ddh = ddh * r2 + 2.0 * dh;
+                dh = dh * r2 + h;
+                h = h * r2 + s.coef[k];
+            }
+        } else {
+            for (int k = s.n_coef - 1; k >= 0; --k) {
+                ddh = ddh * r2 + 2.0 * dh;
+                dh = dh * r2 + h;
+                h = h * r2 + s.coef[k];
+            }
         }
         P = r2 * r2 * h;
         dP = r2 * (2.0 * h + r2 * dh);
+        ddP = 2.0 * h + r2 * (4.0 * dh + r2 * ddh);
     }
     E = Ex = Ey = 0.0;
     if (s.extra_kind == B2_EXTRA_POLY2D) poly2d_eval(s, x, y, E, Ex, Ey);
@@ -449,11 +461,12 @@ __device__ __forceinline__ void trace_ray(const DevOptics& o, Ray& r, double wl)
             // Newton on the implicit form G(t) = r^2 - 2 R zc + k1 zc^2 with zc = z - P(r^2) - E(x, y):
             // polynomial in the ray parameter, no square root; quadratic convergence from the conic hit
             bool conv = false;
+            const bool pure = (s.extra_kind == B2_EXTRA_NONE);
 #pragma unroll 1
             for (int it = 0; it < 8; ++it) {
                 double r2 = px * px + py * py;
-                double P, dP, E;
-                departure(s, px, py, r2, P, dP, E, Ex, Ey);
+                double P, dP, ddP, E;
+                departure(s, px, py, r2, P, dP, ddP, E, Ex, Ey);
                 zc = pz - P - E;
                 double rv = px * vx + py * vy;
                 double dzc = vz - 2.0 * dP * rv - (Ex * vx + Ey * vy);
@@ -472,9 +485,15 @@ __device__ __forceinline__ void trace_ray(const DevOptics& o, Ray& r, double wl)
                 pz += vz * step;
                 zc += dzc * step;
                 gP = dP;
-                // the departure gradient (gP, Ex, Ey) was evaluated one step back: stop only when
-                // that step is below 1e-13 m so the normal is good to ~3e-14 rad (1e-10 px at the
-                // focal plane needs ~4e-13 rad); from the conic seed this is the third evaluation
+                // The departure gradient was evaluated one step back; the normal needs it at the hit
+                // point to ~3e-14 rad (1e-10 px at the focal plane ~ 4e-13 rad).  Pure aspheres:
+                // refresh dP to first order with d2P once the step is small (second evaluation from
+                // the conic seed); summed Zernike / bicubic terms: iterate until the step is < 1e-13 m.
+                if (pure && fabs(step) < 1e-6) {
+                    gP = dP + ddP * (2.0 * rv * step);
+                    conv = true;
+                    break;
+                }
                 if (fabs(step) < 1e-13) {
                     conv = true;
                     break;
@@ -524,8 +543,13 @@ __device__ __forceinline__ void trace_ray(const DevOptics& o, Ray& r, double wl)
                 vz = (e2 * vz - fac) * inb;
             }
         }
-        for (int k = 0; k < s.n_obsc; ++k)
-            if (obscured(s.obsc[k], px, py)) r.vignetted = true;
+        if (s.simple_clear) {
+            double r2 = px * px + py * py;
+            if (!(s.clr_in2 <= r2 && r2 < s.clr_out2)) r.vignetted = true;
+        } else {
+            for (int k = 0; k < s.n_obsc; ++k)
+                if (obscured(s.obsc[k], px, py)) r.vignetted = true;
+        }
         r.x = px; r.y = py; r.z = pz;
         r.vx = vx; r.vy = vy; r.vz = vz;
     }
@@ -582,8 +606,8 @@ k_trace_rays(const __grid_constant__ DevOptics o, int64_t n, double* x, double* 
 }
 
 // RubinOptics / RubinDiffractionOptics.applyTo fused with FocusDepth + Refraction
-__global__ void __launch_bounds__(256)
-k_rubin_optics(const __grid_constant__ DevOptics o, const __grid_constant__ B2OpticsOptions opt, int64_t n,
+__device__ __forceinline__ void
+rubin_optics_body(const DevOptics& o, const B2OpticsOptions& opt, int64_t n,
                double* __restrict__ x, double* __restrict__ y, double* __restrict__ dxdz, double* __restrict__ dydz,
                double* __restrict__ flux, const double* __restrict__ wl_nm, const double* __restrict__ pu,
                const double* __restrict__ pv, const double* __restrict__ time, const double* __restrict__ gauss,
@@ -664,6 +688,20 @@ k_rubin_optics(const __grid_constant__ DevOptics o, const __grid_constant__ B2Op
         }
     }
 }
+
+#define B2_OPTICS_ARGS                                                                                         \
+    const __grid_constant__ DevOptics o, const __grid_constant__ B2OpticsOptions opt, int64_t n,                   \
+        double *__restrict__ x, double *__restrict__ y, double *__restrict__ dxdz, double *__restrict__ dydz,     \
+        double *__restrict__ flux, const double *__restrict__ wl_nm, const double *__restrict__ pu,               \
+        const double *__restrict__ pv, const double *__restrict__ time, const double *__restrict__ gauss,         \
+        double *__restrict__ time_out, unsigned long long *__restrict__ stats
+#define B2_OPTICS_CALL rubin_optics_body(o, opt, n, x, y, dxdz, dydz, flux, wl_nm, pu, pv, time, gauss, time_out, stats)
+// The trace is latency bound on dependent FP64 chains (ncu: stall "wait" dominates at 4 warps per
+// scheduler), so resident warps matter more than a few spilled registers: three builds of the same
+// body at 2 / 3 / 4 blocks per SM; B2_OPTICS_OCC picks one (default set from measurements).
+__global__ void __launch_bounds__(256, 2) k_rubin_optics(B2_OPTICS_ARGS) { B2_OPTICS_CALL; }
+__global__ void __launch_bounds__(256, 3) k_rubin_optics_occ3(B2_OPTICS_ARGS) { B2_OPTICS_CALL; }
+__global__ void __launch_bounds__(256, 4) k_rubin_optics_occ4(B2_OPTICS_ARGS) { B2_OPTICS_CALL; }
 
 // RubinDiffraction.applyTo
 __global__ void __launch_bounds__(256)
@@ -825,6 +863,19 @@ extern "C" int b2_telescope_upload(b2_ctx* ctx, const B2Telescope* tel) {
             if (ob.kind == B2_OBSC_RECTANGLE) { dob.p[0] = ob.p[0] / 2; dob.p[1] = ob.p[1] / 2; }
             if (ob.kind == B2_OBSC_RAY) dob.p[0] = ob.p[0] / 2;
         }
+        d.simple_clear = 0;
+        if (s.n_obsc == 1 && s.obsc[0].negate) {
+            const B2Obsc& ob = s.obsc[0];
+            if (ob.kind == B2_OBSC_CIRCLE && ob.p[1] == 0.0 && ob.p[2] == 0.0) {
+                d.simple_clear = 1;
+                d.clr_in2 = -1.0;
+                d.clr_out2 = ob.p[0] * ob.p[0];
+            } else if (ob.kind == B2_OBSC_ANNULUS && ob.p[2] == 0.0 && ob.p[3] == 0.0) {
+                d.simple_clear = 1;
+                d.clr_in2 = ob.p[0] * ob.p[0];
+                d.clr_out2 = ob.p[1] * ob.p[1];
+            }
+        }
         d.poly_n = s.poly_n;
         d.poly_scale = s.poly_scale;
         d.extra = nullptr;
@@ -942,6 +993,32 @@ extern "C" int b2_trace_rays(b2_ctx* ctx, int64_t n, double* x, double* y, doubl
     return 0;
 }
 
+static int optics_occ() {
+    static int occ = -1;
+    if (occ < 0) {
+        const char* e = getenv("B2_OPTICS_OCC");
+        occ = e ? atoi(e) : 3;
+        if (occ < 2 || occ > 4) occ = 3;
+    }
+    return occ;
+}
+
+static void launch_rubin_optics(b2_ctx* ctx, const B2OpticsOptions& opt, int64_t n, double* x, double* y, double* dxdz,
+                                double* dydz, double* flux, const double* wl, const double* pu, const double* pv,
+                                const double* time, const double* gauss, double* time_out, unsigned long long* stats) {
+    B2_TIMED("k_rubin_optics", ctx->stream);
+    switch (optics_occ()) {
+        case 2:
+            k_rubin_optics<<<nblocks(n), 256, 0, ctx->stream>>>(ctx->opt, opt, n, x, y, dxdz, dydz, flux, wl, pu, pv, time, gauss, time_out, stats);
+            break;
+        case 4:
+            k_rubin_optics_occ4<<<nblocks(n), 256, 0, ctx->stream>>>(ctx->opt, opt, n, x, y, dxdz, dydz, flux, wl, pu, pv, time, gauss, time_out, stats);
+            break;
+        default:
+            k_rubin_optics_occ3<<<nblocks(n), 256, 0, ctx->stream>>>(ctx->opt, opt, n, x, y, dxdz, dydz, flux, wl, pu, pv, time, gauss, time_out, stats);
+    }
+}
+
 extern "C" int b2_rubin_optics(b2_ctx* ctx, int64_t n, double* x, double* y, double* dxdz, double* dydz, double* flux,
                                const double* wl_nm, const double* pu, const double* pv, const double* time,
                                const double* gauss, double* time_out, const B2OpticsOptions* opt, int where,
@@ -974,8 +1051,8 @@ extern "C" int b2_rubin_optics(b2_ctx* ctx, int64_t n, double* x, double* y, dou
         H2D(dv, pv, n);
         H2D(dt, time, n);
         if (gauss) H2D(dg, gauss, n);
-        k_rubin_optics<<<nblocks(n), 256, 0, ctx->stream>>>(ctx->opt, *opt, n, dx, dy, da, db, df, dw, du, dv, dt,
-                                                            gauss ? dg : nullptr, time_out ? dto : nullptr, dstats);
+        launch_rubin_optics(ctx, *opt, n, dx, dy, da, db, df, dw, du, dv, dt, gauss ? dg : nullptr,
+                            time_out ? dto : nullptr, dstats);
         B2_CHECK_LAUNCH();
         D2H(x, dx, n);
         D2H(y, dy, n);
@@ -986,8 +1063,7 @@ extern "C" int b2_rubin_optics(b2_ctx* ctx, int64_t n, double* x, double* y, dou
         if (stats) B2_CUDA(cudaMemcpyAsync(stats, dstats, sizeof(*stats), cudaMemcpyDeviceToHost, ctx->stream));
         B2_CUDA(cudaStreamSynchronize(ctx->stream));
     } else {
-        k_rubin_optics<<<nblocks(n), 256, 0, ctx->stream>>>(ctx->opt, *opt, n, x, y, dxdz, dydz, flux, wl_nm, pu, pv,
-                                                            time, gauss, time_out, dstats);
+        launch_rubin_optics(ctx, *opt, n, x, y, dxdz, dydz, flux, wl_nm, pu, pv, time, gauss, time_out, dstats);
         B2_CHECK_LAUNCH();
         if (stats) {
             B2_CUDA(cudaMemcpyAsync(stats, dstats, sizeof(*stats), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1052,6 +1128,7 @@ extern "C" int b2_sample_time_pupil(b2_ctx* ctx, int64_t n, double* time, double
         }
         B2_CUDA(cudaStreamSynchronize(ctx->stream));
     } else {
+        B2_TIMED("k_sample_time_pupil", ctx->stream);
         k_sample_time_pupil<<<nblocks(n), 256, 0, ctx->stream>>>(n, time, pu, pv, t0, exptime, r_in, r_out, seed, offset);
         B2_CHECK_LAUNCH();
     }

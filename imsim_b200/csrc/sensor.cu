@@ -822,6 +822,7 @@ extern "C" int b2_sensor_read_image(b2_sensor* s, void* pixels, int where) {
 }
 
 static int launch_add_delta(b2_sensor* s, double sign, int clear) {
+    B2_TIMED("k_add_delta", s->ctx->stream);
     DevSensor& d = s->d;
     size_t n = (size_t)d.nx * d.ny;
     int nb = (int)((n + 255) / 256);
@@ -836,6 +837,7 @@ static int launch_update_distortions(b2_sensor* s, bool from_target) {
     DevSensor& d = s->d;
     b2_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
+    B2_TIMED("update_distortions(total)", st);
     B2_CUDA(cudaMemsetAsync(s->changed, 0, (size_t)d.nx * d.ny, st));
     B2_CUDA(cudaMemsetAsync(s->tiles, 0, (size_t)s->tnx * s->tny, st));
     dim3 gt = grid2(d.nx, d.ny, 256);
@@ -862,6 +864,7 @@ static int launch_update_distortions(b2_sensor* s, bool from_target) {
 }
 
 static int launch_bounds_update(b2_sensor* s, int all) {
+    B2_TIMED("k_update_bounds", s->ctx->stream);
     DevSensor& d = s->d;
     k_update_bounds<<<grid2(d.nx, d.ny, 256), 256, 0, s->ctx->stream>>>(d, s->changed, all, s->tiles, s->tnx, s->tny);
     B2_CHECK_LAUNCH();
@@ -877,6 +880,7 @@ static int sensor_update(b2_sensor* s) {
 }
 
 static int init_boundaries(b2_sensor* s, int ocx, int ocy) {
+    B2_TIMED("k_init_boundaries", s->ctx->stream);
     DevSensor& d = s->d;
     k_init_boundaries<<<grid2(d.nx + 1, d.ny + 1, 256), 256, 0, s->ctx->stream>>>(d, ocx, ocy);
     B2_CHECK_LAUNCH();
@@ -976,6 +980,7 @@ extern "C" int b2_sensor_accumulate(b2_sensor* s, int64_t n, const double* x, co
         bool hit = ib < bounds.size();
         int64_t cnt = i2 - i1;
         if (cnt > 0) {
+            B2_TIMED("k_accumulate", st);
             k_accumulate<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d, i1, i2, n, dx, dy, da, db, dw, df, dr, seed,
                                                                          offset, s->dstats, s->dadded);
             B2_CHECK_LAUNCH();

@@ -223,6 +223,9 @@ int b2_ctx_synchronize(b2_ctx* ctx);
    non-tensor FMA rate (fp64 != 0: double, else float) in TFLOP/s.  The roofline
    denominator of the compute-bound trace kernel (MEASURED_PEAKS.json has none). */
 int b2_fma_peak(b2_ctx* ctx, int32_t fp64, double* tflops);
+/* measurement aid: with B2_TIMING=1 in the environment every kernel launch is bracketed by CUDA
+   events on its stream; this returns {"kernel": [launches, total_ms], ...} as JSON and clears the log */
+int b2_timing_report(char* buf, int64_t cap);
 
 /* replaces: base['det_telescope'] (imsim/telescope_loader.py:463) as consumed by
    imsim/photon_ops.py:108-123 */
