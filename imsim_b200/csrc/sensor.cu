@@ -14,6 +14,8 @@
 //   target T [ny][nx]                 the image (float32 or float64)
 // A pixel's polygon is 3 contiguous segments: H[y][x][0..nv+2), H[y+1][x][0..nv+2)
 // and V[y][x][0..2nv) (its own left edge followed by the right neighbour's).
+#include <cstdlib>
+
 #include "b2_common.cuh"
 
 #define PI_D 3.14159265358979323846
@@ -514,13 +516,128 @@ k_update_distortions(const __grid_constant__ DevSensor s, const CT* __restrict__
     }
 }
 
+// Tiled version for NV <= 8 (the models imSim ships: 4 and 8 vertices per edge).
+// One block = 32 x 8 boundary slots.  The charge halo of the tile (39 x 15 pixels for qdist = 3) is
+// staged in shared memory together with one occupancy bit word per halo row, so a slot only visits
+// the pixels that actually hold charge (photon pools are sparse outside star cores), in the
+// reference's (row, column) order; its boundary points live in registers and are written back once.
+// Arithmetic per visited pixel is identical to k_update_distortions (bit-identical results).
+template <typename CT, int NV>
+__global__ void __launch_bounds__(256)
+k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __restrict__ charge,
+                           uint8_t* __restrict__ changed) {
+    constexpr int TX = 32, TY = 8, HW = 64, MAXHR = 24;
+    extern __shared__ unsigned char smem_raw[];
+    const int q = s.qdist;
+    const int hrows = TY + 2 * q + 1;  // <= MAXHR
+    const int hcols = TX + 2 * q + 1;  // <= HW
+    double* sc = reinterpret_cast<double*>(smem_raw);                       // [hrows][HW]
+    unsigned long long* rowbits = reinterpret_cast<unsigned long long*>(sc + MAXHR * HW);  // [MAXHR]
+    float2* KH = reinterpret_cast<float2*>(rowbits + MAXHR);
+    const int nKH = s.nx9 * s.ny9 * (NV + 2), nKV = s.nx9 * s.ny9 * NV;
+    float2* KV = KH + nKH;
+    const int tid = threadIdx.y * TX + threadIdx.x;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int nx = s.nx, ny = s.ny;
+    // stage the halo: warp w takes halo rows w, w + 8, w + 16
+    const int lane = tid & 31, warp = tid >> 5;
+    bool any_local = false;
+    for (int r = warp; r < hrows; r += 8) {
+        int gy = y0 - q - 1 + r;
+        unsigned long long bits = 0ull;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            int c = lane + 32 * half;
+            int gx = x0 - q - 1 + c;
+            double v = 0.0;
+            if (c < hcols && gx >= 0 && gx < nx && gy >= 0 && gy < ny) v = (double)charge[(size_t)gy * nx + gx];
+            sc[r * HW + c] = v;
+            unsigned b = __ballot_sync(0xffffffffu, v != 0.0);
+            bits |= (unsigned long long)b << (32 * half);
+        }
+        if (lane == 0) rowbits[r] = bits;
+        any_local |= (bits != 0ull);
+    }
+    if (!__syncthreads_or(any_local)) return;  // no charge within reach of this tile
+    for (int k = tid; k < nKH; k += 256) KH[k] = s.KH[k];
+    for (int k = tid; k < nKV; k += 256) KV[k] = s.KV[k];
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int cxk = (s.nx9 - 1) / 2, cyk = (s.ny9 - 1) / 2;
+    // ---- horizontal slot: rows j = y-q-1 .. y+q (halo rows ty .. ty+2q+1), cols i = x-q .. x+q
+    if (x < nx && y <= ny) {
+        const unsigned wmask = (1u << (2 * q + 1)) - 1u;
+        bool any = false;
+        for (int dj = 0; dj < 2 * q + 2; ++dj) any |= ((unsigned)(rowbits[ty + dj] >> (tx + 1)) & wmask) != 0u;
+        if (any) {
+            float2* hp = s.H + Hidx(s, x, y);
+            float2 h[NV + 2];
+#pragma unroll
+            for (int k = 0; k < NV + 2; ++k) h[k] = hp[k];
+#pragma unroll 1
+            for (int dj = 0; dj < 2 * q + 2; ++dj) {
+                unsigned bits = (unsigned)(rowbits[ty + dj] >> (tx + 1)) & wmask;
+                while (bits) {
+                    int di = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    double c = sc[(ty + dj) * HW + tx + 1 + di];
+                    const float2* kh = KH + ((q + 1 - dj + cyk) * s.nx9 + (q - di + cxk)) * (NV + 2);
+#pragma unroll
+                    for (int k = 0; k < NV + 2; ++k) {
+                        float2 d = kh[k];
+                        h[k].x = (float)__dadd_rn((double)h[k].x, __dmul_rn((double)d.x, c));
+                        h[k].y = (float)__dadd_rn((double)h[k].y, __dmul_rn((double)d.y, c));
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NV + 2; ++k) hp[k] = h[k];
+            if (y < ny) changed[(size_t)y * nx + x] = 1;
+            if (y > 0) changed[(size_t)(y - 1) * nx + x] = 1;
+        }
+    }
+    // ---- vertical slot: rows j = y-q .. y+q (halo rows ty+1 .. ty+2q+1), cols i = x-q-1 .. x+q
+    if (x <= nx && y < ny) {
+        const unsigned wmask = (1u << (2 * q + 2)) - 1u;
+        bool any = false;
+        for (int dj = 1; dj < 2 * q + 2; ++dj) any |= ((unsigned)(rowbits[ty + dj] >> tx) & wmask) != 0u;
+        if (any) {
+            float2* vp = s.V + Vidx(s, x, y);
+            float2 v[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) v[k] = vp[k];
+#pragma unroll 1
+            for (int dj = 1; dj < 2 * q + 2; ++dj) {
+                unsigned bits = (unsigned)(rowbits[ty + dj] >> tx) & wmask;
+                while (bits) {
+                    int di = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    double c = sc[(ty + dj) * HW + tx + di];
+                    const float2* kv = KV + ((q + 1 - dj + cyk) * s.nx9 + (q + 1 - di + cxk)) * NV;
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) {
+                        float2 d = kv[k];
+                        v[k].x = (float)__dadd_rn((double)v[k].x, __dmul_rn((double)d.x, c));
+                        v[k].y = (float)__dadd_rn((double)v[k].y, __dmul_rn((double)d.y, c));
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NV; ++k) vp[k] = v[k];
+            if (x < nx) changed[(size_t)y * nx + x] = 1;
+            if (x > 0) changed[(size_t)y * nx + x - 1] = 1;
+        }
+    }
+}
+
 // Silicon::updatePixelBounds for every pixel (all = 1) or the flagged ones
 __global__ void __launch_bounds__(256)
 k_update_bounds(const __grid_constant__ DevSensor s, const uint8_t* __restrict__ changed, int all,
                 const uint8_t* __restrict__ tiles, int tnx, int tny) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y;
-    if (!all) {
+    if (!all && tiles != nullptr) {
         int xs = blockIdx.x * blockDim.x;
         if (!tiles_any(tiles, tnx, tny, xs - s.qdist - 2, xs + (int)blockDim.x + s.qdist + 1, y - s.qdist - 2,
                        y + s.qdist + 1, s.nx, s.ny))
@@ -832,6 +949,25 @@ static int launch_add_delta(b2_sensor* s, double sign, int clear) {
     return 0;
 }
 
+template <typename CT>
+static int launch_update_tiled(b2_sensor* s, const CT* charge) {
+    DevSensor& d = s->d;
+    cudaStream_t st = s->ctx->stream;
+    size_t smem = (size_t)24 * 64 * sizeof(double) + 24 * sizeof(unsigned long long) +
+                  (size_t)d.nx9 * d.ny9 * (2 * d.nv + 2) * sizeof(float2);
+    dim3 block(32, 8, 1);
+    dim3 grid((d.nx + 1 + 31) / 32, (d.ny + 1 + 7) / 8, 1);
+    if (d.nv == 4) {
+        if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(k_update_distortions_tiled<CT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_update_distortions_tiled<CT, 4><<<grid, block, smem, st>>>(d, charge, s->changed);
+    } else {
+        if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(k_update_distortions_tiled<CT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_update_distortions_tiled<CT, 8><<<grid, block, smem, st>>>(d, charge, s->changed);
+    }
+    B2_CHECK_LAUNCH();
+    return 0;
+}
+
 // charge_from_target: distortions from the bound image (initialize) or from delta (update)
 static int launch_update_distortions(b2_sensor* s, bool from_target) {
     DevSensor& d = s->d;
@@ -839,6 +975,12 @@ static int launch_update_distortions(b2_sensor* s, bool from_target) {
     cudaStream_t st = ctx->stream;
     B2_TIMED("update_distortions(total)", st);
     B2_CUDA(cudaMemsetAsync(s->changed, 0, (size_t)d.nx * d.ny, st));
+    const bool tiled = (d.nv == 4 || d.nv == 8) && d.qdist <= 7 && getenv("B2_UPDATE_GENERIC") == nullptr;
+    if (tiled) {
+        if (!from_target) return launch_update_tiled<double>(s, d.delta);
+        if (d.dtype_bytes == 4) return launch_update_tiled<float>(s, (const float*)d.target);
+        return launch_update_tiled<double>(s, (const double*)d.target);
+    }
     B2_CUDA(cudaMemsetAsync(s->tiles, 0, (size_t)s->tnx * s->tny, st));
     dim3 gt = grid2(d.nx, d.ny, 256);
     size_t smem = ((size_t)d.nx9 * d.ny9 * (2 * d.nv + 2)) * sizeof(float2);
@@ -866,7 +1008,9 @@ static int launch_update_distortions(b2_sensor* s, bool from_target) {
 static int launch_bounds_update(b2_sensor* s, int all) {
     B2_TIMED("k_update_bounds", s->ctx->stream);
     DevSensor& d = s->d;
-    k_update_bounds<<<grid2(d.nx, d.ny, 256), 256, 0, s->ctx->stream>>>(d, s->changed, all, s->tiles, s->tnx, s->tny);
+    const bool tiled = (d.nv == 4 || d.nv == 8) && d.qdist <= 7 && getenv("B2_UPDATE_GENERIC") == nullptr;
+    k_update_bounds<<<grid2(d.nx, d.ny, 256), 256, 0, s->ctx->stream>>>(d, s->changed, all, tiled ? nullptr : s->tiles,
+                                                                       s->tnx, s->tny);
     B2_CHECK_LAUNCH();
     return 0;
 }
