@@ -107,6 +107,15 @@ class B2OpticsOptions(C.Structure):
         ("index_ratio", C.c_double),
         ("seed", C.c_uint64),
         ("photon_offset", C.c_uint64),
+        ("do_dcr", C.c_int32),
+        ("pad", C.c_int32),
+        ("dcr_base_wavelength", C.c_double),
+        ("dcr_alpha", C.c_double),
+        ("dcr_center", C.c_double * 2),
+        ("dcr_base_refraction", C.c_double),
+        ("dcr_tanz", C.c_double),
+        ("dcr_pth", C.c_double * 3),
+        ("dcr_m", C.c_double * 2),
     ]
 
 

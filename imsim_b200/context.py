@@ -125,6 +125,15 @@ class OpticsContext:
                                                   _lib.ptr(pupil_v), t0, exptime, r_inner, r_outer, seed,
                                                   photon_offset, where))
 
+    def flat_photons(self, x, y, flux, wavelength, bounds, cdf=None, cdf_wave=None, seed=0, photon_offset=0):
+        """Uniform unit-flux photons over ``bounds = (xlo, xhi, ylo, yhi)`` (+ wavelengths from an
+        inverse-CDF table) written straight into device arrays (imsim/flat.py:239-259)."""
+        ncdf = 0 if cdf is None else int(cdf.shape[0])
+        _lib.check(self._lib.b2_flat_photons(self._h, x.shape[0], _lib.ptr(x), _lib.ptr(y), _lib.ptr(flux),
+                                             _lib.ptr(wavelength), float(bounds[0]), float(bounds[1]),
+                                             float(bounds[2]), float(bounds[3]), _lib.ptr(cdf), _lib.ptr(cdf_wave),
+                                             ncdf, int(seed), int(photon_offset)))
+
     @property
     def handle(self):
         return self._h

@@ -77,6 +77,20 @@ __device__ __forceinline__ double medium_n(const B2Medium& m, double wl) {
     }
 }
 
+// galsim.dcr.air_refractive_index_minus_one / get_refraction (wave in nm), used by PhotonDCR
+__device__ __forceinline__ double dcr_refraction(double wave_nm, const double pth[3], double tanz) {
+    double P = pth[0] * 7.50061683;
+    double T = pth[1] - 273.15;
+    double W = pth[2] * 7.50061683;
+    double wu = wave_nm * 1.e-3;
+    double s2 = b2rcp(wu * wu);
+    double nm1 = (64.328 + 29498.1 * b2rcp(146.0 - s2) + 255.4 * b2rcp(41.0 - s2)) * 1.e-6;
+    nm1 *= P * (1.0 + (1.049 - 0.0157 * T) * 1.e-6 * P) / (720.883 * (1.0 + 0.003661 * T));
+    nm1 -= (0.0624 - 0.000680 * s2) / (1.0 + 0.003661 * T) * W * 1.e-6;
+    double r0 = nm1 * (nm1 + 2.0) * 0.5 * b2rcp(nm1 * nm1 + 2.0 * nm1 + 1.0);
+    return r0 * tanz;
+}
+
 // ------------------------------------------------------------------ TAN-SIP
 // packed triangle index for (i,j), i+j<=3, order: 00 01 02 03 10 11 12 20 21 30
 //   f(u,v) = sum ab[i][j] u^i v^j
@@ -619,6 +633,16 @@ rubin_optics_body(const DevOptics& o, const B2OpticsOptions& opt, int64_t n,
         double xi = x[i], yi = y[i];
         double wl = wl_nm[i] * 1e-9;
         double u = pu[i], v = pv[i];
+        if (opt.do_dcr) {  // galsim.PhotonDCR.applyTo
+            if (opt.dcr_alpha != 0.0) {
+                double sc = pow(wl_nm[i] / opt.dcr_base_wavelength, opt.dcr_alpha);
+                xi = sc * (xi - opt.dcr_center[0]) + opt.dcr_center[0];
+                yi = sc * (yi - opt.dcr_center[1]) + opt.dcr_center[1];
+            }
+            double shift = dcr_refraction(wl_nm[i], opt.dcr_pth, opt.dcr_tanz) - opt.dcr_base_refraction;
+            xi += shift * opt.dcr_m[0];
+            yi += shift * opt.dcr_m[1];
+        }
         if (opt.shift_in) {
             xi += opt.stamp_center[0];
             yi += opt.stamp_center[1];
@@ -751,6 +775,35 @@ k_sample_time_pupil(int64_t n, double* __restrict__ time, double* __restrict__ p
         sincospi(2.0 * uphi, &s, &c);
         pu[i] = rr * c;
         pv[i] = rr * s;
+    }
+}
+
+// uniform photons over a rectangle with unit flux (imsim/flat.py:246-257) and wavelengths drawn from
+// a tabulated inverse CDF (the role of galsim.WavelengthSampler, flat.py:177,259)
+__global__ void __launch_bounds__(256)
+k_flat_photons(int64_t n, double* __restrict__ x, double* __restrict__ y, double* __restrict__ flux,
+               double* __restrict__ wl, double xlo, double xhi, double ylo, double yhi,
+               const double* __restrict__ cdf, const double* __restrict__ cdf_wave, int ncdf, uint64_t seed,
+               uint64_t offset) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t r[4], q[4];
+    philox4(seed, offset + (uint64_t)i, 5u, r);
+    x[i] = xlo + (xhi - xlo) * u01(r[0], r[1]);
+    y[i] = ylo + (yhi - ylo) * u01(r[2], r[3]);
+    flux[i] = 1.0;
+    if (wl) {
+        philox4(seed, offset + (uint64_t)i, 6u, q);
+        double u = u01(q[0], q[1]);
+        // largest k with cdf[k] <= u, then linear in the bin (piecewise-constant pdf)
+        int lo = 0, hi = ncdf - 1;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (__ldg(cdf + mid) <= u) lo = mid; else hi = mid;
+        }
+        double c0 = __ldg(cdf + lo), c1 = __ldg(cdf + hi);
+        double f = (c1 > c0) ? (u - c0) / (c1 - c0) : 0.0;
+        wl[i] = __ldg(cdf_wave + lo) + f * (__ldg(cdf_wave + hi) - __ldg(cdf_wave + lo));
     }
 }
 
@@ -1175,5 +1228,18 @@ extern "C" int b2_fma_peak(b2_ctx* ctx, int32_t fp64, double* tflops) {
     cudaEventDestroy(e1);
     double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
     *tflops = flops / (best * 1e-3) / 1e12;
+    return 0;
+}
+
+extern "C" int b2_flat_photons(b2_ctx* ctx, int64_t n, double* x, double* y, double* flux, double* wl, double xlo,
+                               double xhi, double ylo, double yhi, const double* cdf, const double* cdf_wave,
+                               int32_t ncdf, uint64_t seed, uint64_t offset) {
+    B2_REQUIRE(ctx && x && y && flux, "b2_flat_photons: null argument");
+    B2_REQUIRE(!wl || (cdf && cdf_wave && ncdf >= 2), "b2_flat_photons: wavelength sampling needs a CDF table");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    if (n <= 0) return 0;
+    B2_TIMED("k_flat_photons", ctx->stream);
+    k_flat_photons<<<nblocks(n), 256, 0, ctx->stream>>>(n, x, y, flux, wl, xlo, xhi, ylo, yhi, cdf, cdf_wave, ncdf, seed, offset);
+    B2_CHECK_LAUNCH();
     return 0;
 }

@@ -1,0 +1,96 @@
+"""Flat-field production on the B200 (mirror of ``LSST_FlatBuilder.addNoise``,
+imsim/flat.py:133-281).
+
+The reference builds the CCD in ``nx x ny`` sections with a ``buffer_size``
+border, ``niter = ceil(counts / max_counts_per_iter)`` iterations per section:
+
+* no ``sed`` (examples/flat.yaml): ``area = sensor.calculate_pixel_areas(section)``,
+  ``temp = base * area / mean(area)``, Poisson realisation, ``section += temp``
+  (flat.py:220-237) -- the areas come from ``k_pixel_areas``; the Poisson draw is
+  host numpy in this round;
+* ``sed`` given (examples/flat_with_sed.yaml): Poisson number of photons uniform
+  over the bordered section, wavelengths from SED x bandpass,
+  ``sensor.accumulate(photons, section, resume=(it > 0))`` with
+  ``nrecalc = 1e4 * xsize * ysize / (nx * ny)`` (flat.py:96-101,239-264) -- photons
+  are generated in HBM (``k_flat_photons``) and never touch the host.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+
+from .sensor import Image, SiliconSensor
+
+
+def flat_nrecalc(xsize, ysize, nx, ny) -> float:
+    """imsim/flat.py:96-101: recalc every 10,000 electrons per pixel of a section."""
+    return 10_000 * xsize * ysize / (nx * ny)
+
+
+def wavelength_cdf(wave_nm, weight):
+    """Tabulated CDF of ``sed(w) * bandpass(w)`` on ``wave_nm`` (trapezoid), for ``k_flat_photons``."""
+    wave_nm = np.ascontiguousarray(wave_nm, dtype=np.float64)
+    w = np.asarray(weight, dtype=np.float64)
+    c = np.concatenate([[0.0], np.cumsum(0.5 * (w[1:] + w[:-1]) * np.diff(wave_nm))])
+    return np.ascontiguousarray(c / c[-1]), wave_nm
+
+
+def build_flat(image: Image, counts_per_pixel: float, sensor: Optional[SiliconSensor], rng=None,
+               max_counts_per_iter: float = 1000.0, nx: int = 8, ny: int = 2, buffer_size: int = 5,
+               sed_cdf=None, base_level: Optional[Callable] = None, logger=None):
+    """Add a flat field of ``counts_per_pixel`` electrons to ``image`` in place
+    (``LSST_FlatBuilder.addNoise``).  ``sed_cdf = wavelength_cdf(...)`` selects the
+    photon-shot branch; otherwise the pixel-area branch.  ``rng``: numpy Generator / seed.
+    Returns the number of photons shot (0 in the area branch)."""
+    gen = rng if isinstance(rng, np.random.Generator) else np.random.default_rng(rng)
+    niter = int(np.ceil(counts_per_pixel / max_counts_per_iter))
+    counts_per_iter = counts_per_pixel / niter
+    nrow, ncol = image.array.shape
+    x0, y0 = image.xmin, image.ymin
+    dx, dy = ncol // nx, nrow // ny
+    tot_nphot = 0
+    if sed_cdf is not None:
+        import torch
+
+        from .photon_pooling import DevicePhotons
+
+        cdf, cdf_wave = (torch.as_tensor(a, device="cuda:%d" % sensor.ctx.device) for a in sed_cdf)
+    for i in range(nx):
+        xmin = i * dx + x0
+        xmax = (i + 1) * dx + x0 - 1
+        if i == nx - 1:
+            xmax = ncol + x0 - 1
+        for j in range(ny):
+            ymin = j * dy + y0
+            ymax = (j + 1) * dy + y0 - 1
+            if j == ny - 1:
+                ymax = nrow + y0 - 1
+            # section with border (flat.py:209-213); it may stick out of the image like the reference's
+            bx0, bx1, by0, by1 = xmin - buffer_size, xmax + buffer_size, ymin - buffer_size, ymax + buffer_size
+            sec = Image(np.zeros((by1 - by0 + 1, bx1 - bx0 + 1), dtype=image.array.dtype), bx0, by0)
+            for it in range(niter):
+                if sed_cdf is None:
+                    area = sensor.calculate_pixel_areas(sec) if sensor is not None else 1.0
+                    temp = np.full(sec.array.shape, counts_per_iter, dtype=np.float64)
+                    if base_level is not None:
+                        temp *= base_level(sec)
+                    if not isinstance(area, float):
+                        temp *= area.array / np.mean(area.array)
+                    sec.array[:, :] += gen.poisson(temp).astype(sec.array.dtype)
+                else:
+                    nphot = int(gen.poisson(counts_per_iter * sec.array.size))
+                    dp = DevicePhotons(nphot, device="cuda:%d" % sensor.ctx.device,
+                                       fields=("x", "y", "flux", "wavelength"))
+                    sensor.ctx.flat_photons(dp.x, dp.y, dp.flux, dp.wavelength,
+                                            (bx0 - 0.5, bx1 + 0.5, by0 - 0.5, by1 + 0.5), cdf, cdf_wave,
+                                            seed=int(gen.integers(1 << 62)), photon_offset=tot_nphot)
+                    sensor.accumulate(dp, sec, resume=(it > 0), sync_image=(it == niter - 1), want_stats=False)
+                    tot_nphot += nphot
+            # copy just the part that is officially part of this section (flat.py:266-267)
+            image.array[ymin - y0:ymax - y0 + 1, xmin - x0:xmax - x0 + 1] += \
+                sec.array[buffer_size:buffer_size + (ymax - ymin + 1), buffer_size:buffer_size + (xmax - xmin + 1)]
+            if logger is not None:
+                logger.info("Done section %d,%d: mean level => %s", i, j,
+                            image.array[ymin - y0:ymax - y0 + 1, xmin - x0:xmax - x0 + 1].mean())
+    return tot_nphot

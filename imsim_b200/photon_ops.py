@@ -325,3 +325,45 @@ def make_rubin_diffraction_optics(telescope, boresight, img_wcs, icrf_to_field, 
     return RubinDiffractionOptics(telescope=telescope, boresight=boresight, stamp_center=stamp_center,
                                   det_name=det_name, camera=camera, rubin_diffraction=rd,
                                   shift_photons=shift_photons, device=device)
+
+
+def air_refractive_index_minus_one(wave_nm, pressure=69.328, temperature=293.15, H2O_pressure=1.067):
+    """galsim.dcr.air_refractive_index_minus_one (Filippenko 1982); host helper for set-up."""
+    P = pressure * 7.50061683
+    T = temperature - 273.15
+    W = H2O_pressure * 7.50061683
+    sigma_squared = 1.0 / (np.asarray(wave_nm, float) * 1.e-3) ** 2.0
+    n_minus_one = (64.328 + (29498.1 / (146.0 - sigma_squared)) + (255.4 / (41.0 - sigma_squared))) * 1.e-6
+    n_minus_one *= P * (1.0 + (1.049 - 0.0157 * T) * 1.e-6 * P) / (720.883 * (1.0 + 0.003661 * T))
+    n_minus_one -= (0.0624 - 0.000680 * sigma_squared) / (1.0 + 0.003661 * T) * W * 1.e-6
+    return n_minus_one
+
+
+def get_refraction(wave_nm, zenith_angle, **kwargs):
+    """galsim.dcr.get_refraction [radians]."""
+    nm1 = air_refractive_index_minus_one(wave_nm, **kwargs)
+    r0 = nm1 * (nm1 + 2) / 2.0 / (nm1**2 + 2 * nm1 + 1)
+    return r0 * np.tan(zenith_angle)
+
+
+def set_dcr_options(opt: _abi.B2OpticsOptions, base_wavelength, zenith_angle, parallactic_angle, jacobian,
+                    center=(0.0, 0.0), alpha=0.0, scale_unit_rad=np.pi / (180.0 * 3600.0), pressure=69.328,
+                    temperature=293.15, H2O_pressure=1.067):
+    """Arm the fused ``galsim.PhotonDCR`` prologue of ``b2_rubin_optics``
+    (config/imsim-config.yaml:290-296).  ``jacobian``: local WCS [[dudx, dudy], [dvdx, dvdy]]
+    in ``scale_unit`` (arcsec) per pixel; the op moves photons by J^-1 (-s sin q, s cos q) with
+    s = refraction(w) - refraction(base) expressed in ``scale_unit``."""
+    J = np.asarray(jacobian, float).reshape(2, 2)
+    Ji = np.linalg.inv(J)
+    d = np.array([-np.sin(parallactic_angle), np.cos(parallactic_angle)]) / scale_unit_rad
+    m = Ji @ d
+    opt.do_dcr = 1
+    opt.dcr_base_wavelength = float(base_wavelength)
+    opt.dcr_alpha = float(alpha)
+    opt.dcr_center[0], opt.dcr_center[1] = float(center[0]), float(center[1])
+    opt.dcr_base_refraction = float(get_refraction(base_wavelength, zenith_angle, pressure=pressure,
+                                                   temperature=temperature, H2O_pressure=H2O_pressure))
+    opt.dcr_tanz = float(np.tan(zenith_angle))
+    opt.dcr_pth[0], opt.dcr_pth[1], opt.dcr_pth[2] = pressure, temperature, H2O_pressure
+    opt.dcr_m[0], opt.dcr_m[1] = float(m[0]), float(m[1])
+    return opt

@@ -277,6 +277,16 @@ class SiliconSensor:
         return (np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(f, dtype=np.float64),
                 None if y2 is None else np.ascontiguousarray(y2, dtype=np.float64))
 
+    @classmethod
+    def simple_treerings(cls, amplitude=0.5, period=100., r_max=8000., dr=None):
+        """``galsim.SiliconSensor.simple_treerings``: a cosine tree-ring table (used by
+        tests/test_flats.py:135 of the reference)."""
+        k = 2. * np.pi / float(period)
+        if dr is None:
+            dr = period / 100.
+        npoints = int(r_max / dr) + 1
+        return RadialTable.from_func(lambda r: amplitude * np.cos(k * r), x_min=0., x_max=r_max, npoints=npoints)
+
     # -- GalSim API ---------------------------------------------------------
     def updateRNG(self, rng):
         self._seed = _seed_from_rng(rng)

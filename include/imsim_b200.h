@@ -161,6 +161,17 @@ typedef struct {
     double index_ratio;
     uint64_t seed;          /* Philox key when gauss == NULL */
     uint64_t photon_offset; /* global index of photon 0 (Philox counter) */
+    /* galsim.PhotonDCR fused as prologue (config/imsim-config.yaml:290-296): applied to x, y
+       before anything else, like the op that precedes RubinDiffractionOptics in the list */
+    int32_t do_dcr;
+    int32_t pad;
+    double dcr_base_wavelength; /* nm */
+    double dcr_alpha;           /* (w / base)^alpha scaling about dcr_center; 0: none */
+    double dcr_center[2];       /* local_wcs.origin */
+    double dcr_base_refraction; /* get_refraction(base_wavelength, zenith) [rad] */
+    double dcr_tanz;            /* tan(zenith angle) */
+    double dcr_pth[3];          /* pressure [kPa], temperature [K], H2O pressure [kPa] */
+    double dcr_m[2];            /* pixel shift per radian of refraction: J^-1 (-sin q, cos q) * rad->scale_unit */
 } B2OpticsOptions;
 
 typedef struct {
@@ -267,6 +278,13 @@ int b2_rubin_diffraction(b2_ctx* ctx, int64_t n, double* x, double* y, const dou
 int b2_sample_time_pupil(b2_ctx* ctx, int64_t n, double* time, double* pupil_u, double* pupil_v,
                          double t0, double exptime, double r_inner, double r_outer,
                          uint64_t seed, uint64_t photon_offset, int where);
+
+/* uniform unit-flux photons over [xlo,xhi) x [ylo,yhi) and, if wl != NULL, wavelengths from a
+   tabulated inverse CDF (cdf[k] = P(wave <= cdf_wave[k]), k < ncdf): the photon generation of the
+   photon-shot flat, imsim/flat.py:239-259.  DEVICE pointers only (the pool never leaves HBM). */
+int b2_flat_photons(b2_ctx* ctx, int64_t n, double* x, double* y, double* flux, double* wl, double xlo, double xhi,
+                    double ylo, double yhi, const double* cdf, const double* cdf_wave, int32_t ncdf, uint64_t seed,
+                    uint64_t photon_offset);
 
 /* ---- silicon sensor ---------------------------------------------------- */
 /* replaces galsim.SiliconSensor.__init__ (imsim/lsst_image.py:93-103,

@@ -625,6 +625,20 @@ void orc_trace_rays(const B2Telescope* tel, const double* const* poly, const dou
     }
 }
 
+/* galsim/dcr.py: air_refractive_index_minus_one + get_refraction (wave in nm); third-party,
+   restated from the published formula (Filippenko 1982), parity unpinned */
+double orc_dcr_refraction(double wave_nm, const double pth[3], double tanz) {
+    double P = pth[0] * 7.50061683;
+    double T = pth[1] - 273.15;
+    double W = pth[2] * 7.50061683;
+    double sigma_squared = 1.0 / ((wave_nm * 1.e-3) * (wave_nm * 1.e-3));
+    double n_minus_one = (64.328 + (29498.1 / (146.0 - sigma_squared)) + (255.4 / (41.0 - sigma_squared))) * 1.e-6;
+    n_minus_one *= P * (1.0 + (1.049 - 0.0157 * T) * 1.e-6 * P) / (720.883 * (1.0 + 0.003661 * T));
+    n_minus_one -= (0.0624 - 0.000680 * sigma_squared) / (1.0 + 0.003661 * T) * W * 1.e-6;
+    double r0 = n_minus_one * (n_minus_one + 2) / 2.0 / (n_minus_one * n_minus_one + 2 * n_minus_one + 1);
+    return r0 * tanz;
+}
+
 /* ------------------------------------------------------------------ */
 /* RubinOptics.applyTo / RubinDiffractionOptics.applyTo                 */
 /* imsim/photon_ops.py:81-127, 136-148, 274-302, 486-503               */
@@ -643,6 +657,16 @@ void orc_rubin_optics(const B2Telescope* tel, const double* const* poly, const d
 #pragma omp parallel for schedule(static) reduction(+ : nvig, nfail, nz)
     for (int64_t i = 0; i < n; ++i) {
         double xi = x[i], yi = y[i];
+        if (opt->do_dcr) { /* galsim.PhotonDCR.applyTo, the op before the optics in the list */
+            if (opt->dcr_alpha != 0.0) {
+                double sc = pow(wavelength_nm[i] / opt->dcr_base_wavelength, opt->dcr_alpha);
+                xi = sc * (xi - opt->dcr_center[0]) + opt->dcr_center[0];
+                yi = sc * (yi - opt->dcr_center[1]) + opt->dcr_center[1];
+            }
+            double shift = orc_dcr_refraction(wavelength_nm[i], opt->dcr_pth, opt->dcr_tanz) - opt->dcr_base_refraction;
+            xi += shift * opt->dcr_m[0];
+            yi += shift * opt->dcr_m[1];
+        }
         if (opt->shift_in) { /* photon_ops.py:100-102 */
             xi += opt->stamp_center[0];
             yi += opt->stamp_center[1];

@@ -260,3 +260,42 @@ def test_zernike_and_bicubic_perturbations():
     _close(arrs[1][ok], ref[1][ok], scale=0.3)
     # and the perturbation does something (microns on the focal plane)
     assert np.abs(ref[0][ok] - base[0][ok]).max() > 1e-7
+
+
+def test_fused_photon_dcr():
+    """PhotonDCR prologue: GPU == oracle, and both equal an independent numpy evaluation of
+    galsim.dcr's formulas on the pre-trace shift (checked through the plain-optics difference)."""
+    from imsim_b200.photon_ops import get_refraction, set_dcr_options
+    from oracle import oracle as orc
+
+    su = helpers.oracle_setup()
+    ctx = _ctx(su, None)
+    p = helpers.test_photon_arrays(n=20000, center=(1200.0, 900.0))
+    p["wavelength"] = np.random.default_rng(8).uniform(380, 1000, p["x"].size)
+    opt = _abi.B2OpticsOptions()
+    zen, q = np.radians(40.0), np.radians(25.0)
+    J = np.array([[0.2 * np.cos(0.3), -0.2 * np.sin(0.3)], [0.2 * np.sin(0.3), 0.2 * np.cos(0.3)]])
+    set_dcr_options(opt, 622.0, zen, q, J, center=(1200.0, 900.0), alpha=-0.05)
+    ref = orc.rubin_optics(*su.telescope.flatten(), su.img_wcs.to_pod(), su.icrf_to_field.to_pod(),
+                           su.detector.to_pod(), None, opt, p["x"], p["y"], p["flux"], p["wavelength"], p["pupil_u"],
+                           p["pupil_v"], p["time"])
+    x, y, flux = p["x"].copy(), p["y"].copy(), p["flux"].copy()
+    dxdz, dydz = np.empty_like(x), np.empty_like(x)
+    ctx.rubin_optics(x, y, dxdz, dydz, flux, p["wavelength"], p["pupil_u"], p["pupil_v"], p["time"], options=opt)
+    ok = flux > 0
+    _close(x[ok], ref["x"][ok], scale=4000.0)
+    _close(y[ok], ref["y"][ok], scale=4000.0)
+    # independent numpy evaluation of the DCR shift: feed pre-shifted photons to the op without DCR
+    s = (get_refraction(p["wavelength"], zen) - get_refraction(622.0, zen)) * 206264.80624709636
+    du, dv = -s * np.sin(q), s * np.cos(q)
+    Ji = np.linalg.inv(J)
+    sc = (p["wavelength"] / 622.0) ** -0.05
+    xs = sc * (p["x"] - 1200.0) + 1200.0 + Ji[0, 0] * du + Ji[0, 1] * dv
+    ys = sc * (p["y"] - 900.0) + 900.0 + Ji[1, 0] * du + Ji[1, 1] * dv
+    assert np.abs(xs - p["x"]).max() > 0.5  # DCR moves blue photons by pixels at 40 deg zenith angle
+    x2, y2, f2 = xs.copy(), ys.copy(), p["flux"].copy()
+    ctx.rubin_optics(x2, y2, dxdz, dydz, f2, p["wavelength"], p["pupil_u"], p["pupil_v"], p["time"],
+                     options=_abi.B2OpticsOptions())
+    ok = (flux > 0) & (f2 > 0)
+    np.testing.assert_allclose(x[ok], x2[ok], rtol=0, atol=4e-7)
+    np.testing.assert_allclose(y[ok], y2[ok], rtol=0, atol=4e-7)
