@@ -14,6 +14,7 @@
 //   target T [ny][nx]                 the image (float32 or float64)
 // A pixel's polygon is 3 contiguous segments: H[y][x][0..nv+2), H[y+1][x][0..nv+2)
 // and V[y][x][0..2nv) (its own left edge followed by the right neighbour's).
+#include <algorithm>
 #include <cstdlib>
 
 #include "b2_common.cuh"
@@ -46,6 +47,7 @@ struct b2_sensor {
     std::vector<void*> owned;        // tables
     std::vector<void*> image_owned;  // per-image state
     bool bound = false, initialized = false;
+    int sm_count = 148;
     double accum_flux = 0.0;
     uint8_t* changed = nullptr;
     uint8_t* tiles = nullptr;  // charge occupancy per 32x32 tile
@@ -53,6 +55,8 @@ struct b2_sensor {
     unsigned long long* dstats = nullptr;  // device counters
     double* dadded = nullptr;
     Scratch cum;  // cumulative flux scratch
+    Scratch slow;  // compact list of photons that need the full polygon / neighbour treatment
+    unsigned long long* dnslow = nullptr;
 };
 
 enum { ST_POLY = 0, ST_NEIGH = 1, ST_NOTFOUND = 2, ST_B9 = 3, ST_DROP = 4, ST_N = 8 };
@@ -215,17 +219,31 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned v) {
 }
 
 // ------------------------------------------------------------------ accumulate
-// Silicon::accumulate over photons [i1, i2)
+// Silicon::accumulate over photons [i1, i2), in two phases so that warps stay converged:
+//   k_accumulate       every photon: conversion depth, diffusion, nominal pixel, inner-box test.
+//                      ~97 % of the photons are decided here and deposited.  The rest (outside the
+//                      inner bounding box of their nominal pixel) are appended to a compact list.
+//   k_accumulate_slow  the listed photons, all lanes busy: outer box, polygon test, neighbour
+//                      search, coin flip -- exactly the reference's sequence for those photons.
+// Deposits are atomic adds into `delta`, so the split does not change any result.
+struct SlowRec {
+    int ix, iy;
+    double x, y, zconv, flux;
+    int coin, pad;  // unf > 0.5
+};
+
 __global__ void __launch_bounds__(256)
 k_accumulate(const __grid_constant__ DevSensor s, int64_t i1, int64_t i2, int64_t ntot,
              const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ pdxdz,
              const double* __restrict__ pdydz, const double* __restrict__ pwl, const double* __restrict__ pflux,
              const double* __restrict__ rand4, uint64_t seed, uint64_t offset, unsigned long long* __restrict__ stats,
-             double* __restrict__ added) {
+             double* __restrict__ added, SlowRec* __restrict__ slow, unsigned long long* __restrict__ nslow) {
     int64_t i = i1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool active = i < i2;
-    unsigned npoly = 0, nneigh = 0, nnf = 0, nb9 = 0, ndrop = 0;
+    unsigned nb9 = 0, ndrop = 0;
     double my_added = 0.0;
+    bool to_slow = false;
+    SlowRec rec;
     if (active) {
         double g1, g2, unf, udep;
         if (rand4) {
@@ -234,17 +252,19 @@ k_accumulate(const __grid_constant__ DevSensor s, int64_t i1, int64_t i2, int64_
             unf = rand4[2 * ntot + i];
             udep = rand4[3 * ntot + i];
         } else {
-            uint32_t r[4], q[4];
+            // one Philox block per photon: two 24-bit uniforms -> Box-Muller in FP32 (a diffusion
+            // step with 1e-7 relative granularity is statistically exact), two 32-bit uniforms
+            uint32_t r[4];
             philox4(seed, offset + (uint64_t)i, 3u, r);
-            philox4(seed, offset + (uint64_t)i, 4u, q);
-            double u1 = u01(r[0], r[1]), u2 = u01(r[2], r[3]);
-            double sn, cs;
-            sincospi(2.0 * u2, &sn, &cs);
-            double rad = sqrt(-2.0 * log(u1));
-            g1 = rad * cs;
-            g2 = rad * sn;
-            unf = u01(q[0], q[1]);
-            udep = u01(q[2], q[3]);
+            float u1 = ((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+            float u2 = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+            float sn, cs;
+            sincospif(2.0f * u2, &sn, &cs);
+            float rad = sqrtf(-2.0f * logf(u1));
+            g1 = (double)(rad * cs);
+            g2 = (double)(rad * sn);
+            udep = ((double)r[2] + 0.5) * (1.0 / 4294967296.0);
+            unf = ((double)r[3] + 0.5) * (1.0 / 4294967296.0);
         }
         const double T = s.thickness;
         const double invPixelSize = 1. / s.pixel_size;
@@ -288,18 +308,76 @@ k_accumulate(const __grid_constant__ DevSensor s, int64_t i1, int64_t i2, int64_
             double x = __dadd_rn(__dsub_rn(x0, (double)ix), 0.5);
             double y = __dadd_rn(__dsub_rn(y0, (double)iy), 0.5);
             if (fabs(x) < 1e-9 || fabs(x - 1.0) < 1e-9 || fabs(y) < 1e-9 || fabs(y - 1.0) < 1e-9) nb9 = 1;
+            int ax = ix - s.xmin, ay = iy - s.ymin;
+            // nominal pixel off the image: insidePixel() fails with off_edge set -> the photon is lost
+            if (ax >= 0 && ax < s.nx && ay >= 0 && ay < s.ny) {
+                size_t k = (size_t)ay * s.nx + ax;
+                const double4 in = *reinterpret_cast<const double4*>(s.inner + k * 4);
+                double flux = pflux[i];
+                if (x >= in.x && x <= in.y && y >= in.z && y <= in.w) {
+                    atomicAdd(&s.delta[k], flux);
+                    my_added = flux;
+                } else {
+                    to_slow = true;
+                    rec.ix = ix; rec.iy = iy;
+                    rec.x = x; rec.y = y;
+                    rec.zconv = zconv; rec.flux = flux;
+                    rec.coin = (unf > 0.5) ? 1 : 0;
+                    rec.pad = 0;
+                }
+            }
+        }
+    }
+    // warp-aggregated append to the slow list
+    unsigned m = __ballot_sync(0xffffffffu, to_slow);
+    if (m) {
+        int lane = threadIdx.x & 31;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(nslow, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (to_slow) slow[base + __popc(m & ((1u << lane) - 1u))] = rec;
+    }
+    // warp-aggregated statistics
+    unsigned long long w3 = warp_sum(nb9), w4 = warp_sum(ndrop);
+    double wa = my_added;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wa += __shfl_xor_sync(0xffffffffu, wa, o);
+    if ((threadIdx.x & 31) == 0) {
+        if (w3) atomicAdd(&stats[ST_B9], w3);
+        if (w4) atomicAdd(&stats[ST_DROP], w4);
+        if (wa != 0.0) atomicAdd(added, wa);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_accumulate_slow(const __grid_constant__ DevSensor s, const SlowRec* __restrict__ slow,
+                  const unsigned long long* __restrict__ nslow, unsigned long long* __restrict__ stats,
+                  double* __restrict__ added) {
+    const unsigned long long total = *nslow;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned npoly = 0, nneigh = 0, nnf = 0;
+    double my_added = 0.0;
+    // whole warps iterate together so the shuffles below stay converged
+    const unsigned long long first = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (unsigned long long base = first - (threadIdx.x & 31); base < total; base += stride) {
+        unsigned long long j = base + (threadIdx.x & 31);
+        if (j < total) {
+            SlowRec r = slow[j];
+            int ix = r.ix, iy = r.iy;
+            const double x = r.x, y = r.y, zconv = r.zconv;
             bool off_edge = false;
             bool found = inside_pixel(s, ix, iy, x, y, zconv, &off_edge, npoly);
             bool drop = (!found && off_edge);
             if (!drop) {
                 int step = 0;
                 if (!found) {
-                    nneigh = 1;
+                    nneigh++;
                     if ((x > y) && (x > 1.0 - y)) step = 1;
                     else if ((x > y) && (x < 1.0 - y)) step = 7;
                     else if ((x < y) && (x > 1.0 - y)) step = 3;
                     else step = 5;
                     int nn = step;
+#pragma unroll 1
                     for (int m = 1; m < 9; ++m) {
                         int ix_off = ix + c_xoff[nn], iy_off = iy + c_yoff[nn];
                         double x_off = x - c_xoff[nn], y_off = y - c_yoff[nn];
@@ -313,23 +391,20 @@ k_accumulate(const __grid_constant__ DevSensor s, int64_t i1, int64_t i2, int64_
                     }
                 }
                 if (!found) {
-                    nnf = 1;
-                    int nn = (unf > 0.5) ? 0 : step;
+                    nnf++;
+                    int nn = r.coin ? 0 : step;
                     ix += c_xoff[nn];
                     iy += c_yoff[nn];
                 }
                 int ax = ix - s.xmin, ay = iy - s.ymin;
                 if (ax >= 0 && ax < s.nx && ay >= 0 && ay < s.ny) {
-                    double flux = pflux[i];
-                    atomicAdd(&s.delta[(size_t)ay * s.nx + ax], flux);
-                    my_added = flux;
+                    atomicAdd(&s.delta[(size_t)ay * s.nx + ax], r.flux);
+                    my_added += r.flux;
                 }
             }
         }
     }
-    // warp-aggregated statistics
-    unsigned long long w0 = warp_sum(npoly), w1 = warp_sum(nneigh), w2 = warp_sum(nnf), w3 = warp_sum(nb9),
-                       w4 = warp_sum(ndrop);
+    unsigned long long w0 = warp_sum(npoly), w1 = warp_sum(nneigh), w2 = warp_sum(nnf);
     double wa = my_added;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wa += __shfl_xor_sync(0xffffffffu, wa, o);
@@ -337,8 +412,6 @@ k_accumulate(const __grid_constant__ DevSensor s, int64_t i1, int64_t i2, int64_
         if (w0) atomicAdd(&stats[ST_POLY], w0);
         if (w1) atomicAdd(&stats[ST_NEIGH], w1);
         if (w2) atomicAdd(&stats[ST_NOTFOUND], w2);
-        if (w3) atomicAdd(&stats[ST_B9], w3);
-        if (w4) atomicAdd(&stats[ST_DROP], w4);
         if (wa != 0.0) atomicAdd(added, wa);
     }
 }
@@ -796,6 +869,11 @@ extern "C" int b2_sensor_create(b2_ctx* ctx, const B2SensorConfig* cfg, const do
     B2_CUDA(cudaSetDevice(ctx->device));
     b2_sensor* s = new b2_sensor();
     s->ctx = ctx;
+    {
+        cudaDeviceProp prop;
+        B2_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+        s->sm_count = prop.multiProcessorCount;
+    }
     s->cfg = *cfg;
     DevSensor& d = s->d;
     memset(&d, 0, sizeof(d));
@@ -866,6 +944,7 @@ extern "C" int b2_sensor_create(b2_ctx* ctx, const B2SensorConfig* cfg, const do
     s->owned.push_back(p);
     s->dstats = (unsigned long long*)p;
     s->dadded = (double*)((char*)p + ST_N * sizeof(unsigned long long));
+    s->dnslow = (unsigned long long*)((char*)p + ST_N * sizeof(unsigned long long) + 8);
     B2_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = s;
     return 0;
@@ -883,6 +962,7 @@ extern "C" int b2_sensor_destroy(b2_sensor* s) {
     free_list(s->image_owned);
     free_list(s->owned);
     if (s->cum.ptr) cudaFree(s->cum.ptr);
+    if (s->slow.ptr) cudaFree(s->slow.ptr);
     delete s;
     return 0;
 }
@@ -1117,6 +1197,16 @@ extern "C" int b2_sensor_accumulate(b2_sensor* s, int64_t n, const double* x, co
         }
         s->accum_flux = acc;
     }
+    {
+        // worst case every photon of the largest chunk needs the slow path
+        int64_t maxchunk = n, prev = 0;
+        if (!bounds.empty()) {
+            maxchunk = 0;
+            for (int64_t bnd : bounds) { maxchunk = std::max(maxchunk, bnd - prev); prev = bnd; }
+            maxchunk = std::max(maxchunk, n - prev);
+        }
+        if (maxchunk > 0 && b2_scratch_reserve(ctx, s->slow, (size_t)maxchunk * sizeof(SlowRec))) return 1;
+    }
     int64_t i1 = 0;
     size_t ib = 0;
     while (i1 < n) {
@@ -1124,10 +1214,22 @@ extern "C" int b2_sensor_accumulate(b2_sensor* s, int64_t n, const double* x, co
         bool hit = ib < bounds.size();
         int64_t cnt = i2 - i1;
         if (cnt > 0) {
-            B2_TIMED("k_accumulate", st);
-            k_accumulate<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d, i1, i2, n, dx, dy, da, db, dw, df, dr, seed,
-                                                                         offset, s->dstats, s->dadded);
-            B2_CHECK_LAUNCH();
+            {
+                B2_TIMED("k_accumulate", st);
+                B2_CUDA(cudaMemsetAsync(s->dnslow, 0, sizeof(unsigned long long), st));
+                k_accumulate<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d, i1, i2, n, dx, dy, da, db, dw, df, dr,
+                                                                             seed, offset, s->dstats, s->dadded,
+                                                                             (SlowRec*)s->slow.ptr, s->dnslow);
+                B2_CHECK_LAUNCH();
+            }
+            {
+                B2_TIMED("k_accumulate_slow", st);
+                int64_t want = (cnt + 255) / 256;
+                unsigned blocks = (unsigned)(want < (int64_t)s->sm_count * 8 ? want : (int64_t)s->sm_count * 8);
+                k_accumulate_slow<<<blocks, 256, 0, st>>>(d, (const SlowRec*)s->slow.ptr, s->dnslow, s->dstats,
+                                                          s->dadded);
+                B2_CHECK_LAUNCH();
+            }
         }
         if (hit) {
             if (sensor_update(s)) return 1;
