@@ -38,6 +38,9 @@ UNIT = "photons/s"
 POOL = 1 << 25  # photons per step (33.5 M): every SoA array is 268 MB > L2 (126 MB)
 ALG_BYTES_TRACE = 96.0  # read x,y,wl,u,v,t,flux (56 B) + write x,y,dxdz,dydz,flux (40 B)
 ALG_FLOP_TRACE = 4000.0  # SURVEY 8d estimate of the reference's FP64 op count per photon (3.8-5.6 k)
+# fused k_pool_step = trace + sensor fast path: SURVEY 8d adds 56 B (6 reads + 1 atomic RMW) and ~100 FLOP
+ALG_BYTES_POOL = 96.0 + 56.0
+ALG_FLOP_POOL = 4100.0
 DETECTORS = ["R22_S11", "R21_S11", "R23_S11", "R12_S11", "R32_S11", "R22_S00", "R22_S22", "R11_S11"]
 
 
@@ -201,6 +204,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=2_000_000)
     ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused", action="store_true", help="time the three separate kernels instead of b2_pool_step")
     ap.add_argument("--kernel-timing", action="store_true",
                     help="diagnostic: bracket every kernel with CUDA events (B2_TIMING=1) and print the breakdown "
                          "to stderr; adds event overhead, do not quote `value` from such a run")
@@ -267,7 +271,6 @@ def main():
 
     # ---- device-resident steps -------------------------------------------------------
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     for i in range(W):
         refill(work[i % 2])
         pool.process(work[i % 2], image, resume=True, recalc=True)
@@ -276,6 +279,8 @@ def main():
         from imsim_b200._lib import timing_report
 
         timing_report()  # drop warm-up launches
+    ctx.kernel_ms()
+    ctx.record_kernel_events(True)
     clocks = ClockSampler(local)
     clocks.start()
     l0 = launch_count()
@@ -285,16 +290,18 @@ def main():
         dp = work[i % 2]
         refill(dp)  # untimed input restore (the ops work in place); events bracket only the path
         ev[i][0].record()
-        pool.ctx.sample_time_pupil(dp.time, dp.pupil_u, dp.pupil_v, pool.t0, pool.exptime, pool.r_inner,
-                                   pool.r_outer, pool.seed, pool.offset)
-        pool.opt.photon_offset = pool.offset
-        kev[i][0].record()
-        ctx.rubin_optics(dp.x, dp.y, dp.dxdz, dp.dydz, dp.flux, dp.wavelength, dp.pupil_u, dp.pupil_v, dp.time,
-                         options=pool.opt, want_stats=False)
-        kev[i][1].record()
-        dp._has.update(pupil_u=True, pupil_v=True, time=True, dxdz=True, dydz=True)
-        pool.offset += P
-        sensor.accumulate(dp, image, resume=True, recalc=True, sync_image=False, want_stats=False)
+        if args.unfused:
+            pool.ctx.sample_time_pupil(dp.time, dp.pupil_u, dp.pupil_v, pool.t0, pool.exptime, pool.r_inner,
+                                       pool.r_outer, pool.seed, pool.offset)
+            pool.opt.photon_offset = pool.offset
+            ctx.rubin_optics(dp.x, dp.y, dp.dxdz, dp.dydz, dp.flux, dp.wavelength, dp.pupil_u, dp.pupil_v, dp.time,
+                             options=pool.opt, want_stats=False)
+            dp._has.update(pupil_u=True, pupil_v=True, time=True, dxdz=True, dydz=True)
+            pool.offset += P
+            sensor.accumulate(dp, image, resume=True, recalc=True, sync_image=False, want_stats=False)
+        else:
+            # one kernel per batch: sampler -> DCR/optics/FocusDepth/Refraction -> sensor deposit (b2_pool_step)
+            pool.process(dp, image, resume=True, recalc=True, fused=True)
         ev[i][1].record()
     barrier()
     launches = launch_count() - l0
@@ -303,7 +310,10 @@ def main():
         rep = timing_report()
         sys.stderr.write("per-step kernel ms: " + json.dumps({k: round(v[1] / K, 4) for k, v in rep.items()}) + "\n")
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    trace_ms = [a.elapsed_time(b) for a, b in kev]
+    kern_total_ms, kern_count = ctx.kernel_ms()
+    ctx.record_kernel_events(False)
+    trace_ms = [kern_total_ms / max(kern_count, 1)]
+    dominant = "k_rubin_optics" if args.unfused else "k_pool_step"
     total_ms = float(np.sum(step_ms))
     tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -348,8 +358,10 @@ def main():
         fp64_peak = ctx.fma_peak(True)
         fp32_peak = ctx.fma_peak(False)
         tr_ms = float(np.mean(trace_ms))
-        ach_gbs = ALG_BYTES_TRACE * P / (tr_ms * 1e-3) / 1e9
-        ach_tf = ALG_FLOP_TRACE * P / (tr_ms * 1e-3) / 1e12
+        alg_bytes = ALG_BYTES_TRACE if args.unfused else ALG_BYTES_POOL
+        alg_flop = ALG_FLOP_TRACE if args.unfused else ALG_FLOP_POOL
+        ach_gbs = alg_bytes * P / (tr_ms * 1e-3) / 1e9
+        ach_tf = alg_flop * P / (tr_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -358,16 +370,15 @@ def main():
                     "steps": e2e_K},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"kernel": "k_rubin_optics", "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak,
+            "roofline": {"kernel": dominant, "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "kernel_ms": tr_ms, "share_of_step": tr_ms * K / total_ms,
                          "note": "kernel is FP64-pipe bound, see roofline_fp64"},
-            "roofline_fp64": {"kernel": "k_rubin_optics", "bound": "fp64 fma pipe", "achieved": ach_tf,
+            "roofline_fp64": {"kernel": dominant, "bound": "fp64 fma pipe", "achieved": ach_tf,
                               "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
-                              "flop_per_photon_algorithmic": ALG_FLOP_TRACE,
+                              "flop_per_photon_algorithmic": alg_flop, "bytes_per_photon_algorithmic": alg_bytes,
                               "peak_source": "b2_fma_peak measured in this run", "fp32_peak": fp32_peak},
-            "breakdown_ms": {"step": total_ms / K, "trace": tr_ms, "sampler+accumulate+boundary_update":
-                             total_ms / K - tr_ms},
+            "breakdown_ms": {"step": total_ms / K, dominant: tr_ms, "rest_of_step": total_ms / K - tr_ms},
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample, 1)

@@ -16,8 +16,9 @@ import numpy as np
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SRC = [os.path.join(_HERE, "csrc", f) for f in ("abi.cu", "optics.cu", "sensor.cu")]
-_HDR = [os.path.join(_HERE, "csrc", "b2_common.cuh"), os.path.join(os.path.dirname(_HERE), "include", "imsim_b200.h")]
+_SRC = [os.path.join(_HERE, "csrc", f) for f in ("abi.cu", "optics.cu", "sensor.cu", "pool.cu")]
+_HDR = [os.path.join(_HERE, "csrc", f) for f in ("b2_common.cuh", "optics_device.cuh", "sensor_device.cuh")] + \
+    [os.path.join(os.path.dirname(_HERE), "include", "imsim_b200.h")]
 SO_PATH = os.path.join(_HERE, "_build", "libimsim_b200.so")
 
 NVCC_FLAGS = [
@@ -72,6 +73,8 @@ _SIGNATURES = {
     "b2_ctx_synchronize": (C.c_int, [vp]),
     "b2_fma_peak": (C.c_int, [vp, C.c_int32, dp]),
     "b2_timing_report": (C.c_int, [C.c_char_p, C.c_int64]),
+    "b2_ctx_record_kernel_events": (C.c_int, [vp, C.c_int32]),
+    "b2_ctx_kernel_ms": (C.c_int, [vp, dp, C.POINTER(C.c_int64)]),
     "b2_telescope_upload": (C.c_int, [vp, C.POINTER(_abi.B2Telescope)]),
     "b2_telescope_set_extra": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int64]),
     "b2_wcs_upload": (C.c_int, [vp, C.POINTER(_abi.B2TanSip), C.POINTER(_abi.B2TanSip)]),
@@ -97,6 +100,9 @@ _SIGNATURES = {
     "b2_sensor_pixel_areas": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int]),
     "b2_plain_accumulate": (C.c_int, [vp, C.c_int64, vp, vp, vp, C.c_int, dp]),
     "b2_sensor_get_pixel": (C.c_int, [vp, C.c_int32, C.c_int32, vp, vp]),
+    "b2_pool_step": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.POINTER(_abi.B2OpticsOptions), C.c_double,
+                               C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32,
+                               C.c_int32, C.c_int32, C.POINTER(_abi.B2OpticsStats), C.POINTER(_abi.B2AccumStats)]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

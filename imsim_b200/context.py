@@ -67,6 +67,16 @@ class OpticsContext:
     def synchronize(self):
         _lib.check(self._lib.b2_ctx_synchronize(self._h))
 
+    def record_kernel_events(self, on=True):
+        """Bracket the main kernel of pool_step / rubin_optics with CUDA events (roofline timing)."""
+        _lib.check(self._lib.b2_ctx_record_kernel_events(self._h, int(bool(on))))
+
+    def kernel_ms(self):
+        """(total_ms, launches) of the bracketed kernels since the last call."""
+        ms, cnt = C.c_double(0.0), C.c_int64(0)
+        _lib.check(self._lib.b2_ctx_kernel_ms(self._h, C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
+
     def fma_peak(self, fp64=True) -> float:
         """Measured non-tensor FMA ceiling in TFLOP/s (roofline denominator of the trace kernel)."""
         out = C.c_double(0.0)

@@ -149,3 +149,29 @@ extern "C" int b2_timing_report(char* buf, int64_t cap) {
     memcpy(buf, out.c_str(), out.size() + 1);
     return 0;
 }
+
+// ---------------------------------------------------------------- dominant-kernel events
+extern "C" int b2_ctx_record_kernel_events(b2_ctx* ctx, int32_t on) {
+    B2_REQUIRE(ctx, "null context");
+    ctx->record_events = on != 0;
+    return 0;
+}
+
+// sum of the recorded launches' durations [ms] and their count; clears the list
+extern "C" int b2_ctx_kernel_ms(b2_ctx* ctx, double* total_ms, int64_t* count) {
+    B2_REQUIRE(ctx && total_ms && count, "b2_ctx_kernel_ms: null argument");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    double tot = 0.0;
+    for (auto& ev : ctx->events) {
+        B2_CUDA(cudaEventSynchronize(ev.second));
+        float ms = 0.f;
+        B2_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        tot += ms;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    *total_ms = tot;
+    *count = (int64_t)ctx->events.size();
+    ctx->events.clear();
+    return 0;
+}

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/imsim_b200.h"
@@ -123,6 +124,9 @@ struct b2_ctx {
     Scratch scratch;         // staging for B2_HOST calls
     Scratch stats;           // small device buffer for counters
     B2TanSip img_host, field_host;
+    // live timing of the dominant kernel (bench.py roofline): event pairs around each launch
+    bool record_events = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
 };
 
 int b2_scratch_reserve(b2_ctx* ctx, Scratch& s, size_t bytes);

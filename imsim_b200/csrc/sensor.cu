@@ -17,206 +17,7 @@
 #include <algorithm>
 #include <cstdlib>
 
-#include "b2_common.cuh"
-
-#define PI_D 3.14159265358979323846
-#define B2_MAX_NV 32
-
-struct DevSensor {
-    int nv, nx9, ny9, qdist;
-    int xmin, ymin, nx, ny;
-    int ntr, nabs, tr_spline, pad;
-    double diff_step, pixel_size, thickness;
-    double trc[2];
-    double tr_max;
-    const double *tr_r, *tr_f, *tr_y2;
-    const double *abs_w, *abs_l;
-    const float2 *KH, *KV;
-    float2 *H, *V;
-    double *inner, *outer;
-    double* delta;
-    void* target;
-    int dtype_bytes, pad2;
-    double frac[B2_MAX_NV];  // (tan(theta_k)+1)/2, k = 0..nv-1, double (GalSim _emptypoly)
-};
-
-struct b2_sensor {
-    b2_ctx* ctx = nullptr;
-    B2SensorConfig cfg;
-    DevSensor d;
-    std::vector<void*> owned;        // tables
-    std::vector<void*> image_owned;  // per-image state
-    bool bound = false, initialized = false;
-    int sm_count = 148;
-    double accum_flux = 0.0;
-    uint8_t* changed = nullptr;
-    uint8_t* tiles = nullptr;  // charge occupancy per 32x32 tile
-    int tnx = 0, tny = 0;
-    unsigned long long* dstats = nullptr;  // device counters
-    double* dadded = nullptr;
-    Scratch cum;  // cumulative flux scratch
-    Scratch slow;  // compact list of photons that need the full polygon / neighbour treatment
-    unsigned long long* dnslow = nullptr;
-};
-
-enum { ST_POLY = 0, ST_NEIGH = 1, ST_NOTFOUND = 2, ST_B9 = 3, ST_DROP = 4, ST_N = 8 };
-
-// ------------------------------------------------------------------ device helpers
-__device__ __forceinline__ size_t Hidx(const DevSensor& s, int x, int y) {
-    return ((size_t)y * s.nx + x) * (s.nv + 2);
-}
-__device__ __forceinline__ size_t Vidx(const DevSensor& s, int x, int y) {
-    return ((size_t)y * (s.nx + 1) + x) * s.nv;
-}
-
-__device__ __forceinline__ int table_index(int n, const double* __restrict__ x, double a) {
-    if (a <= __ldg(x)) return 1;
-    if (a >= __ldg(x + n - 1)) return n - 1;
-    int lo = 0, hi = n - 1;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (__ldg(x + mid) <= a) lo = mid; else hi = mid;
-    }
-    return hi;
-}
-
-// GalSim Table.cpp linear / spline interpolation; explicit _rn ops: no FMA contraction,
-// so the values match the host (non-FMA) evaluation bit for bit
-__device__ __forceinline__ double table_linear(int n, const double* __restrict__ x, const double* __restrict__ f, double a) {
-    a = fmin(fmax(a, __ldg(x)), __ldg(x + n - 1));
-    int i = table_index(n, x, a);
-    double xi = __ldg(x + i), xm = __ldg(x + i - 1);
-    double ax = __ddiv_rn(__dsub_rn(xi, a), __dsub_rn(xi, xm));
-    double bx = __dsub_rn(1.0, ax);
-    return __dadd_rn(__dmul_rn(__ldg(f + i), bx), __dmul_rn(__ldg(f + i - 1), ax));
-}
-
-__device__ __forceinline__ double table_spline(int n, const double* __restrict__ x, const double* __restrict__ f,
-                                               const double* __restrict__ y2, double a) {
-    int i = table_index(n, x, a);
-    double xi = __ldg(x + i), xm = __ldg(x + i - 1);
-    double h = __dsub_rn(xi, xm);
-    double aa = __dsub_rn(xi, a);
-    double bb = __dsub_rn(h, aa);
-    double t1 = __dadd_rn(__dmul_rn(aa, __ldg(f + i - 1)), __dmul_rn(bb, __ldg(f + i)));
-    double t2 = __dadd_rn(__dmul_rn(__dadd_rn(aa, h), __ldg(y2 + i - 1)), __dmul_rn(__dadd_rn(bb, h), __ldg(y2 + i)));
-    double t3 = __dmul_rn(__dmul_rn(__dmul_rn(1. / 6., aa), bb), t2);
-    return __ddiv_rn(__dsub_rn(t1, t3), h);
-}
-
-// walk the polygon of pixel (ax, ay) counter-clockwise starting at the BL corner and
-// call f(n_is, px, py, ex, ey) with the stored point (pixel frame) and the undistorted one
-template <typename F>
-__device__ __forceinline__ void walk_polygon(const DevSensor& s, int ax, int ay, F&& f) {
-    const int nv = s.nv;
-    const float2* hb = s.H + Hidx(s, ax, ay);
-    const float2* ht = s.H + Hidx(s, ax, ay + 1);
-    const float2* vl = s.V + Vidx(s, ax, ay);
-    const float2* vr = vl + nv;
-    // bottom edge: BL corner, nv points, BR corner (all in this pixel's frame)
-    {
-        float2 p = hb[0];
-        f((double)p.x, (double)p.y, 0.0, 0.0);
-    }
-    for (int k = 0; k < nv; ++k) {
-        float2 p = hb[k + 1];
-        f((double)p.x, (double)p.y, s.frac[k], 0.0);
-    }
-    {
-        float2 p = hb[nv + 1];
-        f((double)p.x, (double)p.y, 1.0, 0.0);
-    }
-    for (int k = 0; k < nv; ++k) {
-        float2 p = vr[k];
-        f((double)p.x + 1.0, (double)p.y, 1.0, s.frac[k]);
-    }
-    {
-        float2 p = ht[nv + 1];
-        f((double)p.x, (double)p.y + 1.0, 1.0, 1.0);
-    }
-    for (int k = nv - 1; k >= 0; --k) {
-        float2 p = ht[k + 1];
-        f((double)p.x, (double)p.y + 1.0, s.frac[k], 1.0);
-    }
-    {
-        float2 p = ht[0];
-        f((double)p.x, (double)p.y + 1.0, 0.0, 1.0);
-    }
-    for (int k = nv - 1; k >= 0; --k) {
-        float2 p = vl[k];
-        f((double)p.x, (double)p.y, 0.0, s.frac[k]);
-    }
-}
-
-// Silicon::insidePixel.  ix, iy: image coordinates.  Returns inside; sets *off_edge like GalSim.
-__device__ __forceinline__ bool inside_pixel(const DevSensor& s, int ix, int iy, double x, double y, double zconv,
-                                             bool* off_edge, unsigned& npoly) {
-    int ax = ix - s.xmin, ay = iy - s.ymin;
-    if (ax < 0 || ax >= s.nx || ay < 0 || ay >= s.ny) {
-        if (off_edge) *off_edge = true;
-        return false;
-    }
-    size_t k = ((size_t)ay * s.nx + ax) * 4;
-    const double4 in = *reinterpret_cast<const double4*>(s.inner + k);  // xmin xmax ymin ymax
-    bool inside;
-    if (x >= in.x && x <= in.y && y >= in.z && y <= in.w) {
-        inside = true;
-    } else {
-        const double4 out = *reinterpret_cast<const double4*>(s.outer + k);
-        if (!(x >= out.x && x <= out.y && y >= out.z && y <= out.w)) {
-            inside = false;
-        } else {
-            const double zfactor = tanh(zconv / 12.0);
-            // Polygon::contains crossing test over consecutive vertices
-            bool in_poly = false;
-            double x1 = 0.0, y1 = 0.0, xf = 0.0, yf = 0.0;
-            bool first = true;
-            auto edge = [&](double xa, double ya, double xb, double yb) {
-                if (y > fmin(ya, yb)) {
-                    if (y <= fmax(ya, yb)) {
-                        if (x <= fmax(xa, xb)) {
-                            double xinters = 0.0;
-                            bool have = (ya != yb);
-                            if (have) xinters = __dadd_rn(__ddiv_rn(__dmul_rn(__dsub_rn(y, ya), __dsub_rn(xb, xa)), __dsub_rn(yb, ya)), xa);
-                            // GalSim keeps the previous xinters when ya == yb; with y > min and
-                            // y <= max that case is impossible (min == max), so it is never read
-                            if ((xa == xb) || (x <= xinters)) in_poly = !in_poly;
-                        }
-                    }
-                }
-            };
-            walk_polygon(s, ax, ay, [&](double px, double py, double ex, double ey) {
-                double qx = __dadd_rn(ex, __dmul_rn(__dsub_rn(px, ex), zfactor));
-                double qy = __dadd_rn(ey, __dmul_rn(__dsub_rn(py, ey), zfactor));
-                if (first) {
-                    xf = qx; yf = qy;
-                    first = false;
-                } else {
-                    edge(x1, y1, qx, qy);
-                }
-                x1 = qx; y1 = qy;
-            });
-            edge(x1, y1, xf, yf);
-            inside = in_poly;
-            npoly++;
-        }
-    }
-    if (!inside && off_edge) {
-        *off_edge = false;
-        if (ax == 0 && x < in.x) *off_edge = true;
-        if (ax == s.nx - 1 && x > in.y) *off_edge = true;
-        if (ay == 0 && y < in.z) *off_edge = true;
-        if (ay == s.ny - 1 && y > in.w) *off_edge = true;
-    }
-    return inside;
-}
-
-__constant__ int c_xoff[9] = {0, 1, 1, 0, -1, -1, -1, 0, 1};
-__constant__ int c_yoff[9] = {0, 0, 1, 1, 1, 0, -1, -1, -1};
-
-__device__ __forceinline__ unsigned long long warp_sum(unsigned v) {
-    return (unsigned long long)__reduce_add_sync(0xffffffffu, v);
-}
+#include "sensor_device.cuh"
 
 // ------------------------------------------------------------------ accumulate
 // Silicon::accumulate over photons [i1, i2), in two phases so that warps stay converged:
@@ -226,12 +27,6 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned v) {
 //   k_accumulate_slow  the listed photons, all lanes busy: outer box, polygon test, neighbour
 //                      search, coin flip -- exactly the reference's sequence for those photons.
 // Deposits are atomic adds into `delta`, so the split does not change any result.
-struct SlowRec {
-    int ix, iy;
-    double x, y, zconv, flux;
-    int coin, pad;  // unf > 0.5
-};
-
 __global__ void __launch_bounds__(256)
 k_accumulate(const __grid_constant__ DevSensor s, int64_t i1, int64_t i2, int64_t ntot,
              const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ pdxdz,
@@ -252,91 +47,17 @@ k_accumulate(const __grid_constant__ DevSensor s, int64_t i1, int64_t i2, int64_
             unf = rand4[2 * ntot + i];
             udep = rand4[3 * ntot + i];
         } else {
-            // one Philox block per photon: two 24-bit uniforms -> Box-Muller in FP32 (a diffusion
-            // step with 1e-7 relative granularity is statistically exact), two 32-bit uniforms
-            uint32_t r[4];
-            philox4(seed, offset + (uint64_t)i, 3u, r);
-            float u1 = ((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-            float u2 = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-            float sn, cs;
-            sincospif(2.0f * u2, &sn, &cs);
-            float rad = sqrtf(-2.0f * logf(u1));
-            g1 = (double)(rad * cs);
-            g2 = (double)(rad * sn);
-            udep = ((double)r[2] + 0.5) * (1.0 / 4294967296.0);
-            unf = ((double)r[3] + 0.5) * (1.0 / 4294967296.0);
+            sensor_draws(seed, offset + (uint64_t)i, g1, g2, unf, udep);
         }
-        const double T = s.thickness;
-        const double invPixelSize = 1. / s.pixel_size;
-        const double diffStep_pixel_z = s.diff_step / (T * s.pixel_size);
-        double x0 = px[i], y0 = py[i];
-        // calculateConversionDepth
-        double dz;
         double a = 0.0, b = 0.0;
         if (pdxdz) {
             a = pdxdz[i];
             b = pdydz[i];
         }
-        if (pwl) {
-            double abs_length = table_linear(s.nabs, s.abs_w, s.abs_l, pwl[i]);
-            double si_length = __dmul_rn(-abs_length, log(__dsub_rn(1.0, udep)));
-            if (pdxdz) {
-                double nrm = sqrt(__dadd_rn(__dadd_rn(1.0, __dmul_rn(a, a)), __dmul_rn(b, b)));
-                dz = fmin(T - 1.0, __ddiv_rn(si_length, nrm));
-            } else {
-                dz = si_length;
-            }
-        } else {
-            dz = 1.0;
-        }
-        if (pdxdz) {
-            double dz_pixel = __dmul_rn(dz, invPixelSize);
-            x0 = __dadd_rn(x0, __dmul_rn(a, dz_pixel));
-            y0 = __dadd_rn(y0, __dmul_rn(b, dz_pixel));
-        }
-        double zconv = __dsub_rn(T, dz);
-        if (zconv < 0.0) {
-            ndrop = 1;
-        } else {
-            if (s.diff_step != 0.) {
-                double diffStep = fmax(0.0, __dmul_rn(diffStep_pixel_z, sqrt(__dmul_rn(zconv, T))));
-                x0 = __dadd_rn(x0, __dmul_rn(diffStep, g1));
-                y0 = __dadd_rn(y0, __dmul_rn(diffStep, g2));
-            }
-            int ix = (int)floor(x0 + 0.5);
-            int iy = (int)floor(y0 + 0.5);
-            double x = __dadd_rn(__dsub_rn(x0, (double)ix), 0.5);
-            double y = __dadd_rn(__dsub_rn(y0, (double)iy), 0.5);
-            if (fabs(x) < 1e-9 || fabs(x - 1.0) < 1e-9 || fabs(y) < 1e-9 || fabs(y - 1.0) < 1e-9) nb9 = 1;
-            int ax = ix - s.xmin, ay = iy - s.ymin;
-            // nominal pixel off the image: insidePixel() fails with off_edge set -> the photon is lost
-            if (ax >= 0 && ax < s.nx && ay >= 0 && ay < s.ny) {
-                size_t k = (size_t)ay * s.nx + ax;
-                const double4 in = *reinterpret_cast<const double4*>(s.inner + k * 4);
-                double flux = pflux[i];
-                if (x >= in.x && x <= in.y && y >= in.z && y <= in.w) {
-                    atomicAdd(&s.delta[k], flux);
-                    my_added = flux;
-                } else {
-                    to_slow = true;
-                    rec.ix = ix; rec.iy = iy;
-                    rec.x = x; rec.y = y;
-                    rec.zconv = zconv; rec.flux = flux;
-                    rec.coin = (unf > 0.5) ? 1 : 0;
-                    rec.pad = 0;
-                }
-            }
-        }
+        to_slow = sensor_fast_path(s, px[i], py[i], pdxdz != nullptr, a, b, pwl != nullptr, pwl ? pwl[i] : 0.0,
+                                   pflux[i], g1, g2, unf, udep, rec, my_added, nb9, ndrop);
     }
-    // warp-aggregated append to the slow list
-    unsigned m = __ballot_sync(0xffffffffu, to_slow);
-    if (m) {
-        int lane = threadIdx.x & 31;
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(nslow, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (to_slow) slow[base + __popc(m & ((1u << lane) - 1u))] = rec;
-    }
+    slow_append(to_slow, rec, slow, nslow);
     // warp-aggregated statistics
     unsigned long long w3 = warp_sum(nb9), w4 = warp_sum(ndrop);
     double wa = my_added;
@@ -1257,6 +978,44 @@ extern "C" int b2_sensor_accumulate(b2_sensor* s, int64_t n, const double* x, co
     }
     return 0;
 }
+
+// ---- pieces of the accumulate protocol used by the fused pool step (pool.cu) ----
+int b2_sensor_begin_accumulate(b2_sensor* s, int32_t ocx, int32_t ocy, int32_t resume, int32_t recalc, int64_t n,
+                               uint64_t* n_updates) {
+    B2_REQUIRE(s && s->bound, "accumulate: no image bound");
+    B2_REQUIRE(!resume || s->initialized, "accumulate: resume=True but there was no previous accumulate on this image");
+    b2_ctx* ctx = s->ctx;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    B2_CUDA(cudaMemsetAsync(s->dstats, 0, ST_N * sizeof(unsigned long long) + 64, st));
+    *n_updates = 0;
+    if (!resume) {
+        if (sensor_initialize(s, ocx, ocy)) return 1;
+    } else {
+        if (launch_add_delta(s, -1.0, 0)) return 1;  // subtractDelta
+        if (recalc) {
+            if (sensor_update(s)) return 1;
+            s->accum_flux = 0.0;
+            (*n_updates)++;
+        }
+    }
+    if (n > 0 && b2_scratch_reserve(ctx, s->slow, (size_t)n * sizeof(SlowRec))) return 1;
+    B2_CUDA(cudaMemsetAsync(s->dnslow, 0, sizeof(unsigned long long), st));
+    return 0;
+}
+
+int b2_sensor_run_slow(b2_sensor* s, int64_t n) {
+    cudaStream_t st = s->ctx->stream;
+    B2_TIMED("k_accumulate_slow", st);
+    int64_t want = (n + 255) / 256;
+    unsigned blocks = (unsigned)(want < (int64_t)s->sm_count * 8 ? want : (int64_t)s->sm_count * 8);
+    if (blocks == 0) return 0;
+    k_accumulate_slow<<<blocks, 256, 0, st>>>(s->d, (const SlowRec*)s->slow.ptr, s->dnslow, s->dstats, s->dadded);
+    B2_CHECK_LAUNCH();
+    return 0;
+}
+
+int b2_sensor_end_accumulate(b2_sensor* s) { return launch_add_delta(s, 1.0, 0); }
 
 extern "C" int b2_plain_accumulate(b2_sensor* s, int64_t n, const double* x, const double* y, const double* flux,
                                    int where, double* added_flux) {

@@ -267,8 +267,17 @@ class PhotonPool:
         self.opt.index_ratio = float(index_ratio)
         self.opt.seed = self.seed
 
-    def process(self, dp: DevicePhotons, image, resume: bool, recalc: bool, sample=True, want_stats=False):
-        """Run the chain on a device pool and accumulate onto the sensor's bound image."""
+    def process(self, dp: DevicePhotons, image, resume: bool, recalc: bool, sample=True, want_stats=False,
+                fused=None, write_back=False):
+        """Run the chain on a device pool and accumulate onto the sensor's bound image.
+
+        ``fused`` (default: whenever the sensor runs the pooled cadence ``nrecalc == 0``): one
+        kernel per batch, photon -> charge deposit without intermediate arrays (``b2_pool_step``);
+        otherwise the three separate kernels.  Both give identical images."""
+        if fused is None:
+            fused = bool(sample) and self.sensor.pod.nrecalc == 0.0
+        if fused:
+            return self._process_fused(dp, image, resume, recalc, want_stats, write_back)
         if sample:
             self.ctx.sample_time_pupil(dp.time, dp.pupil_u, dp.pupil_v, self.t0, self.exptime, self.r_inner,
                                        self.r_outer, self.seed, self.offset)
@@ -281,3 +290,28 @@ class PhotonPool:
         added = self.sensor.accumulate(dp, image, resume=resume, recalc=recalc, sync_image=False,
                                        want_stats=want_stats)
         return added, stats
+
+    def _process_fused(self, dp, image, resume, recalc, want_stats, write_back):
+        import ctypes as C
+
+        sensor = self.sensor
+        if resume and image is not sensor._last_image:
+            raise _lib.B2Error("image must be the same as used for the last accumulate call if resume is True")
+        if not resume:
+            sensor._bind(image)
+        sensor._last_image = image
+        self.opt.photon_offset = self.offset
+        ostats = _abi.B2OpticsStats() if want_stats else None
+        astats = _abi.B2AccumStats() if want_stats else None
+        _lib.check(_lib.load().b2_pool_step(
+            self.ctx.handle, sensor._h, dp.n, _lib.ptr(dp.x), _lib.ptr(dp.y), _lib.ptr(dp.dxdz), _lib.ptr(dp.dydz),
+            _lib.ptr(dp.flux), _lib.ptr(dp.wavelength), C.byref(self.opt), self.t0, self.exptime, self.r_inner,
+            self.r_outer, self.seed, sensor._seed & 0xFFFFFFFFFFFFFFFF, self.offset, int(bool(resume)),
+            int(bool(recalc)), int(bool(write_back)), C.byref(ostats) if want_stats else None,
+            C.byref(astats) if want_stats else None))
+        self.offset += dp.n
+        sensor._photon_offset += dp.n
+        sensor.last_stats = astats
+        if write_back:
+            dp._has.update(dxdz=True, dydz=True)
+        return (astats.added_flux if want_stats else None), ostats

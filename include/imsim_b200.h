@@ -237,6 +237,11 @@ int b2_fma_peak(b2_ctx* ctx, int32_t fp64, double* tflops);
 /* measurement aid: with B2_TIMING=1 in the environment every kernel launch is bracketed by CUDA
    events on its stream; this returns {"kernel": [launches, total_ms], ...} as JSON and clears the log */
 int b2_timing_report(char* buf, int64_t cap);
+/* measurement aid for the roofline of the dominant kernel: when switched on, b2_pool_step and
+   b2_rubin_optics bracket their main kernel with CUDA events on the launching stream;
+   b2_ctx_kernel_ms returns the summed durations and the number of launches, and clears the list */
+int b2_ctx_record_kernel_events(b2_ctx* ctx, int32_t on);
+int b2_ctx_kernel_ms(b2_ctx* ctx, double* total_ms, int64_t* count);
 
 /* replaces: base['det_telescope'] (imsim/telescope_loader.py:463) as consumed by
    imsim/photon_ops.py:108-123 */
@@ -321,6 +326,19 @@ int b2_sensor_pixel_areas(b2_sensor* s, int32_t orig_center_x, int32_t orig_cent
    (imsim/photon_pooling.py:139-140,212) */
 int b2_plain_accumulate(b2_sensor* s, int64_t n, const double* x, const double* y, const double* flux,
                         int where, double* added_flux);
+/* One photon batch of the pooled pipeline as a single kernel, on DEVICE arrays
+   (imsim/photon_pooling.py:149-160 with the op list of config/imsim-config.yaml:281-320):
+   TimeSampler + PupilAnnulusSampler -> [PhotonDCR] -> RubinDiffractionOptics -> FocusDepth -> Refraction ->
+   SiliconSensor.accumulate(photons, image, resume, recalc).  Needs nrecalc == 0 (pooled cadence).
+   x, y, flux in (pixel positions of the pooled photons), wl_nm in; if write_back != 0 the traced
+   photons (x, y, dxdz, dydz, flux) are stored like the separate ops would leave them.
+   Draws: sampler Philox(sampler_seed), kick Philox(opt->seed), sensor Philox(sensor_seed), all
+   counted from photon_offset (opt->photon_offset for the kick) -- identical to the unfused calls. */
+int b2_pool_step(b2_ctx* ctx, b2_sensor* sensor, int64_t n, double* x, double* y, double* dxdz, double* dydz,
+                 double* flux, const double* wl_nm, const B2OpticsOptions* opt, double t0, double exptime,
+                 double r_inner, double r_outer, uint64_t sampler_seed, uint64_t sensor_seed,
+                 uint64_t photon_offset, int32_t resume, int32_t recalc, int32_t write_back,
+                 B2OpticsStats* ostats, B2AccumStats* astats);
 /* debug/inspection: copy boundary state of pixel (ix,iy) in image coords:
    poly: (4*nv+4)*2 doubles in polygon order; bounds: inner[4], outer[4] (xmin,xmax,ymin,ymax) */
 int b2_sensor_get_pixel(b2_sensor* s, int32_t ix, int32_t iy, double* poly, double* bounds);

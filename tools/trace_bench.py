@@ -43,3 +43,39 @@ for i in range(8):
 ms = float(np.median(times[3:]))
 print("OCC=%s n=%d  %.3f ms  %.3e photons/s  vignetted frac %.4f" % (os.environ.get("B2_OPTICS_OCC", "default"), n, ms,
                                                                       n / ms * 1e3, float((dp.flux == 0).double().mean())))
+
+# ---- decomposition: no diffraction; trace only (k_trace_rays on stop-plane rays)
+def timeit(fn, reps=6):
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts[2:]))
+
+ctx.set_diffraction(None)
+def run_nodif():
+    ctx.rubin_optics(dp.x, dp.y, dp.dxdz, dp.dydz, dp.flux, dp.wavelength, dp.pupil_u, dp.pupil_v, dp.time,
+                     options=opt, want_stats=False)
+for f in ("x", "y", "wavelength", "flux"):
+    getattr(dp, f).copy_(getattr(src, f))
+ms = timeit(run_nodif)
+print("  no diffraction: %.3f ms  %.3e photons/s" % (ms, n / ms * 1e3))
+vx, vy, vz = (torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(3))
+for f in ("x", "y"):
+    getattr(dp, f).copy_(getattr(src, f))
+ms = timeit(lambda: ctx.xy_to_v(dp.x, dp.y, out=(vx, vy, vz)))
+print("  xy_to_v only:   %.3f ms  %.3e photons/s" % (ms, n / ms * 1e3))
+z = torch.zeros(n, dtype=torch.float64, device="cuda")
+t = torch.zeros(n, dtype=torch.float64, device="cuda")
+wl_m = dp.wavelength * 1e-9
+vig = torch.zeros(n, dtype=torch.uint8, device="cuda")
+fail = torch.zeros(n, dtype=torch.uint8, device="cuda")
+rx, ry = dp.pupil_u.clone(), dp.pupil_v.clone()
+def run_trace():
+    rx.copy_(dp.pupil_u); ry.copy_(dp.pupil_v); z.zero_(); t.zero_()
+    a, b, c = vx.clone(), vy.clone(), vz.clone()
+    ctx.trace_rays(rx, ry, z, a, b, c, t, wl_m, vig, fail)
+base = timeit(lambda: (rx.copy_(dp.pupil_u), ry.copy_(dp.pupil_v), z.zero_(), t.zero_(), vx.clone(), vy.clone(), vz.clone()))
+ms = timeit(run_trace) - base
+print("  trace_rays only: %.3f ms  %.3e photons/s" % (ms, n / ms * 1e3))
