@@ -52,55 +52,75 @@ def dist_info():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons.  Started before the warm-up (nvidia-smi needs ~0.3 s to
+    produce its first line) and sampled every 20 ms; the summary uses the samples that fall inside
+    the timed window, or, if the window is shorter than the sampling period, the samples taken while
+    the GPU was under load (warm-up + timed region)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.samples = []
+        self.samples = []  # (wall time, fields)
         self.proc = None
+        self.window = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.samples and time.time() - t0 < 3.0:  # wait for the first line
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.time(), line.strip()))
+
+    def mark(self, t_begin, t_end):
+        self.window = (t_begin, t_end)
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             pass
-        sm, mx, reasons, power = [], [], set(), []
-        for s in self.samples:
+        rows = []
+        for ts, s in self.samples:
             f = [t.strip() for t in s.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-                power.append(float(f[3]))
+                rows.append((ts, float(f[1]), float(f[2]), float(f[3]), f[5:9], float(f[9])))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        sel, how = [], "timed window"
+        if self.window:
+            sel = [r for r in rows if self.window[0] - 0.02 <= r[0] <= self.window[1] + 0.02]
+        if not sel:
+            sel, how = [r for r in rows if r[5] > 50.0], "under load (warm-up + timed region)"
+        if not sel:
+            sel, how = rows, "all samples"
+        reasons = set()
+        for r in sel:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median([r[1] for r in sel])) if sel else None,
+                "sm_max_mhz": max(r[2] for r in sel) if sel else None,
+                "power_w_max": max(r[3] for r in sel) if sel else None, "reasons": sorted(reasons),
+                "samples": len(sel), "selection": how}
 
 
 def sensor_inputs():
@@ -271,6 +291,8 @@ def main():
 
     # ---- device-resident steps -------------------------------------------------------
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    clocks = ClockSampler(local)
+    clocks.start()
     for i in range(W):
         refill(work[i % 2])
         pool.process(work[i % 2], image, resume=True, recalc=True)
@@ -281,11 +303,9 @@ def main():
         timing_report()  # drop warm-up launches
     ctx.kernel_ms()
     ctx.record_kernel_events(True)
-    clocks = ClockSampler(local)
-    clocks.start()
     l0 = launch_count()
     step_ms = []
-    t_region0 = time.perf_counter()
+    t_region0_wall = time.time()
     for i in range(K):
         dp = work[i % 2]
         refill(dp)  # untimed input restore (the ops work in place); events bracket only the path
@@ -304,6 +324,7 @@ def main():
             pool.process(dp, image, resume=True, recalc=True, fused=True)
         ev[i][1].record()
     barrier()
+    clocks.mark(t_region0_wall, time.time())
     launches = launch_count() - l0
     clk = clocks.stop()
     if args.kernel_timing and rank == 0:
