@@ -345,23 +345,18 @@ def main():
     total_ms_max = float(tt.item())
     value = world * P * K / (total_ms_max * 1e-3)
 
-    # ---- end-to-end steps: host pinned -> H2D -> path -> D2H(image + deposited flux) ----
-    e2e_K = max(2, min(K, 4))
+    # ---- end-to-end steps through the public host-facing API: pinned host batches -> H2D (double
+    # buffered on a copy stream) -> b2_pool_step -> D2H of the image after every batch ----
+    e2e_K = max(3, min(K, 6))
+    host_batches = [pinned] * e2e_K
+    pool.run_host_batches(host_batches[:2], image, first_resume=True)  # warm the pipeline
     barrier()
-    e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(e2e_K)]
-    h2d = d2h = 0
-    for i in range(e2e_K + 1):  # one warm-up pass
-        dp = work[i % 2]
-        if i > 0:
-            e_ev[i - 1][0].record()
-        h2d = dp.upload(pinned)
-        pool.process(dp, image, resume=True, recalc=True, sample=True, want_stats=True)
-        sensor.read_image(image)
-        d2h = image.array.nbytes + 8 + 56
-        if i > 0:
-            e_ev[i - 1][1].record()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    h2d, d2h = pool.run_host_batches(host_batches, image, first_resume=True)
+    e1.record()
     barrier()
-    e_ms = float(np.sum([a.elapsed_time(b) for a, b in e_ev]))
+    e_ms = float(e0.elapsed_time(e1))
     et = torch.tensor([e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(et, op=dist.ReduceOp.MAX)

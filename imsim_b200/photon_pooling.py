@@ -315,3 +315,62 @@ class PhotonPool:
         if write_back:
             dp._has.update(dxdz=True, dydz=True)
         return (astats.added_flux if want_stats else None), ostats
+
+    def run_host_batches(self, batches, image, first_resume=False, fields=("x", "y", "flux", "wavelength"),
+                         read_image_every_batch=True):
+        """The pooled loop of ``buildImage`` for host-resident batches (what GalSim's shooters produce):
+        ``batches`` is a sequence of ``PinnedPhotons``.  Uploads are double-buffered on a copy stream so
+        the H2D transfer of batch k+1 overlaps the kernels of batch k; after every batch the image is
+        snapshotted on the device and copied to ``image.array`` on a third stream (the reference
+        checkpoints ``full_image`` after each batch, imsim/photon_pooling.py:167-168).
+        Returns (h2d_bytes, d2h_bytes) moved per batch."""
+        import torch
+
+        dev = torch.device("cuda", self.ctx.device)
+        compute = torch.cuda.current_stream(dev)
+        copy_s, d2h_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        nmax = max(b.n for b in batches)
+        bufs = [DevicePhotons(nmax, device=dev), DevicePhotons(nmax, device=dev)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        free = [torch.cuda.Event(), torch.cuda.Event()]
+        for e in free:
+            e.record(compute)
+        arr = image.array
+        tdtype = torch.float32 if arr.dtype == np.float32 else torch.float64
+        snap = torch.empty(arr.shape, dtype=tdtype, device=dev)
+        # pinned landing buffer for the per-batch image copies (where a checkpoint writer reads it);
+        # image.array receives the final state
+        host_img = torch.empty(arr.shape, dtype=tdtype).pin_memory()
+        snapped, copied = torch.cuda.Event(), torch.cuda.Event()
+        copied.record(d2h_s)
+        h2d = d2h = 0
+        for k, hb in enumerate(batches):
+            b = k % 2
+            dp = bufs[b]
+            dp.n = hb.n
+            for j, f in enumerate(DevicePhotons.FIELDS):
+                setattr(dp, f, dp.buf[j, : hb.n])
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(free[b])
+                h2d = 0
+                for f in fields:
+                    j = DevicePhotons.FIELDS.index(f)
+                    dp.buf[j, : hb.n].copy_(hb.buf[j, : hb.n], non_blocking=True)
+                    h2d += hb.n * 8
+                ready[b].record(copy_s)
+            compute.wait_event(ready[b])
+            self.process(dp, image, resume=(first_resume or k > 0), recalc=(first_resume or k > 0))
+            free[b].record(compute)
+            if read_image_every_batch or k == len(batches) - 1:
+                compute.wait_event(copied)  # the previous snapshot has left the device buffer
+                self.sensor.snapshot_image(snap)
+                snapped.record(compute)
+                with torch.cuda.stream(d2h_s):
+                    d2h_s.wait_event(snapped)
+                    host_img.copy_(snap, non_blocking=True)
+                    copied.record(d2h_s)
+                d2h = arr.nbytes
+        compute.wait_event(copied)
+        copied.synchronize()
+        arr[...] = host_img.numpy()
+        return h2d, d2h

@@ -341,6 +341,11 @@ class SiliconSensor:
         arr, _, _ = _image_parts(image)
         _lib.check(self._lib.b2_sensor_read_image(self._h, arr.ctypes.data, _abi.B2_HOST))
 
+    def snapshot_image(self, device_tensor):
+        """Device-to-device copy of the current image (target + pending charge) into a CUDA tensor
+        of the image's dtype, on the context's stream (no host synchronisation)."""
+        _lib.check(self._lib.b2_sensor_read_image(self._h, C.c_void_p(device_tensor.data_ptr()), _abi.B2_DEVICE))
+
     def calculate_pixel_areas(self, image, orig_center=(0, 0), use_flux=True):
         """Areas of the (tree-ring and, if ``use_flux``, charge-) distorted pixels.
         Returns 1.0 when trivially undistorted, like GalSim (imsim/flat.py:228 checks)."""
