@@ -90,6 +90,8 @@ _SIGNATURES = {
                                        C.c_uint64, C.c_uint64, C.c_int]),
     "b2_flat_photons": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp,
                                   C.c_int32, C.c_uint64, C.c_uint64]),
+    "b2_object_photons": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32, vp, vp, C.c_int32,
+                                    C.c_uint64, C.c_uint64]),
     "b2_sensor_create": (C.c_int, [vp, C.POINTER(_abi.B2SensorConfig), vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
     "b2_sensor_destroy": (C.c_int, [vp]),
     "b2_sensor_bind_image": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int]),

@@ -144,6 +144,16 @@ class OpticsContext:
                                              float(bounds[2]), float(bounds[3]), _lib.ptr(cdf), _lib.ptr(cdf_wave),
                                              ncdf, int(seed), int(photon_offset)))
 
+    def object_photons(self, x, y, flux, wavelength, obj_x, obj_y, obj_sigma, obj_cum, cdf=None, cdf_wave=None,
+                       seed=0, photon_offset=0):
+        """Pooled photons of point-like objects behind a Gaussian PSF, generated in HBM
+        (``obj_cum``: int64 CUDA tensor of nobj+1 cumulative photon counts)."""
+        ncdf = 0 if cdf is None else int(cdf.shape[0])
+        _lib.check(self._lib.b2_object_photons(
+            self._h, x.shape[0], _lib.ptr(x), _lib.ptr(y), _lib.ptr(flux), _lib.ptr(wavelength), _lib.ptr(obj_x),
+            _lib.ptr(obj_y), _lib.ptr(obj_sigma), C.c_void_p(obj_cum.data_ptr()), int(obj_x.shape[0]), _lib.ptr(cdf),
+            _lib.ptr(cdf_wave), ncdf, int(seed), int(photon_offset)))
+
     @property
     def handle(self):
         return self._h

@@ -175,6 +175,49 @@ k_flat_photons(int64_t n, double* __restrict__ x, double* __restrict__ y, double
     }
 }
 
+// Photons of a table of point-like objects seen through a Gaussian PSF, generated in HBM: thread k
+// finds its object by binary search in the cumulative photon counts (the device form of
+// merge_photon_arrays o build_stamps, imsim/photon_pooling.py:151-152), draws the PSF offset and
+// the wavelength.  First step of SURVEY section 8 f1 (stage-1 generation on device): DeltaFunction
+// objects x Gaussian PSF only; flux 1 per photon.
+__global__ void __launch_bounds__(256)
+k_object_photons(int64_t n, double* __restrict__ x, double* __restrict__ y, double* __restrict__ flux,
+                 double* __restrict__ wl, const double* __restrict__ obj_x, const double* __restrict__ obj_y,
+                 const double* __restrict__ obj_sigma, const int64_t* __restrict__ obj_cum, int32_t nobj,
+                 const double* __restrict__ cdf, const double* __restrict__ cdf_wave, int ncdf, uint64_t seed,
+                 uint64_t offset) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // object j owns photons [obj_cum[j], obj_cum[j+1])
+    int lo = 0, hi = nobj;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(obj_cum + mid) <= i) lo = mid; else hi = mid;
+    }
+    uint32_t r[4];
+    philox4(seed, offset + (uint64_t)i, 7u, r);
+    float u1 = ((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    float u2 = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    float rad = sqrtf(-2.0f * logf(u1));
+    double sg = __ldg(obj_sigma + lo);
+    x[i] = __ldg(obj_x + lo) + sg * (double)(rad * cs);
+    y[i] = __ldg(obj_y + lo) + sg * (double)(rad * sn);
+    flux[i] = 1.0;
+    if (wl) {
+        double u = ((double)r[2] * 4294967296.0 + (double)r[3] + 0.5) * (1.0 / 18446744073709551616.0);
+        int a = 0, b = ncdf - 1;
+        while (b - a > 1) {
+            int mid = (a + b) >> 1;
+            if (__ldg(cdf + mid) <= u) a = mid; else b = mid;
+        }
+        double c0 = __ldg(cdf + a), c1 = __ldg(cdf + b);
+        double f = (c1 > c0) ? (u - c0) / (c1 - c0) : 0.0;
+        wl[i] = __ldg(cdf_wave + a) + f * (__ldg(cdf_wave + b) - __ldg(cdf_wave + a));
+    }
+}
+
 // ------------------------------------------------------------------ host side
 static inline int nblocks(int64_t n, int bs = 256) { return (int)((n + bs - 1) / bs); }
 
@@ -618,6 +661,21 @@ extern "C" int b2_flat_photons(b2_ctx* ctx, int64_t n, double* x, double* y, dou
     if (n <= 0) return 0;
     B2_TIMED("k_flat_photons", ctx->stream);
     k_flat_photons<<<nblocks(n), 256, 0, ctx->stream>>>(n, x, y, flux, wl, xlo, xhi, ylo, yhi, cdf, cdf_wave, ncdf, seed, offset);
+    B2_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b2_object_photons(b2_ctx* ctx, int64_t n, double* x, double* y, double* flux, double* wl,
+                                 const double* obj_x, const double* obj_y, const double* obj_sigma,
+                                 const int64_t* obj_cum, int32_t nobj, const double* cdf, const double* cdf_wave,
+                                 int32_t ncdf, uint64_t seed, uint64_t offset) {
+    B2_REQUIRE(ctx && x && y && flux && obj_x && obj_y && obj_sigma && obj_cum && nobj > 0, "b2_object_photons: null argument");
+    B2_REQUIRE(!wl || (cdf && cdf_wave && ncdf >= 2), "b2_object_photons: wavelength sampling needs a CDF table");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    if (n <= 0) return 0;
+    B2_TIMED("k_object_photons", ctx->stream);
+    k_object_photons<<<nblocks(n), 256, 0, ctx->stream>>>(n, x, y, flux, wl, obj_x, obj_y, obj_sigma, obj_cum, nobj, cdf,
+                                                          cdf_wave, ncdf, seed, offset);
     B2_CHECK_LAUNCH();
     return 0;
 }

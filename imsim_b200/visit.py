@@ -1,0 +1,130 @@
+"""Synthetic visit driver: the per-detector pooled pipeline of one LSSTCam exposure, sharded by
+detector over the GPUs of a box (imsim/ccd.py:72-89 iterates the same 189 CCDs
+as output files, config/imsim-config.yaml:326 `output.nproc` is the reference's scaling knob).
+
+For every detector of this rank:
+  1. set-up: telescope with the detector's height offset, WCS pair fitted to chief rays, detector affine,
+     sensor model by vendor + that detector's tree rings                (imsim/lsst_image.py:93-103)
+  2. object table -> per-batch integer photon counts                     (imsim/photon_pooling.py:279-313)
+  3. for each of nbatch batches: photons generated in HBM (k_object_photons), then ONE fused kernel
+     sampler -> optics -> sensor (b2_pool_step) with recalc=True         (photon_pooling.py:141-160)
+  4. image back to the host (where the reference writes the e-image / checkpoint)
+No collective on the photon path; ``sharding.gather_visit_metadata`` collects per-CCD records.
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _abi
+from .context import OpticsContext
+from .detector import lsstcam_like
+from .diffraction import RUBIN_LATITUDE, diffraction_config
+from .photon_pooling import DevicePhotons, LSST_PhotonPoolingImageBuilder, ObjectInfo, PhotonPool, ProcessingMode
+from .sensor import Image, SiliconSensor
+from .synthetic import gpu_tracer, make_detector_setup
+
+#: ITL rafts of LSSTCam (the rest of the science rafts carry e2v CCDs)
+ITL_RAFTS = {"R01", "R02", "R03", "R10", "R20", "R41", "R42", "R43"}
+
+
+def vendor_of(det_name: str) -> str:
+    return "itl" if det_name[:3] in ITL_RAFTS else "e2v"
+
+
+def synthetic_objects(n_obj: int, nx: int, ny: int, seed: int, total_photons: float):
+    """Object table of a dense field: positions uniform on the CCD, fluxes dN/dm ~ 10^(0.3 m) over 9
+    magnitudes, scaled to ``total_photons``; PSF sigma 0.7'' FWHM at 0.2''/px."""
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(0, nx, n_obj)
+    y = rng.uniform(0, ny, n_obj)
+    u = rng.uniform(0, 1, n_obj)
+    m = np.log10(1 + u * (10 ** (0.3 * 9) - 1)) / 0.3  # 0 (bright) .. 9 (faint), more faint ones
+    w = 10 ** (-0.4 * m)
+    flux = np.maximum(np.round(w / w.sum() * total_photons), 1).astype(np.int64)
+    sigma = np.full(n_obj, 0.7 / 2.355 / 0.2)
+    return x, y, flux, sigma
+
+
+class DetectorRunner:
+    """Reusable per-GPU state: one context, one sensor object per vendor model (re-bound per detector)."""
+
+    def __init__(self, device: int, sensor_models: Dict[str, tuple], absorption_table, tree_rings=None,
+                 band: str = "r", rot_tel_pos: float = np.radians(60.0), altitude=np.radians(67.0),
+                 azimuth=np.radians(213.0), exptime: float = 30.0, seed: int = 1):
+        import torch
+
+        self.torch = torch
+        self.device = device
+        self.ctx = OpticsContext(device=device, stream=torch.cuda.current_stream(torch.device("cuda", device)))
+        self.tracer = gpu_tracer(self.ctx)
+        self.sensor_models = sensor_models
+        self.absorption = absorption_table
+        self.tree_rings = tree_rings or {}
+        self.band, self.rot_tel_pos, self.exptime, self.seed = band, rot_tel_pos, exptime, seed
+        self.dif = diffraction_config(latitude=RUBIN_LATITUDE, altitude=altitude, azimuth=azimuth)
+        self._sensors: Dict[tuple, SiliconSensor] = {}
+
+    def sensor_for(self, det_name: str) -> SiliconSensor:
+        cfg, dat = self.sensor_models[vendor_of(det_name)]
+        tr = self.tree_rings.get(det_name)
+        # a sensor owns its tree-ring table; detectors differ, so sensors are built per detector and
+        # closed after use (boundary arrays are the big allocation: ~2.5 GB per 4k x 4k CCD)
+        return SiliconSensor(config=cfg, vertex_data=dat, nrecalc=0, strength=1.0, rng=self.seed,
+                             treering_func=tr[1] if tr else None, treering_center=tr[0] if tr else (0.0, 0.0),
+                             absorption_table=self.absorption, context=self.ctx)
+
+    def run(self, det_name: str, objects, nbatch: int = 10, wavelength_cdf=None, det_index: int = 0) -> dict:
+        torch = self.torch
+        dev = torch.device("cuda", self.device)
+        t0 = time.perf_counter()
+        det = lsstcam_like(det_name)
+        su = make_detector_setup(self.tracer, det_name, band=self.band, rot_tel_pos=self.rot_tel_pos, detector=det)
+        self.ctx.set_telescope(su.telescope)
+        self.ctx.set_wcs(su.img_wcs, su.icrf_to_field)
+        self.ctx.set_detector(su.detector)
+        self.ctx.set_diffraction(self.dif)
+        sensor = self.sensor_for(det_name)
+        image = Image(np.zeros((det.ny, det.nx), np.float32), 0, 0)
+        pool = PhotonPool(self.ctx, sensor, exptime=self.exptime, seed=self.seed + 1000 * det_index)
+        ox, oy, oflux, osig = objects
+        infos = [ObjectInfo(i, int(f), ProcessingMode.PHOT) for i, f in enumerate(oflux)]
+        _, phot, faint = LSST_PhotonPoolingImageBuilder.partition_objects(infos, nbatch)
+        batches = LSST_PhotonPoolingImageBuilder.make_photon_batches({}, {"random_seed": self.seed + det_index}, None,
+                                                                     phot, faint, nbatch)
+        d_ox = torch.as_tensor(ox, device=dev)
+        d_oy = torch.as_tensor(oy, device=dev)
+        d_os = torch.as_tensor(osig, device=dev)
+        cdf = cdfw = None
+        if wavelength_cdf is not None:
+            cdf, cdfw = (torch.as_tensor(a, device=dev) for a in wavelength_cdf)
+        t_setup = time.perf_counter() - t0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n_total = 0
+        for k, batch in enumerate(batches):
+            idx = np.fromiter((o.index for o in batch), dtype=np.int64, count=len(batch))
+            cnt = np.fromiter((int(o.phot_flux) for o in batch), dtype=np.int64, count=len(batch))
+            keep = cnt > 0
+            idx, cnt = idx[keep], cnt[keep]
+            n = int(cnt.sum())
+            if n == 0:
+                continue
+            cum = torch.as_tensor(np.concatenate([[0], np.cumsum(cnt)]), device=dev)
+            sel = torch.as_tensor(idx, device=dev)
+            dp = DevicePhotons(n, device=dev, fields=("x", "y", "flux", "wavelength"))
+            self.ctx.object_photons(dp.x, dp.y, dp.flux, dp.wavelength, d_ox[sel].contiguous(), d_oy[sel].contiguous(),
+                                    d_os[sel].contiguous(), cum, cdf, cdfw, seed=self.seed + 7 * det_index,
+                                    photon_offset=n_total)
+            pool.process(dp, image, resume=(k > 0), recalc=(k > 0), fused=True)
+            n_total += n
+        sensor.read_image(image)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        rec = {"det_name": det_name, "device": self.device, "photons": n_total, "nbatch": len(batches),
+               "electrons": float(image.array.sum(dtype=np.float64)), "gpu_ms": float(e0.elapsed_time(e1)),
+               "setup_ms": 1e3 * t_setup}
+        sensor.close()
+        return rec, image

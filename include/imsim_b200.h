@@ -291,6 +291,14 @@ int b2_flat_photons(b2_ctx* ctx, int64_t n, double* x, double* y, double* flux, 
                     double ylo, double yhi, const double* cdf, const double* cdf_wave, int32_t ncdf, uint64_t seed,
                     uint64_t photon_offset);
 
+/* photons of a table of point-like objects behind a Gaussian PSF, generated on the device: object j
+   owns photons [obj_cum[j], obj_cum[j+1]) of the pool (obj_cum has nobj+1 entries, obj_cum[nobj] = n),
+   i.e. build_stamps + merge_photon_arrays (imsim/photon_pooling.py:151-152) for DeltaFunction objects
+   with their per-batch photon counts (photon_pooling.py:300-304).  DEVICE pointers only. */
+int b2_object_photons(b2_ctx* ctx, int64_t n, double* x, double* y, double* flux, double* wl, const double* obj_x,
+                      const double* obj_y, const double* obj_sigma, const int64_t* obj_cum, int32_t nobj,
+                      const double* cdf, const double* cdf_wave, int32_t ncdf, uint64_t seed, uint64_t photon_offset);
+
 /* ---- silicon sensor ---------------------------------------------------- */
 /* replaces galsim.SiliconSensor.__init__ (imsim/lsst_image.py:93-103,
    config/imsim-config.yaml:230-235).  vertex_data: the .dat table,

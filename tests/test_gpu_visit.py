@@ -1,0 +1,58 @@
+"""Device-side photon generation and the per-detector visit runner."""
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def test_object_photons_statistics():
+    import torch
+
+    from imsim_b200 import OpticsContext
+    from imsim_b200.flat import wavelength_cdf
+    from imsim_b200.photon_pooling import DevicePhotons
+
+    ctx = OpticsContext(device=0, stream=torch.cuda.current_stream())
+    ox = np.array([100.0, 2000.5, 3999.0])
+    oy = np.array([50.0, 1000.25, 3900.0])
+    cnt = np.array([200000, 1, 300000])
+    sig = np.array([1.5, 2.0, 0.5])
+    n = int(cnt.sum())
+    cum = torch.as_tensor(np.concatenate([[0], np.cumsum(cnt)]), device="cuda")
+    wave = np.linspace(500, 700, 21)
+    cdf = wavelength_cdf(wave, np.linspace(1, 3, 21))
+    dp = DevicePhotons(n)
+    ctx.object_photons(dp.x, dp.y, dp.flux, dp.wavelength, *(torch.as_tensor(a, device="cuda") for a in (ox, oy, sig)),
+                       cum, *(torch.as_tensor(a, device="cuda") for a in cdf), seed=3)
+    x, y, wl, fl = (t.cpu().numpy() for t in (dp.x, dp.y, dp.wavelength, dp.flux))
+    assert np.all(fl == 1.0)
+    a, b = slice(0, 200000), slice(200001, n)
+    assert abs(x[a].mean() - 100.0) < 0.02 and abs(y[a].std() - 1.5) < 0.02
+    assert abs(x[b].mean() - 3999.0) < 0.01 and abs(x[b].std() - 0.5) < 0.01
+    assert abs(x[200000] - 2000.5) < 12 and abs(y[200000] - 1000.25) < 12
+    assert wl.min() >= 500 and wl.max() <= 700
+    # pdf rises linearly 1 -> 3: mean wavelength = 500 + 200 * (1/2 + 1/12 * 2/2) = 616.67
+    assert abs(wl.mean() - (500 + 200 * (0.5 + (3 - 1) / (6.0 * (3 + 1)) * 1.0))) < 0.5
+
+
+def test_detector_runner_conserves_photons():
+    from imsim_b200.flat import wavelength_cdf
+    from imsim_b200.visit import DetectorRunner, synthetic_objects, vendor_of
+
+    assert vendor_of("R22_S11") == "e2v" and vendor_of("R01_S00") == "itl"
+    models = {"e2v": helpers.sensor_model("lsst_e2v_50_4"), "itl": helpers.sensor_model("lsst_itl_50_4")}
+    runner = DetectorRunner(0, models, helpers.absorption(), tree_rings={"R22_S11": helpers.tree_ring_table()})
+    objs = synthetic_objects(2000, 4096, 4004, seed=1, total_photons=3e6)
+    wave = np.linspace(550, 690, 15)
+    rec, image = runner.run("R22_S11", objs, nbatch=10, wavelength_cdf=wavelength_cdf(wave, np.ones_like(wave)))
+    assert rec["photons"] == int(objs[2].sum()) and rec["nbatch"] == 10
+    # r-band photons: nearly all convert; a few are vignetted or fall off the chip near the edges
+    assert 0.9 * rec["photons"] < rec["electrons"] <= rec["photons"]
+    # the brightest object shows up where it was put (optics keep photons within a few pixels)
+    k = int(np.argmax(objs[2]))
+    cx, cy = int(round(objs[0][k])), int(round(objs[1][k]))
+    if 10 < cx < 4086 and 10 < cy < 3994:
+        stamp = image.array[cy - 8:cy + 9, cx - 8:cx + 9]
+        assert stamp.sum() > 0.7 * objs[2][k]
