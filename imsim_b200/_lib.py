@@ -94,6 +94,7 @@ _SIGNATURES = {
                                     C.c_uint64, C.c_uint64]),
     "b2_sensor_create": (C.c_int, [vp, C.POINTER(_abi.B2SensorConfig), vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
     "b2_sensor_destroy": (C.c_int, [vp]),
+    "b2_sensor_set_treerings": (C.c_int, [vp, C.c_double, C.c_double, vp, vp, vp, C.c_int32]),
     "b2_sensor_bind_image": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int]),
     "b2_sensor_read_image": (C.c_int, [vp, vp, C.c_int]),
     "b2_sensor_accumulate": (C.c_int, [vp, C.c_int64] + [vp] * 7 + [C.c_uint64, C.c_uint64, C.c_int32, C.c_int32,

@@ -671,6 +671,37 @@ extern "C" int b2_sensor_create(b2_ctx* ctx, const B2SensorConfig* cfg, const do
     return 0;
 }
 
+// replace the tree-ring table / centre of an existing sensor (next detector of the same vendor): the
+// per-image boundary arrays, the big allocation, are kept
+extern "C" int b2_sensor_set_treerings(b2_sensor* s, double cx, double cy, const double* tr_r, const double* tr_f,
+                                       const double* tr_y2, int32_t n) {
+    B2_REQUIRE(s, "b2_sensor_set_treerings: null sensor");
+    B2_REQUIRE(n <= 2 || (tr_r && tr_f), "b2_sensor_set_treerings: table missing");
+    b2_ctx* ctx = s->ctx;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    DevSensor& d = s->d;
+    d.trc[0] = cx;
+    d.trc[1] = cy;
+    s->cfg.treering_center[0] = cx;
+    s->cfg.treering_center[1] = cy;
+    d.ntr = n;
+    d.tr_spline = 0;
+    d.tr_r = d.tr_f = d.tr_y2 = nullptr;
+    if (n > 2) {
+        if (dev_upload(ctx, s->owned, tr_r, (size_t)n, &d.tr_r)) return 1;
+        if (dev_upload(ctx, s->owned, tr_f, (size_t)n, &d.tr_f)) return 1;
+        d.tr_max = tr_r[n - 1];
+        if (tr_y2) {
+            if (dev_upload(ctx, s->owned, tr_y2, (size_t)n, &d.tr_y2)) return 1;
+            d.tr_spline = 1;
+        }
+        B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    s->initialized = false;
+    return 0;
+}
+
 static void free_list(std::vector<void*>& v) {
     for (void* p : v) cudaFree(p);
     v.clear();

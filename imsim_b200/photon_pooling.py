@@ -167,6 +167,22 @@ class LSST_PhotonPoolingImageBuilder:
                 objects_by_mode[ProcessingMode.FAINT])
 
 
+def photon_batch_counts(phot_flux, modes_faint, nbatch: int, ud):
+    """Vectorised ``partition_objects`` + ``make_photon_batches`` for the device pipeline: integer
+    photon counts per (batch, object), identical to the list-based reference algebra
+    (imsim/photon_pooling.py:300-311,374-377).  ``phot_flux``: int64 array; ``modes_faint``: bool array
+    (True = FAINT); ``ud``: callable returning uniforms in [0, 1), called once per faint object in order."""
+    f = np.asarray(phot_flux, dtype=np.int64)
+    faint = np.asarray(modes_faint, dtype=bool) | (f < nbatch)
+    counts = np.zeros((nbatch, f.size), dtype=np.int64)
+    i = np.arange(nbatch, dtype=np.int64)[:, None]
+    bright = ~faint
+    counts[:, bright] = (f[None, bright] * (i + 1)) // nbatch - (f[None, bright] * i) // nbatch
+    for k in np.nonzero(faint)[0]:
+        counts[int(ud() * nbatch), k] = f[k]
+    return counts
+
+
 # ---------------------------------------------------------------------------
 # device-resident pool
 # ---------------------------------------------------------------------------

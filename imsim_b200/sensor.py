@@ -277,6 +277,19 @@ class SiliconSensor:
         return (np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(f, dtype=np.float64),
                 None if y2 is None else np.ascontiguousarray(y2, dtype=np.float64))
 
+    def set_treerings(self, treering_func, treering_center=(0.0, 0.0)):
+        """Switch to another detector's tree rings, keeping the device allocations."""
+        tr = self._treering_arrays(treering_func)
+        cx, cy = (treering_center.x, treering_center.y) if hasattr(treering_center, 'x') else treering_center
+        self.treering_func, self.treering_center, self._tr = treering_func, treering_center, tr
+        n = 0 if tr is None else len(tr[0])
+        _lib.check(self._lib.b2_sensor_set_treerings(
+            self._h, float(cx), float(cy), tr[0].ctypes.data if tr else None, tr[1].ctypes.data if tr else None,
+            tr[2].ctypes.data if (tr and tr[2] is not None) else None, n))
+        self.pod.treering_center[0], self.pod.treering_center[1] = float(cx), float(cy)
+        self.pod.n_treering = n
+        self._last_image = None
+
     @classmethod
     def simple_treerings(cls, amplitude=0.5, period=100., r_max=8000., dr=None):
         """``galsim.SiliconSensor.simple_treerings``: a cosine tree-ring table (used by

@@ -22,7 +22,7 @@ from . import _abi
 from .context import OpticsContext
 from .detector import lsstcam_like
 from .diffraction import RUBIN_LATITUDE, diffraction_config
-from .photon_pooling import DevicePhotons, LSST_PhotonPoolingImageBuilder, ObjectInfo, PhotonPool, ProcessingMode
+from .photon_pooling import DevicePhotons, PhotonPool, photon_batch_counts
 from .sensor import Image, SiliconSensor
 from .synthetic import gpu_tracer, make_detector_setup
 
@@ -68,13 +68,20 @@ class DetectorRunner:
         self._sensors: Dict[tuple, SiliconSensor] = {}
 
     def sensor_for(self, det_name: str) -> SiliconSensor:
-        cfg, dat = self.sensor_models[vendor_of(det_name)]
+        """One sensor object per vendor model, re-used across detectors: only the tree-ring table
+        changes (``set_treerings``); the ~2.5 GB of boundary arrays stay allocated."""
+        vendor = vendor_of(det_name)
         tr = self.tree_rings.get(det_name)
-        # a sensor owns its tree-ring table; detectors differ, so sensors are built per detector and
-        # closed after use (boundary arrays are the big allocation: ~2.5 GB per 4k x 4k CCD)
-        return SiliconSensor(config=cfg, vertex_data=dat, nrecalc=0, strength=1.0, rng=self.seed,
-                             treering_func=tr[1] if tr else None, treering_center=tr[0] if tr else (0.0, 0.0),
-                             absorption_table=self.absorption, context=self.ctx)
+        func, center = (tr[1], tr[0]) if tr else (None, (0.0, 0.0))
+        s = self._sensors.get(vendor)
+        if s is None:
+            cfg, dat = self.sensor_models[vendor]
+            s = SiliconSensor(config=cfg, vertex_data=dat, nrecalc=0, strength=1.0, rng=self.seed, treering_func=func,
+                              treering_center=center, absorption_table=self.absorption, context=self.ctx)
+            self._sensors[vendor] = s
+        else:
+            s.set_treerings(func, center)
+        return s
 
     def run(self, det_name: str, objects, nbatch: int = 10, wavelength_cdf=None, det_index: int = 0) -> dict:
         torch = self.torch
@@ -90,10 +97,8 @@ class DetectorRunner:
         image = Image(np.zeros((det.ny, det.nx), np.float32), 0, 0)
         pool = PhotonPool(self.ctx, sensor, exptime=self.exptime, seed=self.seed + 1000 * det_index)
         ox, oy, oflux, osig = objects
-        infos = [ObjectInfo(i, int(f), ProcessingMode.PHOT) for i, f in enumerate(oflux)]
-        _, phot, faint = LSST_PhotonPoolingImageBuilder.partition_objects(infos, nbatch)
-        batches = LSST_PhotonPoolingImageBuilder.make_photon_batches({}, {"random_seed": self.seed + det_index}, None,
-                                                                     phot, faint, nbatch)
+        gen = np.random.default_rng(self.seed + det_index)
+        counts = photon_batch_counts(oflux, np.zeros(len(oflux), bool), nbatch, gen.random)
         d_ox = torch.as_tensor(ox, device=dev)
         d_oy = torch.as_tensor(oy, device=dev)
         d_os = torch.as_tensor(osig, device=dev)
@@ -104,11 +109,10 @@ class DetectorRunner:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         n_total = 0
-        for k, batch in enumerate(batches):
-            idx = np.fromiter((o.index for o in batch), dtype=np.int64, count=len(batch))
-            cnt = np.fromiter((int(o.phot_flux) for o in batch), dtype=np.int64, count=len(batch))
-            keep = cnt > 0
-            idx, cnt = idx[keep], cnt[keep]
+        for k in range(nbatch):
+            cnt = counts[k]
+            idx = np.nonzero(cnt)[0]
+            cnt = cnt[idx]
             n = int(cnt.sum())
             if n == 0:
                 continue
@@ -123,8 +127,7 @@ class DetectorRunner:
         sensor.read_image(image)
         e1.record()
         torch.cuda.synchronize(dev)
-        rec = {"det_name": det_name, "device": self.device, "photons": n_total, "nbatch": len(batches),
+        rec = {"det_name": det_name, "device": self.device, "photons": n_total, "nbatch": nbatch,
                "electrons": float(image.array.sum(dtype=np.float64)), "gpu_ms": float(e0.elapsed_time(e1)),
                "setup_ms": 1e3 * t_setup}
-        sensor.close()
         return rec, image

@@ -310,6 +310,10 @@ int b2_sensor_create(b2_ctx* ctx, const B2SensorConfig* cfg, const double* verte
                      const double* treering_r, const double* treering_f, const double* treering_y2,
                      const double* abs_wave, const double* abs_len, b2_sensor** out);
 int b2_sensor_destroy(b2_sensor* s);
+/* new tree-ring table / centre for the next detector of the same vendor (config/imsim-config.yaml:233-235
+   rebuilds the sensor per image; this keeps the per-image boundary arrays allocated) */
+int b2_sensor_set_treerings(b2_sensor* s, double center_x, double center_y, const double* treering_r,
+                            const double* treering_f, const double* treering_y2, int32_t n);
 /* bind the image the next accumulate calls add to: bounds (xmin,ymin,nx,ny),
    dtype_bytes 4 (float32) or 8 (float64); pixels: row-major ny*nx, host or device per `where`.
    (galsim.Image passed to SiliconSensor.accumulate, imsim/photon_pooling.py:210) */

@@ -138,3 +138,28 @@ def test_merge_photon_arrays():
     np.testing.assert_array_equal(merged.x, np.concatenate([s.photons.x for s in stamps]))
     np.testing.assert_array_equal(merged.wavelength, np.concatenate([s.photons.wavelength for s in stamps]))
     assert merged.hasAllocatedWavelengths() and not merged.hasAllocatedAngles() and not merged.hasAllocatedPupil()
+
+
+def test_vectorised_batch_counts_equal_list_algebra():
+    from imsim_b200.photon_pooling import photon_batch_counts
+
+    rng = np.random.default_rng(3)
+    flux = rng.integers(0, 100000, 300)
+    flux[:20] = rng.integers(0, 11, 20)  # fewer photons than batches -> treated as faint
+    faint = np.zeros(300, bool)
+    faint[50:60] = True
+    nbatch = 11
+    infos = [ObjectInfo(i, int(f), ProcessingMode.FAINT if faint[i] else ProcessingMode.PHOT)
+             for i, f in enumerate(flux)]
+    _, phot, fnt = Builder.partition_objects(infos, nbatch)
+    draws = list(np.random.default_rng(9).random(len(fnt)))
+    it = iter(draws)
+    batches = Builder.make_photon_batches({}, {"rng": lambda: next(it)}, None, phot, fnt, nbatch)
+    it2 = iter(draws)
+    counts = photon_batch_counts(flux, faint, nbatch, lambda: next(it2))
+    ref = np.zeros_like(counts)
+    for b, batch in enumerate(batches):
+        for o in batch:
+            ref[b, o.index] += o.phot_flux
+    np.testing.assert_array_equal(counts, ref)
+    np.testing.assert_array_equal(counts.sum(axis=0), flux)
