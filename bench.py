@@ -37,10 +37,16 @@ METRIC = "photons/sec/GPU (optics+sensor)"
 UNIT = "photons/s"
 POOL = 1 << 25  # photons per step (33.5 M): every SoA array is 268 MB > L2 (126 MB)
 ALG_BYTES_TRACE = 96.0  # read x,y,wl,u,v,t,flux (56 B) + write x,y,dxdz,dydz,flux (40 B)
-ALG_FLOP_TRACE = 4000.0  # SURVEY 8d estimate of the reference's FP64 op count per photon (3.8-5.6 k)
-# fused k_pool_step = trace + sensor fast path: SURVEY 8d adds 56 B (6 reads + 1 atomic RMW) and ~100 FLOP
+# FP64 operations per photon of the reference arithmetic, INSTRUMENTED: oracle/count_flops.py compiles the
+# oracle with a counting scalar (add 1308 + mul 2012 + div 323 + sqrt 121 per photon for RubinDiffractionOptics
+# + Refraction; 15 transcendental calls not counted); pinned by tests/test_flop_count.py
+ALG_FLOP_TRACE = 3765.0
+# fused k_pool_step = trace + sensor fast path: SURVEY 8d adds 56 B (6 reads + 1 atomic RMW) and ~60 FLOP
 ALG_BYTES_POOL = 96.0 + 56.0
-ALG_FLOP_POOL = 4100.0
+ALG_FLOP_POOL = ALG_FLOP_TRACE + 60.0
+# DRAM traffic of k_pool_step<4> from `ncu --set full` (profiles/r01_k_pool_step_details.csv):
+# (1.188 GB read + 0.118 GB written) / 33554432 photons
+NCU_TRAFFIC_BYTES_PER_PHOTON_POOL = 38.9
 DETECTORS = ["R22_S11", "R21_S11", "R23_S11", "R12_S11", "R32_S11", "R22_S00", "R22_S22", "R11_S11"]
 
 
@@ -450,7 +456,10 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"kernel": dominant, "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                         "traffic": None if args.unfused else NCU_TRAFFIC_BYTES_PER_PHOTON_POOL * P,
+                         "traffic_source": "ncu --set full capture of the same kernel, per launch scaled to this pool "
+                                           "size (profiles/r01_k_pool_step_details.csv)", "peak_source": peak_src,
                          "kernel_ms": tr_ms, "share_of_step": tr_ms * K / total_ms,
                          "note": "kernel is FP64-pipe bound, see roofline_fp64"},
             "roofline_fp64": {"kernel": dominant, "bound": "fp64 fma pipe", "achieved": ach_tf,

@@ -28,7 +28,7 @@
 
 #include <stdint.h>
 
-#ifdef __cplusplus
+#if defined(__cplusplus) && !defined(B2_STRUCTS_ONLY)
 extern "C" {
 #endif
 
@@ -212,6 +212,7 @@ typedef struct {
     uint64_t n_dropped_bottom;  /* zconv < 0 */
 } B2AccumStats;
 
+#ifndef B2_STRUCTS_ONLY /* (the oracle's FLOP counter re-reads only the POD structs above) */
 typedef struct b2_ctx b2_ctx;
 typedef struct b2_sensor b2_sensor;
 
@@ -355,7 +356,8 @@ int b2_pool_step(b2_ctx* ctx, b2_sensor* sensor, int64_t n, double* x, double* y
    poly: (4*nv+4)*2 doubles in polygon order; bounds: inner[4], outer[4] (xmin,xmax,ymin,ymax) */
 int b2_sensor_get_pixel(b2_sensor* s, int32_t ix, int32_t iy, double* poly, double* bounds);
 
-#ifdef __cplusplus
+#endif /* B2_STRUCTS_ONLY */
+#if defined(__cplusplus) && !defined(B2_STRUCTS_ONLY)
 }
 #endif
 #endif /* IMSIM_B200_H */
