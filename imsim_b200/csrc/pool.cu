@@ -159,3 +159,147 @@ extern "C" int b2_pool_step(b2_ctx* ctx, b2_sensor* sensor, int64_t n, double* x
     }
     return 0;
 }
+
+// ------------------------------------------------------------------ photon-shot flat, fused
+// imsim/flat.py:239-264 shoots, per iteration, Poisson(counts * area) photons uniform over the bordered
+// section, samples their wavelengths and calls sensor.accumulate.  Uniform photons in random order make
+// every inner-box gather and every charge deposit a random DRAM access.  Here the photons of one
+// iteration are generated tile by tile (32 x 32 pixels) with per-tile Poisson counts drawn on the host --
+// the same distribution as N uniform photons in any order -- and go straight from registers to the
+// charge deposit: no photon array exists, gathers and atomics stay in one tile's cache lines.
+struct FlatParams {
+    int tiles_x, tiles_y, tile;      // tile grid over the bound image
+    double xlo, xhi, ylo, yhi;       // photon rectangle (image bounds +- 0.5)
+    uint64_t seed, sensor_seed, offset;
+    int ncdf;
+};
+
+__global__ void __launch_bounds__(256)
+k_flat_step(const __grid_constant__ DevSensor s, const __grid_constant__ FlatParams fp,
+            const int64_t* __restrict__ tile_cum, const double* __restrict__ cdf, const double* __restrict__ cdf_wave,
+            unsigned long long* __restrict__ sstats, double* __restrict__ added, SlowRec* __restrict__ slow,
+            unsigned long long* __restrict__ nslow) {
+    const int t = blockIdx.x;
+    const int tx = t % fp.tiles_x, ty = t / fp.tiles_x;
+    // tile rectangle clipped to the photon rectangle
+    const double x0 = fmax(fp.xlo, fp.xlo + (double)tx * fp.tile), x1 = fmin(fp.xhi, fp.xlo + (double)(tx + 1) * fp.tile);
+    const double y0 = fmax(fp.ylo, fp.ylo + (double)ty * fp.tile), y1 = fmin(fp.yhi, fp.ylo + (double)(ty + 1) * fp.tile);
+    const int64_t first = tile_cum[t], last = tile_cum[t + 1];
+    unsigned nb9 = 0, ndrop = 0;
+    double my_added = 0.0;
+    // whole warps iterate together (ballots in slow_append)
+    for (int64_t base = first + (threadIdx.x & ~31); base < last; base += blockDim.x) {
+        int64_t i = base + (threadIdx.x & 31);
+        bool to_slow = false;
+        SlowRec rec;
+        if (i < last) {
+            const uint64_t idx = fp.offset + (uint64_t)i;
+            uint32_t r[4];
+            philox4(fp.seed, idx, 5u, r);
+            double x = x0 + (x1 - x0) * u01(r[0], r[1]);
+            double y = y0 + (y1 - y0) * u01(r[2], r[3]);
+            double g1, g2, unf, udep;
+            sensor_draws(fp.sensor_seed, idx, g1, g2, unf, udep);
+            double wl = 0.0;
+            const bool has_wl = fp.ncdf >= 2;
+            if (has_wl) {
+                uint32_t q[4];
+                philox4(fp.seed, idx, 6u, q);
+                double u = u01(q[0], q[1]);
+                int lo = 0, hi = fp.ncdf - 1;
+                while (hi - lo > 1) {
+                    int mid = (lo + hi) >> 1;
+                    if (__ldg(cdf + mid) <= u) lo = mid; else hi = mid;
+                }
+                double c0 = __ldg(cdf + lo), c1 = __ldg(cdf + hi);
+                double f = (c1 > c0) ? (u - c0) / (c1 - c0) : 0.0;
+                wl = __ldg(cdf_wave + lo) + f * (__ldg(cdf_wave + hi) - __ldg(cdf_wave + lo));
+            }
+            double add1 = 0.0;
+            unsigned b9 = 0, dr = 0;
+            to_slow = sensor_fast_path(s, x, y, false, 0.0, 0.0, has_wl, wl, 1.0, g1, g2, unf, udep, rec, add1, b9, dr);
+            my_added += add1;
+            nb9 += b9;
+            ndrop += dr;
+        }
+        slow_append(to_slow, rec, slow, nslow);
+    }
+    unsigned long long w3 = warp_sum(nb9), w4 = warp_sum(ndrop);
+    double wa = my_added;
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) wa += __shfl_xor_sync(0xffffffffu, wa, k);
+    if ((threadIdx.x & 31) == 0) {
+        if (w3) atomicAdd(&sstats[ST_B9], w3);
+        if (w4) atomicAdd(&sstats[ST_DROP], w4);
+        if (wa != 0.0) atomicAdd(added, wa);
+    }
+}
+
+// One iteration of the photon-shot flat on the sensor's bound image: tile_cum (DEVICE, int64,
+// tiles_x*tiles_y + 1 entries) holds the cumulative per-tile photon counts of this iteration.
+extern "C" int b2_flat_step(b2_ctx* ctx, b2_sensor* sensor, const int64_t* tile_cum, int64_t n_total, int32_t tile,
+                            const double* cdf, const double* cdf_wave, int32_t ncdf, uint64_t seed,
+                            uint64_t sensor_seed, uint64_t photon_offset, int32_t resume, int32_t update_after,
+                            B2AccumStats* astats) {
+    B2_REQUIRE(ctx && sensor && tile_cum, "b2_flat_step: null argument");
+    B2_REQUIRE(sensor->ctx == ctx && sensor->bound, "b2_flat_step: sensor not bound to an image of this context");
+    B2_REQUIRE(tile >= 8 && tile <= 256, "b2_flat_step: tile must be 8..256 pixels");
+    B2_REQUIRE(ncdf == 0 || (cdf && cdf_wave && ncdf >= 2), "b2_flat_step: bad wavelength CDF");
+    B2_REQUIRE(ncdf == 0 || sensor->d.nabs > 0, "b2_flat_step: the sensor has no absorption table");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevSensor& d = sensor->d;
+    uint64_t n_updates = 0;
+    // chunking at the nrecalc cadence is done by the caller (whole iterations between updates)
+    if (b2_sensor_begin_accumulate(sensor, 0, 0, resume, 0, n_total, &n_updates)) return 1;
+    FlatParams fp;
+    fp.tile = tile;
+    fp.tiles_x = (d.nx + tile - 1) / tile;
+    fp.tiles_y = (d.ny + tile - 1) / tile;
+    fp.xlo = d.xmin - 0.5;
+    fp.xhi = d.xmin + d.nx - 0.5;
+    fp.ylo = d.ymin - 0.5;
+    fp.yhi = d.ymin + d.ny - 0.5;
+    fp.seed = seed;
+    fp.sensor_seed = sensor_seed;
+    fp.offset = photon_offset;
+    fp.ncdf = ncdf;
+    if (n_total > 0) {
+        B2_TIMED("k_flat_step", st);
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (ctx->record_events) {
+            B2_CUDA(cudaEventCreate(&e0));
+            B2_CUDA(cudaEventCreate(&e1));
+            B2_CUDA(cudaEventRecord(e0, st));
+        }
+        k_flat_step<<<fp.tiles_x * fp.tiles_y, 256, 0, st>>>(d, fp, tile_cum, cdf, cdf_wave, sensor->dstats, sensor->dadded,
+                                                             (SlowRec*)sensor->slow.ptr, sensor->dnslow);
+        B2_CHECK_LAUNCH();
+        if (ctx->record_events) {
+            B2_CUDA(cudaEventRecord(e1, st));
+            ctx->events.emplace_back(e0, e1);
+        }
+        if (b2_sensor_run_slow(sensor, n_total)) return 1;
+    }
+    if (update_after) {
+        if (b2_sensor_update_now(sensor)) return 1;
+        n_updates++;
+    }
+    if (b2_sensor_end_accumulate(sensor)) return 1;
+    if (astats) {
+        unsigned long long hs[ST_N];
+        double addedv = 0.0;
+        B2_CUDA(cudaMemcpyAsync(hs, sensor->dstats, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaMemcpyAsync(&addedv, sensor->dadded, sizeof(double), cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaStreamSynchronize(st));
+        memset(astats, 0, sizeof(*astats));
+        astats->added_flux = addedv;
+        astats->n_polygon_tests = hs[ST_POLY];
+        astats->n_neighbor_search = hs[ST_NEIGH];
+        astats->n_not_found = hs[ST_NOTFOUND];
+        astats->n_boundary_1e9 = hs[ST_B9];
+        astats->n_dropped_bottom = hs[ST_DROP];
+        astats->n_updates = n_updates;
+    }
+    return 0;
+}

@@ -1048,6 +1048,13 @@ int b2_sensor_run_slow(b2_sensor* s, int64_t n) {
 
 int b2_sensor_end_accumulate(b2_sensor* s) { return launch_add_delta(s, 1.0, 0); }
 
+// Silicon::update right now (distortions from delta, image += delta, delta = 0)
+int b2_sensor_update_now(b2_sensor* s) {
+    if (sensor_update(s)) return 1;
+    s->accum_flux = 0.0;
+    return 0;
+}
+
 extern "C" int b2_plain_accumulate(b2_sensor* s, int64_t n, const double* x, const double* y, const double* flux,
                                    int where, double* added_flux) {
     B2_REQUIRE(s && s->bound, "b2_plain_accumulate: no image bound");

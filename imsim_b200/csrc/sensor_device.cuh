@@ -307,3 +307,4 @@ int b2_sensor_begin_accumulate(b2_sensor* s, int32_t ocx, int32_t ocy, int32_t r
                                uint64_t* n_updates);
 int b2_sensor_run_slow(b2_sensor* s, int64_t n);
 int b2_sensor_end_accumulate(b2_sensor* s);
+int b2_sensor_update_now(b2_sensor* s);

@@ -20,6 +20,9 @@ from typing import Callable, Optional
 
 import numpy as np
 
+import ctypes as C
+
+from . import _lib
 from .sensor import Image, SiliconSensor
 
 
@@ -38,10 +41,13 @@ def wavelength_cdf(wave_nm, weight):
 
 def build_flat(image: Image, counts_per_pixel: float, sensor: Optional[SiliconSensor], rng=None,
                max_counts_per_iter: float = 1000.0, nx: int = 8, ny: int = 2, buffer_size: int = 5,
-               sed_cdf=None, base_level: Optional[Callable] = None, logger=None):
+               sed_cdf=None, base_level: Optional[Callable] = None, logger=None, fused: bool = True):
     """Add a flat field of ``counts_per_pixel`` electrons to ``image`` in place
     (``LSST_FlatBuilder.addNoise``).  ``sed_cdf = wavelength_cdf(...)`` selects the
     photon-shot branch; otherwise the pixel-area branch.  ``rng``: numpy Generator / seed.
+    ``fused`` (photon branch): generate the photons tile by tile inside the deposit kernel
+    (``b2_flat_step``; boundary updates fall on iteration ends) instead of materialising photon
+    arrays and calling ``accumulate`` (``fused=False``: the reference's literal sequence).
     Returns the number of photons shot (0 in the area branch)."""
     gen = rng if isinstance(rng, np.random.Generator) else np.random.default_rng(rng)
     niter = int(np.ceil(counts_per_pixel / max_counts_per_iter))
@@ -78,6 +84,32 @@ def build_flat(image: Image, counts_per_pixel: float, sensor: Optional[SiliconSe
                     if not isinstance(area, float):
                         temp *= area.array / np.mean(area.array)
                     sec.array[:, :] += gen.poisson(temp).astype(sec.array.dtype)
+                elif fused:
+                    # tile-ordered generation fused with the deposit (b2_flat_step): per-tile Poisson counts
+                    if it == 0:
+                        tile = 32
+                        tnx, tny = -(-sec.array.shape[1] // tile), -(-sec.array.shape[0] // tile)
+                        wx = np.minimum(tile, sec.array.shape[1] - tile * np.arange(tnx))
+                        wy = np.minimum(tile, sec.array.shape[0] - tile * np.arange(tny))
+                        tile_area = np.outer(wy, wx).ravel().astype(np.float64)
+                        sensor._bind(sec)
+                        sensor._last_image = sec
+                        accum = 0.0
+                    cnt = gen.poisson(counts_per_iter * tile_area)
+                    cum = torch.as_tensor(np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64),
+                                          device="cuda:%d" % sensor.ctx.device)
+                    nphot = int(cnt.sum())
+                    accum += nphot
+                    update_after = int(sensor.nrecalc > 0 and accum >= sensor.nrecalc / sensor.strength)
+                    if update_after:
+                        accum = 0.0
+                    _lib.check(_lib.load().b2_flat_step(
+                        sensor.ctx.handle, sensor._h, C.c_void_p(cum.data_ptr()), nphot, tile,
+                        _lib.ptr(cdf), _lib.ptr(cdf_wave), int(cdf.shape[0]), int(gen.integers(1 << 62)),
+                        sensor._seed & 0xFFFFFFFFFFFFFFFF, tot_nphot, int(it > 0), update_after, None))
+                    if it == niter - 1:
+                        sensor.read_image(sec)
+                    tot_nphot += nphot
                 else:
                     nphot = int(gen.poisson(counts_per_iter * sec.array.size))
                     dp = DevicePhotons(nphot, device="cuda:%d" % sensor.ctx.device,

@@ -352,6 +352,15 @@ int b2_pool_step(b2_ctx* ctx, b2_sensor* sensor, int64_t n, double* x, double* y
                  double r_inner, double r_outer, uint64_t sampler_seed, uint64_t sensor_seed,
                  uint64_t photon_offset, int32_t resume, int32_t recalc, int32_t write_back,
                  B2OpticsStats* ostats, B2AccumStats* astats);
+/* One iteration of the photon-shot flat (imsim/flat.py:239-264) on the sensor's bound image, fused:
+   photons are generated tile by tile (tile x tile pixels) straight into the charge deposit.
+   tile_cum: DEVICE int64[tiles+1], cumulative per-tile photon counts of this iteration (Poisson counts drawn
+   by the caller: the same distribution as n_total uniform photons); wavelengths from the inverse CDF if
+   ncdf >= 2 (else conversion at 1 micron, like a PhotonArray without wavelengths).
+   resume as in accumulate(); update_after != 0 performs the boundary update (nrecalc reached) before return. */
+int b2_flat_step(b2_ctx* ctx, b2_sensor* sensor, const int64_t* tile_cum, int64_t n_total, int32_t tile,
+                 const double* cdf, const double* cdf_wave, int32_t ncdf, uint64_t seed, uint64_t sensor_seed,
+                 uint64_t photon_offset, int32_t resume, int32_t update_after, B2AccumStats* astats);
 /* debug/inspection: copy boundary state of pixel (ix,iy) in image coords:
    poly: (4*nv+4)*2 doubles in polygon order; bounds: inner[4], outer[4] (xmin,xmax,ymin,ymax) */
 int b2_sensor_get_pixel(b2_sensor* s, int32_t ix, int32_t iy, double* poly, double* bounds);

@@ -51,7 +51,8 @@ def test_treerings_flat_area_branch():
     assert cov10 > 0.5 * tot and cov01 > 0.5 * tot and cov11 > 0.5 * tot
 
 
-def test_photon_shot_flat_with_sed():
+@pytest.mark.parametrize("fused", [False, True])
+def test_photon_shot_flat_with_sed(fused):
     """tests/test_flats.py:167-216: with wavelengths, red light is lost out of the back of the sensor;
     the photon branch reproduces the BF sign."""
     cfg, dat = helpers.sensor_model("lsst_itl_50_8")
@@ -63,10 +64,28 @@ def test_photon_shot_flat_with_sed():
         wave = np.linspace(lo, hi, 50)
         cdf = wavelength_cdf(wave, np.ones_like(wave))
         img = Image(np.zeros((n, n), np.float32), 1, 1)
-        nphot = build_flat(img, 4000, sensor, rng=3, max_counts_per_iter=1000, nx=1, ny=1, sed_cdf=cdf)
+        nphot = build_flat(img, 4000, sensor, rng=3, max_counts_per_iter=1000, nx=1, ny=1, sed_cdf=cdf, fused=fused)
         results[band] = (img.array.astype(float), nphot)
         assert nphot == pytest.approx(4000 * (n + 10) ** 2, rel=0.01)
     r, y = results["r"][0], results["y"][0]
     np.testing.assert_allclose(r.mean(), 4000, rtol=0.02)
     assert y.mean() < 0.9 * r.mean()  # photons lost out the back in y band
     assert r.var() == pytest.approx(r.mean(), rel=0.15)
+
+
+def test_fused_flat_brighter_fatter_statistics():
+    """Photon-shot flat through the fused tile kernel, r band, 30 ke-/px on 128^2: Poisson mean,
+    sub-Poisson variance and positive neighbour covariances stronger along y (tests/test_flats.py:69-111)."""
+    cfg, dat = helpers.sensor_model("lsst_itl_50_8")
+    n = 128
+    sensor = SiliconSensor(config=cfg, vertex_data=dat, rng=21, nrecalc=flat_nrecalc(n + 10, n + 10, 1, 1),
+                           absorption_table=helpers.absorption())
+    wave = np.linspace(550.0, 690.0, 30)
+    img = Image(np.zeros((n, n), np.float32), 1, 1)
+    tot = 30_000
+    build_flat(img, tot, sensor, rng=5, max_counts_per_iter=2000, nx=1, ny=1, sed_cdf=wavelength_cdf(wave, np.ones(30)))
+    a = img.array.astype(float)
+    np.testing.assert_allclose(a.mean(), tot, rtol=0.01)
+    assert 0.8 * tot < a.var() < tot
+    cov10, cov01, cov11 = _cov(a)
+    assert cov10 > 2e-3 * tot and cov10 > cov01 > -2e-3 * tot
