@@ -104,7 +104,7 @@ bool b2_timing_enabled() {
     return on == 1;
 }
 
-void b2_timing_begin(const char* name, cudaStream_t st) {
+long b2_timing_begin(const char* name, cudaStream_t st) {
     TimedLaunch t;
     t.name = name;
     cudaEventCreate(&t.e0);
@@ -112,11 +112,12 @@ void b2_timing_begin(const char* name, cudaStream_t st) {
     cudaEventRecord(t.e0, st);
     std::lock_guard<std::mutex> lk(g_timed_mu);
     g_timed.push_back(t);
+    return (long)g_timed.size() - 1;
 }
 
-void b2_timing_end(cudaStream_t st) {
+void b2_timing_end(long slot, cudaStream_t st) {
     std::lock_guard<std::mutex> lk(g_timed_mu);
-    cudaEventRecord(g_timed.back().e1, st);
+    if (slot < (long)g_timed.size()) cudaEventRecord(g_timed[slot].e1, st);
 }
 
 // JSON {"kernel": [count, total_ms], ...} of everything timed since the last report; clears the log

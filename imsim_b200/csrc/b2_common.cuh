@@ -44,16 +44,16 @@ static inline int b2_fail(const char* fmt, const char* a = "", const char* b = "
 // Optional per-kernel device timing (B2_TIMING=1): cudaEvents around each launch on the launching
 // stream, resolved lazily by b2_timing_report().  Off by default: no events, no overhead.
 bool b2_timing_enabled();
-void b2_timing_begin(const char* name, cudaStream_t st);
-void b2_timing_end(cudaStream_t st);
-struct B2TimedScope {
+long b2_timing_begin(const char* name, cudaStream_t st);
+void b2_timing_end(long slot, cudaStream_t st);
+struct B2TimedScope {  // scopes may nest (a host entry point timing itself around timed launches)
     cudaStream_t st;
-    bool on;
-    B2TimedScope(const char* name, cudaStream_t s) : st(s), on(b2_timing_enabled()) {
-        if (on) b2_timing_begin(name, st);
+    long slot;
+    B2TimedScope(const char* name, cudaStream_t s) : st(s), slot(-1) {
+        if (b2_timing_enabled()) slot = b2_timing_begin(name, st);
     }
     ~B2TimedScope() {
-        if (on) b2_timing_end(st);
+        if (slot >= 0) b2_timing_end(slot, st);
     }
 };
 #define B2_TIMED(name, stream) B2TimedScope _b2_timed_scope(name, stream)

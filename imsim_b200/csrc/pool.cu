@@ -11,6 +11,8 @@
 #include "optics_device.cuh"
 #include "sensor_device.cuh"
 
+#include <algorithm>
+
 struct PoolParams {
     double t0, exptime, r_in, r_out;
     uint64_t sampler_seed, sensor_seed, offset;
@@ -169,6 +171,7 @@ extern "C" int b2_pool_step(b2_ctx* ctx, b2_sensor* sensor, int64_t n, double* x
 // charge deposit: no photon array exists, gathers and atomics stay in one tile's cache lines.
 struct FlatParams {
     int tiles_x, tiles_y, tile;      // tile grid over the bound image
+    int tile0;                       // first tile of this launch
     double xlo, xhi, ylo, yhi;       // photon rectangle (image bounds +- 0.5)
     uint64_t seed, sensor_seed, offset;
     int ncdf;
@@ -179,12 +182,16 @@ k_flat_step(const __grid_constant__ DevSensor s, const __grid_constant__ FlatPar
             const int64_t* __restrict__ tile_cum, const double* __restrict__ cdf, const double* __restrict__ cdf_wave,
             unsigned long long* __restrict__ sstats, double* __restrict__ added, SlowRec* __restrict__ slow,
             unsigned long long* __restrict__ nslow) {
-    const int t = blockIdx.x;
+    const int t = fp.tile0 + blockIdx.x;
     const int tx = t % fp.tiles_x, ty = t / fp.tiles_x;
     // tile rectangle clipped to the photon rectangle
     const double x0 = fmax(fp.xlo, fp.xlo + (double)tx * fp.tile), x1 = fmin(fp.xhi, fp.xlo + (double)(tx + 1) * fp.tile);
     const double y0 = fmax(fp.ylo, fp.ylo + (double)ty * fp.tile), y1 = fmin(fp.yhi, fp.ylo + (double)(ty + 1) * fp.tile);
-    const int64_t first = tile_cum[t], last = tile_cum[t + 1];
+    // blockIdx.y: slice of the tile's photons (keeps every SM busy when a pass holds few tiles)
+    const int64_t tfirst = tile_cum[t], tcount = tile_cum[t + 1] - tfirst;
+    const int64_t per = ((tcount + gridDim.y - 1) / gridDim.y + 31) & ~(int64_t)31;
+    const int64_t first = tfirst + per * blockIdx.y;
+    const int64_t last = (first + per < tfirst + tcount) ? first + per : tfirst + tcount;
     unsigned nb9 = 0, ndrop = 0;
     double my_added = 0.0;
     // whole warps iterate together (ballots in slow_append)
@@ -235,8 +242,12 @@ k_flat_step(const __grid_constant__ DevSensor s, const __grid_constant__ FlatPar
     }
 }
 
-// One iteration of the photon-shot flat on the sensor's bound image: tile_cum (DEVICE, int64,
-// tiles_x*tiles_y + 1 entries) holds the cumulative per-tile photon counts of this iteration.
+// One iteration of the photon-shot flat on the sensor's bound image: tile_cum (HOST, int64,
+// tiles_x*tiles_y + 1 entries, tile_cum[0] = 0) holds the cumulative per-tile photon counts of this
+// iteration.  The tiles are processed in passes of at most FLAT_PASS_PHOTONS photons so that the
+// compact list of slow-path photons stays bounded however large the section is.
+static const int64_t FLAT_PASS_PHOTONS = (int64_t)1 << 27;
+
 extern "C" int b2_flat_step(b2_ctx* ctx, b2_sensor* sensor, const int64_t* tile_cum, int64_t n_total, int32_t tile,
                             const double* cdf, const double* cdf_wave, int32_t ncdf, uint64_t seed,
                             uint64_t sensor_seed, uint64_t photon_offset, int32_t resume, int32_t update_after,
@@ -250,12 +261,25 @@ extern "C" int b2_flat_step(b2_ctx* ctx, b2_sensor* sensor, const int64_t* tile_
     cudaStream_t st = ctx->stream;
     DevSensor& d = sensor->d;
     uint64_t n_updates = 0;
-    // chunking at the nrecalc cadence is done by the caller (whole iterations between updates)
-    if (b2_sensor_begin_accumulate(sensor, 0, 0, resume, 0, n_total, &n_updates)) return 1;
     FlatParams fp;
     fp.tile = tile;
     fp.tiles_x = (d.nx + tile - 1) / tile;
     fp.tiles_y = (d.ny + tile - 1) / tile;
+    const int ntiles = fp.tiles_x * fp.tiles_y;
+    B2_REQUIRE(tile_cum[0] == 0 && tile_cum[ntiles] == n_total, "b2_flat_step: tile_cum does not sum to n_total");
+    // largest pass, for the slow-list reservation
+    int64_t max_pass = 0;
+    for (int a = 0; a < ntiles;) {
+        int b = a + 1;
+        while (b < ntiles && tile_cum[b + 1] - tile_cum[a] <= FLAT_PASS_PHOTONS) b++;
+        max_pass = std::max(max_pass, tile_cum[b] - tile_cum[a]);
+        a = b;
+    }
+    // chunking at the nrecalc cadence is done by the caller (whole iterations between updates)
+    if (b2_sensor_begin_accumulate(sensor, 0, 0, resume, 0, max_pass, &n_updates)) return 1;
+    if (b2_scratch_reserve(ctx, ctx->scratch, (size_t)(ntiles + 1) * sizeof(int64_t))) return 1;
+    int64_t* dcum = (int64_t*)ctx->scratch.ptr;
+    B2_CUDA(cudaMemcpyAsync(dcum, tile_cum, (size_t)(ntiles + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     fp.xlo = d.xmin - 0.5;
     fp.xhi = d.xmin + d.nx - 0.5;
     fp.ylo = d.ymin - 0.5;
@@ -264,22 +288,34 @@ extern "C" int b2_flat_step(b2_ctx* ctx, b2_sensor* sensor, const int64_t* tile_
     fp.sensor_seed = sensor_seed;
     fp.offset = photon_offset;
     fp.ncdf = ncdf;
-    if (n_total > 0) {
-        B2_TIMED("k_flat_step", st);
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
-        if (ctx->record_events) {
-            B2_CUDA(cudaEventCreate(&e0));
-            B2_CUDA(cudaEventCreate(&e1));
-            B2_CUDA(cudaEventRecord(e0, st));
+    for (int a = 0; a < ntiles && n_total > 0;) {
+        int b = a + 1;
+        while (b < ntiles && tile_cum[b + 1] - tile_cum[a] <= FLAT_PASS_PHOTONS) b++;
+        const int64_t n_pass = tile_cum[b] - tile_cum[a];
+        fp.tile0 = a;
+        if (n_pass > 0) {
+            if (a > 0) B2_CUDA(cudaMemsetAsync(sensor->dnslow, 0, sizeof(unsigned long long), st));
+            {
+                B2_TIMED("k_flat_step", st);
+                cudaEvent_t e0 = nullptr, e1 = nullptr;
+                if (ctx->record_events) {
+                    B2_CUDA(cudaEventCreate(&e0));
+                    B2_CUDA(cudaEventCreate(&e1));
+                    B2_CUDA(cudaEventRecord(e0, st));
+                }
+                int split = (sensor->sm_count * 16 + (b - a) - 1) / (b - a);
+                split = std::max(1, std::min(split, 64));
+                k_flat_step<<<dim3(b - a, split), 256, 0, st>>>(d, fp, dcum, cdf, cdf_wave, sensor->dstats, sensor->dadded,
+                                                   (SlowRec*)sensor->slow.ptr, sensor->dnslow);
+                B2_CHECK_LAUNCH();
+                if (ctx->record_events) {
+                    B2_CUDA(cudaEventRecord(e1, st));
+                    ctx->events.emplace_back(e0, e1);
+                }
+            }
+            if (b2_sensor_run_slow(sensor, n_pass)) return 1;
         }
-        k_flat_step<<<fp.tiles_x * fp.tiles_y, 256, 0, st>>>(d, fp, tile_cum, cdf, cdf_wave, sensor->dstats, sensor->dadded,
-                                                             (SlowRec*)sensor->slow.ptr, sensor->dnslow);
-        B2_CHECK_LAUNCH();
-        if (ctx->record_events) {
-            B2_CUDA(cudaEventRecord(e1, st));
-            ctx->events.emplace_back(e0, e1);
-        }
-        if (b2_sensor_run_slow(sensor, n_total)) return 1;
+        a = b;
     }
     if (update_after) {
         if (b2_sensor_update_now(sensor)) return 1;

@@ -509,40 +509,86 @@ k_pixel_areas(const __grid_constant__ DevSensor s, double* __restrict__ areas) {
     areas[(size_t)y * s.nx + x] = fabs(area) / 2.0;
 }
 
-// inclusive prefix sum of flux, single block (chunk boundaries for nrecalc > 0); the
-// running total is carried in double like the reference's host loop
-__global__ void k_find_chunks(const double* __restrict__ flux, int64_t n, double accum0, double nrecalc,
-                              int64_t* __restrict__ bounds, int max_bounds, int* __restrict__ nb, double* accum_out) {
-    // serial scan by one thread per launch is too slow for large n; use a block-wide
-    // sequential-by-tile scan: 1024 threads, each tile of 1024 photons scanned in shared memory
-    __shared__ double tile[1024];
+// Chunk boundaries for nrecalc > 0 (Silicon::accumulate updates the pixel boundaries each time the flux
+// added since the last update reaches nrecalc).  Two kernels: k_segment_sums reduces the flux array in
+// segments of CHUNK_SEG photons; k_find_chunks (one block) walks the segment sums and scans photon by
+// photon, in photon order like the reference's loop, only the segments in which a boundary falls.  For
+// unit / integer fluxes (stars, flats) the result is exactly the sequential one; for general fluxes the
+// segment sums round differently from a photon-by-photon running total, which can move a boundary by
+// one photon when the total lands within an ulp of nrecalc.
+#define CHUNK_SEG 4096
+
+__global__ void __launch_bounds__(256)
+k_segment_sums(const double* __restrict__ flux, int64_t n, double* __restrict__ sums) {
+    const int64_t base = (int64_t)blockIdx.x * CHUNK_SEG;
+    double a = 0.0;
+#pragma unroll 4
+    for (int k = threadIdx.x; k < CHUNK_SEG; k += 256) {
+        int64_t i = base + k;
+        if (i < n) a += flux[i];
+    }
+    __shared__ double part[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += part[k];
+        sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_find_chunks(const double* __restrict__ flux, int64_t n, const double* __restrict__ sums, int64_t nseg, double accum0,
+              double nrecalc, int64_t* __restrict__ bounds, int max_bounds, int* __restrict__ nb, double* accum_out) {
+    __shared__ double ssum[1024];
+    __shared__ double tile[CHUNK_SEG];
     __shared__ double carry;
-    __shared__ int count;
+    __shared__ int count, need, kstart;
     if (threadIdx.x == 0) {
         carry = accum0;
         count = 0;
     }
-    __syncthreads();
-    for (int64_t base = 0; base < n; base += 1024) {
-        int64_t i = base + threadIdx.x;
-        tile[threadIdx.x] = (i < n) ? flux[i] : 0.0;
+    for (int64_t seg0 = 0; seg0 < nseg; seg0 += 1024) {
+        const int lim = (int)((nseg - seg0 < 1024) ? (nseg - seg0) : 1024);
         __syncthreads();
-        if (threadIdx.x == 0) {
-            // exact sequential semantics (order of additions = photon order)
-            double acc = carry;
-            int64_t lim = (n - base < 1024) ? (n - base) : 1024;
-            for (int k = 0; k < lim; ++k) {
-                acc += tile[k];
-                if (acc >= nrecalc) {
-                    if (count < max_bounds) bounds[count] = base + k + 1;
-                    count++;
-                    acc = 0.0;
-                }
+        ssum[threadIdx.x] = (threadIdx.x < lim) ? sums[seg0 + threadIdx.x] : 0.0;
+        if (threadIdx.x == 0) kstart = 0;
+        __syncthreads();
+        for (;;) {
+            if (threadIdx.x == 0) {
+                int k = kstart;
+                double acc = carry;
+                while (k < lim && acc + ssum[k] < nrecalc) acc += ssum[k++];
+                carry = acc;
+                need = (k < lim) ? k : -1;
+                kstart = k + 1;
             }
-            carry = acc;
+            __syncthreads();
+            const int seg = need;
+            if (seg < 0) break;
+            const int64_t base = (seg0 + seg) * CHUNK_SEG;
+            for (int k = threadIdx.x; k < CHUNK_SEG; k += 1024) tile[k] = (base + k < n) ? flux[base + k] : 0.0;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                // exact sequential semantics inside the segment (order of additions = photon order)
+                double acc = carry;
+                const int m = (int)((n - base < CHUNK_SEG) ? (n - base) : CHUNK_SEG);
+                for (int k = 0; k < m; ++k) {
+                    acc += tile[k];
+                    if (acc >= nrecalc) {
+                        if (count < max_bounds) bounds[count] = base + k + 1;
+                        count++;
+                        acc = 0.0;
+                    }
+                }
+                carry = acc;
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
         *nb = count;
         *accum_out = carry;
@@ -930,12 +976,19 @@ extern "C" int b2_sensor_accumulate(b2_sensor* s, int64_t n, const double* x, co
     double nrecalc = s->cfg.nrecalc;
     if (nrecalc > 0 && n > 0) {
         const int max_bounds = 1 << 20;
-        if (b2_scratch_reserve(ctx, s->cum, (size_t)max_bounds * 8 + 64)) return 1;
+        const int64_t nseg = (n + CHUNK_SEG - 1) / CHUNK_SEG;
+        if (b2_scratch_reserve(ctx, s->cum, (size_t)max_bounds * 8 + 64 + (size_t)nseg * 8)) return 1;
         int64_t* dbounds = (int64_t*)s->cum.ptr;
         int* dnb = (int*)((char*)s->cum.ptr + (size_t)max_bounds * 8);
         double* dacc = (double*)((char*)s->cum.ptr + (size_t)max_bounds * 8 + 8);
-        k_find_chunks<<<1, 1024, 0, st>>>(df, n, s->accum_flux, nrecalc, dbounds, max_bounds, dnb, dacc);
-        B2_CHECK_LAUNCH();
+        double* dsums = (double*)((char*)s->cum.ptr + (size_t)max_bounds * 8 + 64);
+        {
+            B2_TIMED("k_find_chunks", st);
+            k_segment_sums<<<(unsigned)nseg, 256, 0, st>>>(df, n, dsums);
+            B2_CHECK_LAUNCH();
+            k_find_chunks<<<1, 1024, 0, st>>>(df, n, dsums, nseg, s->accum_flux, nrecalc, dbounds, max_bounds, dnb, dacc);
+            B2_CHECK_LAUNCH();
+        }
         int nb = 0;
         double acc = 0.0;
         B2_CUDA(cudaMemcpyAsync(&nb, dnb, sizeof(int), cudaMemcpyDeviceToHost, st));

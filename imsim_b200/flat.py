@@ -39,6 +39,9 @@ def wavelength_cdf(wave_nm, weight):
     return np.ascontiguousarray(c / c[-1]), wave_nm
 
 
+MAX_UNFUSED_CHUNK = 1 << 27  # photons per accumulate call of the unfused photon-shot branch (4 GiB of SoA)
+
+
 def build_flat(image: Image, counts_per_pixel: float, sensor: Optional[SiliconSensor], rng=None,
                max_counts_per_iter: float = 1000.0, nx: int = 8, ny: int = 2, buffer_size: int = 5,
                sed_cdf=None, base_level: Optional[Callable] = None, logger=None, fused: bool = True):
@@ -96,28 +99,36 @@ def build_flat(image: Image, counts_per_pixel: float, sensor: Optional[SiliconSe
                         sensor._last_image = sec
                         accum = 0.0
                     cnt = gen.poisson(counts_per_iter * tile_area)
-                    cum = torch.as_tensor(np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64),
-                                          device="cuda:%d" % sensor.ctx.device)
+                    cum = np.ascontiguousarray(np.concatenate([[0], np.cumsum(cnt)]), dtype=np.int64)
                     nphot = int(cnt.sum())
                     accum += nphot
                     update_after = int(sensor.nrecalc > 0 and accum >= sensor.nrecalc / sensor.strength)
                     if update_after:
                         accum = 0.0
                     _lib.check(_lib.load().b2_flat_step(
-                        sensor.ctx.handle, sensor._h, C.c_void_p(cum.data_ptr()), nphot, tile,
+                        sensor.ctx.handle, sensor._h, C.c_void_p(cum.ctypes.data), nphot, tile,
                         _lib.ptr(cdf), _lib.ptr(cdf_wave), int(cdf.shape[0]), int(gen.integers(1 << 62)),
                         sensor._seed & 0xFFFFFFFFFFFFFFFF, tot_nphot, int(it > 0), update_after, None))
                     if it == niter - 1:
                         sensor.read_image(sec)
                     tot_nphot += nphot
                 else:
+                    # the reference's literal sequence, in device-memory-bounded chunks of photons
                     nphot = int(gen.poisson(counts_per_iter * sec.array.size))
-                    dp = DevicePhotons(nphot, device="cuda:%d" % sensor.ctx.device,
-                                       fields=("x", "y", "flux", "wavelength"))
-                    sensor.ctx.flat_photons(dp.x, dp.y, dp.flux, dp.wavelength,
-                                            (bx0 - 0.5, bx1 + 0.5, by0 - 0.5, by1 + 0.5), cdf, cdf_wave,
-                                            seed=int(gen.integers(1 << 62)), photon_offset=tot_nphot)
-                    sensor.accumulate(dp, sec, resume=(it > 0), sync_image=(it == niter - 1), want_stats=False)
+                    done = 0
+                    while done < nphot or (nphot == 0 and done == 0):
+                        m = min(nphot - done, MAX_UNFUSED_CHUNK)
+                        dp = DevicePhotons(m, device="cuda:%d" % sensor.ctx.device,
+                                           fields=("x", "y", "flux", "wavelength"))
+                        sensor.ctx.flat_photons(dp.x, dp.y, dp.flux, dp.wavelength,
+                                                (bx0 - 0.5, bx1 + 0.5, by0 - 0.5, by1 + 0.5), cdf, cdf_wave,
+                                                seed=int(gen.integers(1 << 62)), photon_offset=tot_nphot + done)
+                        last = done + m >= nphot
+                        sensor.accumulate(dp, sec, resume=(it > 0 or done > 0),
+                                          sync_image=(it == niter - 1 and last), want_stats=False)
+                        done += m
+                        if nphot == 0:
+                            break
                     tot_nphot += nphot
             # copy just the part that is officially part of this section (flat.py:266-267)
             image.array[ymin - y0:ymax - y0 + 1, xmin - x0:xmax - x0 + 1] += \

@@ -354,8 +354,9 @@ int b2_pool_step(b2_ctx* ctx, b2_sensor* sensor, int64_t n, double* x, double* y
                  B2OpticsStats* ostats, B2AccumStats* astats);
 /* One iteration of the photon-shot flat (imsim/flat.py:239-264) on the sensor's bound image, fused:
    photons are generated tile by tile (tile x tile pixels) straight into the charge deposit.
-   tile_cum: DEVICE int64[tiles+1], cumulative per-tile photon counts of this iteration (Poisson counts drawn
-   by the caller: the same distribution as n_total uniform photons); wavelengths from the inverse CDF if
+   tile_cum: HOST int64[tiles+1], tile_cum[0] = 0, cumulative per-tile photon counts of this iteration (Poisson
+   counts drawn by the caller: the same distribution as n_total uniform photons; tiles are processed in passes
+   of <= 2^27 photons so scratch stays bounded); cdf / cdf_wave: DEVICE; wavelengths from the inverse CDF if
    ncdf >= 2 (else conversion at 1 micron, like a PhotonArray without wavelengths).
    resume as in accumulate(); update_after != 0 performs the boundary update (nrecalc reached) before return. */
 int b2_flat_step(b2_ctx* ctx, b2_sensor* sensor, const int64_t* tile_cum, int64_t n_total, int32_t tile,
