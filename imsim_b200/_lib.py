@@ -66,6 +66,7 @@ _SIGNATURES = {
     "b2_last_error": (C.c_char_p, []),
     "b2_abi_version": (C.c_int, []),
     "b2_launch_count": (C.c_uint64, []),
+    "b2_telescope_program": (C.c_int, [C.c_void_p]),
     "b2_sizeof": (C.c_int64, [C.c_int32]),
     "b2_ctx_create": (C.c_int, [C.c_int, vp, C.POINTER(vp)]),
     "b2_ctx_destroy": (C.c_int, [vp]),

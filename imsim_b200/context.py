@@ -50,6 +50,11 @@ class OpticsContext:
             _lib.check(self._lib.b2_telescope_set_extra(self._h, i, kind, arr.ctypes.data, arr.size))
         self.telescope = tel
 
+    @property
+    def program(self) -> int:
+        """Surface program of the uploaded telescope (0 interpreter, 1 Rubin layout; -1 none)."""
+        return int(self._lib.b2_telescope_program(self._h))
+
     def set_wcs(self, img_wcs, icrf_to_field):
         a = img_wcs.to_pod() if isinstance(img_wcs, TanSipWCS) else img_wcs
         b = icrf_to_field.to_pod() if isinstance(icrf_to_field, TanSipWCS) else icrf_to_field

@@ -119,6 +119,7 @@ struct b2_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool have_tel = false, have_wcs = false, have_det = false;
+    int program = 0;         // surface program matching the uploaded telescope (optics_device.cuh), 0 = generic
     DevOptics opt;           // host copy, passed to kernels by value (__grid_constant__)
     std::vector<void*> extras;  // device allocations owned by the context
     Scratch scratch;         // staging for B2_HOST calls

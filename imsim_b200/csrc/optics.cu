@@ -36,13 +36,14 @@ k_v_to_xy(const __grid_constant__ DevOptics o, int64_t n, const double* __restri
     y[i] = b;
 }
 
+template <int PROG>
 __global__ void __launch_bounds__(256)
 k_trace_rays(const __grid_constant__ DevOptics o, int64_t n, double* x, double* y, double* z, double* vx, double* vy,
              double* vz, double* t, const double* __restrict__ wl, uint8_t* vig, uint8_t* fail) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Ray r{x[i], y[i], z[i], vx[i], vy[i], vz[i], t[i], vig[i] != 0, fail[i] != 0};
-    trace_ray(o, r, wl[i]);
+    trace_ray<PROG>(o, r, wl[i]);
     x[i] = r.x; y[i] = r.y; z[i] = r.z;
     vx[i] = r.vx; vy[i] = r.vy; vz[i] = r.vz;
     t[i] = r.t;
@@ -51,6 +52,7 @@ k_trace_rays(const __grid_constant__ DevOptics o, int64_t n, double* x, double* 
 }
 
 // RubinOptics / RubinDiffractionOptics.applyTo fused with FocusDepth + Refraction
+template <int PROG>
 __device__ __forceinline__ void
 rubin_optics_body(const DevOptics& o, const B2OpticsOptions& opt, int64_t n,
                double* __restrict__ x, double* __restrict__ y, double* __restrict__ dxdz, double* __restrict__ dydz,
@@ -63,7 +65,7 @@ rubin_optics_body(const DevOptics& o, const B2OpticsOptions& opt, int64_t n,
     if (active) {
         double g = 0.0;
         if (o.dif.enabled) g = gauss ? gauss[i] : philox_normal(opt.seed, opt.photon_offset + (uint64_t)i, 0u);
-        OpticsOut r = optics_photon(o, opt, x[i], y[i], wl_nm[i], pu[i], pv[i], time[i], flux[i], g);
+        OpticsOut r = optics_photon<PROG>(o, opt, x[i], y[i], wl_nm[i], pu[i], pv[i], time[i], flux[i], g);
         vig = r.vig;
         fail = r.fail;
         offz = r.offz;
@@ -92,13 +94,14 @@ rubin_optics_body(const DevOptics& o, const B2OpticsOptions& opt, int64_t n,
         double *__restrict__ flux, const double *__restrict__ wl_nm, const double *__restrict__ pu,               \
         const double *__restrict__ pv, const double *__restrict__ time, const double *__restrict__ gauss,         \
         double *__restrict__ time_out, unsigned long long *__restrict__ stats
-#define B2_OPTICS_CALL rubin_optics_body(o, opt, n, x, y, dxdz, dydz, flux, wl_nm, pu, pv, time, gauss, time_out, stats)
 // The trace is latency bound on dependent FP64 chains (ncu: stall "wait" dominates at 4 warps per
-// scheduler), so resident warps matter more than a few spilled registers: three builds of the same
-// body at 2 / 3 / 4 blocks per SM; B2_OPTICS_OCC picks one (default set from measurements).
-__global__ void __launch_bounds__(256, 2) k_rubin_optics(B2_OPTICS_ARGS) { B2_OPTICS_CALL; }
-__global__ void __launch_bounds__(256, 3) k_rubin_optics_occ3(B2_OPTICS_ARGS) { B2_OPTICS_CALL; }
-__global__ void __launch_bounds__(256, 4) k_rubin_optics_occ4(B2_OPTICS_ARGS) { B2_OPTICS_CALL; }
+// scheduler), so resident warps matter more than a few spilled registers: builds of the same body at
+// 2 / 3 / 4 blocks per SM (B2_OPTICS_OCC picks one; default set from measurements), each as the generic
+// interpreter and as the LSST surface program.
+template <int MINB, int PROG>
+__global__ void __launch_bounds__(256, MINB) k_rubin_optics(B2_OPTICS_ARGS) {
+    rubin_optics_body<PROG>(o, opt, n, x, y, dxdz, dydz, flux, wl_nm, pu, pv, time, gauss, time_out, stats);
+}
 
 // RubinDiffraction.applyTo
 __global__ void __launch_bounds__(256)
@@ -287,6 +290,8 @@ extern "C" int b2_diffraction_config(b2_ctx* ctx, const B2Diffraction* cfg) {
     return 0;
 }
 
+static void select_program(b2_ctx* ctx);
+
 extern "C" int b2_telescope_upload(b2_ctx* ctx, const B2Telescope* tel) {
     B2_REQUIRE(ctx && tel, "b2_telescope_upload: null argument");
     B2_REQUIRE(tel->n_surfaces >= 1 && tel->n_surfaces <= B2_DEV_MAX_SURF, "b2_telescope_upload: 1..16 surfaces supported");
@@ -346,6 +351,7 @@ extern "C" int b2_telescope_upload(b2_ctx* ctx, const B2Telescope* tel) {
         if (s.extra_kind != B2_EXTRA_NONE) d.pad = s.extra_kind;  // remembered until the table arrives
     }
     ctx->have_tel = true;
+    select_program(ctx);
     return 0;
 }
 
@@ -364,6 +370,7 @@ extern "C" int b2_telescope_set_extra(b2_ctx* ctx, int is, int kind, const doubl
     B2_CUDA(cudaStreamSynchronize(ctx->stream));
     d.extra = (const double*)p;
     d.extra_kind = kind;
+    select_program(ctx);
     return 0;
 }
 
@@ -444,27 +451,53 @@ extern "C" int b2_trace_rays(b2_ctx* ctx, int64_t n, double* x, double* y, doubl
         for (int k = 0; k < 8; ++k) H2D(d[k], h[k], n);
         B2_CUDA(cudaMemcpyAsync(dv, vig, n, cudaMemcpyHostToDevice, ctx->stream));
         B2_CUDA(cudaMemcpyAsync(df, fail, n, cudaMemcpyHostToDevice, ctx->stream));
-        k_trace_rays<<<nblocks(n), 256, 0, ctx->stream>>>(ctx->opt, n, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], dv, df);
+        if (ctx->program == B2_PROG_LSST)
+            k_trace_rays<B2_PROG_LSST><<<nblocks(n), 256, 0, ctx->stream>>>(ctx->opt, n, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], dv, df);
+        else
+            k_trace_rays<B2_PROG_GENERIC><<<nblocks(n), 256, 0, ctx->stream>>>(ctx->opt, n, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], dv, df);
         B2_CHECK_LAUNCH();
         for (int k = 0; k < 7; ++k) D2H(h[k], d[k], n);
         B2_CUDA(cudaMemcpyAsync(vig, dv, n, cudaMemcpyDeviceToHost, ctx->stream));
         B2_CUDA(cudaMemcpyAsync(fail, df, n, cudaMemcpyDeviceToHost, ctx->stream));
         B2_CUDA(cudaStreamSynchronize(ctx->stream));
     } else {
-        k_trace_rays<<<nblocks(n), 256, 0, ctx->stream>>>(ctx->opt, n, x, y, z, vx, vy, vz, t, wl, vig, fail);
+        if (ctx->program == B2_PROG_LSST)
+            k_trace_rays<B2_PROG_LSST><<<nblocks(n), 256, 0, ctx->stream>>>(ctx->opt, n, x, y, z, vx, vy, vz, t, wl, vig, fail);
+        else
+            k_trace_rays<B2_PROG_GENERIC><<<nblocks(n), 256, 0, ctx->stream>>>(ctx->opt, n, x, y, z, vx, vy, vz, t, wl, vig, fail);
         B2_CHECK_LAUNCH();
     }
     return 0;
 }
 
-static int optics_occ() {
+extern "C" int b2_telescope_program(b2_ctx* ctx) { return (ctx && ctx->have_tel) ? ctx->program : -1; }
+
+static int optics_occ(int program) {
     static int occ = -1;
     if (occ < 0) {
         const char* e = getenv("B2_OPTICS_OCC");
-        occ = e ? atoi(e) : 3;
-        if (occ < 2 || occ > 4) occ = 3;
+        occ = e ? atoi(e) : 0;
+        if (occ < 2 || occ > 4) occ = 0;
     }
-    return occ;
+    if (occ) return occ;
+    return program == B2_PROG_LSST ? 4 : 3;  // k_rubin_optics per 2^24 photons: program 2.50 / 2.37 ms at 3 / 4; interpreter 2.95 at 3
+}
+
+// Surface program of the uploaded telescope (optics_device.cuh); B2_PROGRAM=0 forces the interpreter.
+static void select_program(b2_ctx* ctx) {
+    const DevOptics& o = ctx->opt;
+    ctx->program = B2_PROG_GENERIC;
+    const char* e = getenv("B2_PROGRAM");
+    if (e && e[0] == '0') return;
+    if (o.n_surf != B2_PROG_LSST_LEN || o.n_media != 2) return;
+    for (int i = 0; i < o.n_surf; ++i) {
+        const DevSurf& d = o.surf[i];
+        const SurfSpec sp = lsst_spec(i);
+        if ((d.kind == B2_SURF_ASPHERE) != sp.asphere || d.interact != sp.interact) return;
+        if (sp.interact == B2_INT_REFRACT && (d.med_in != sp.med_in || d.med_out != sp.med_out)) return;
+        if (d.extra_kind != B2_EXTRA_NONE || d.pad != 0 || !d.simple_clear || d.n_coef > 4) return;
+    }
+    ctx->program = B2_PROG_LSST;
 }
 
 static void launch_rubin_optics(b2_ctx* ctx, const B2OpticsOptions& opt, int64_t n, double* x, double* y, double* dxdz,
@@ -477,16 +510,20 @@ static void launch_rubin_optics(b2_ctx* ctx, const B2OpticsOptions& opt, int64_t
         cudaEventCreate(&e1);
         cudaEventRecord(e0, ctx->stream);
     }
-    switch (optics_occ()) {
-        case 2:
-            k_rubin_optics<<<nblocks(n), 256, 0, ctx->stream>>>(ctx->opt, opt, n, x, y, dxdz, dydz, flux, wl, pu, pv, time, gauss, time_out, stats);
-            break;
-        case 4:
-            k_rubin_optics_occ4<<<nblocks(n), 256, 0, ctx->stream>>>(ctx->opt, opt, n, x, y, dxdz, dydz, flux, wl, pu, pv, time, gauss, time_out, stats);
-            break;
-        default:
-            k_rubin_optics_occ3<<<nblocks(n), 256, 0, ctx->stream>>>(ctx->opt, opt, n, x, y, dxdz, dydz, flux, wl, pu, pv, time, gauss, time_out, stats);
+#define B2_LAUNCH_OPTICS(MINB, PROG)                                                                              \
+    k_rubin_optics<MINB, PROG><<<nblocks(n), 256, 0, ctx->stream>>>(ctx->opt, opt, n, x, y, dxdz, dydz, flux, wl, pu, \
+                                                                    pv, time, gauss, time_out, stats)
+    const int occ = optics_occ(ctx->program);
+    if (ctx->program == B2_PROG_LSST) {
+        if (occ == 2) B2_LAUNCH_OPTICS(2, B2_PROG_LSST);
+        else if (occ == 4) B2_LAUNCH_OPTICS(4, B2_PROG_LSST);
+        else B2_LAUNCH_OPTICS(3, B2_PROG_LSST);
+    } else {
+        if (occ == 2) B2_LAUNCH_OPTICS(2, B2_PROG_GENERIC);
+        else if (occ == 4) B2_LAUNCH_OPTICS(4, B2_PROG_GENERIC);
+        else B2_LAUNCH_OPTICS(3, B2_PROG_GENERIC);
     }
+#undef B2_LAUNCH_OPTICS
     if (ctx->record_events) {
         cudaEventRecord(e1, ctx->stream);
         ctx->events.emplace_back(e0, e1);

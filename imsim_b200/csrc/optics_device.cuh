@@ -345,13 +345,14 @@ __device__ __forceinline__ void bicubic_eval(const double* blk, double x, double
 
 // even-asphere polynomial P(r^2) = sum coef[k] r^(4+2k) with dP/d(r^2) and d2P/d(r^2)^2, plus the
 // summed extra term E(x, y) with its gradient: everything on the surface that is not the base conic
-__device__ __forceinline__ void departure(const DevSurf& s, double x, double y, double r2, double& P, double& dP,
-                                          double& ddP, double& E, double& Ex, double& Ey) {
+__device__ __forceinline__ void departure(const DevSurf& s, const int kind, const int extra_kind, const bool small_poly,
+                                          double x, double y, double r2, double& P, double& dP, double& ddP, double& E,
+                                          double& Ex, double& Ey) {
     P = dP = ddP = 0.0;
-    if (s.kind == B2_SURF_ASPHERE) {
+    if (kind == B2_SURF_ASPHERE) {
         // P = r2^2 h(r2); Horner for h, h', h'' from the highest coefficient
         double h = 0.0, dh = 0.0, ddh = 0.0;
-        if (s.n_coef <= 4) {  // the usual case, fully unrolled (unused coefficients are zero)
+        if (small_poly) {  // n_coef <= 4: the usual case, fully unrolled (unused coefficients are zero)
 #pragma unroll
             for (int k = 3; k >= 0; --k) {
                 ddh = ddh * r2 + 2.0 * dh;
@@ -359,6 +360,7 @@ __device__ __forceinline__ void departure(const DevSurf& s, double x, double y, 
                 h = h * r2 + s.coef[k];
             }
         } else {
+#pragma unroll 1
             for (int k = s.n_coef - 1; k >= 0; --k) {
                 ddh = ddh * r2 + 2.0 * dh;
                 dh = dh * r2 + h;
@@ -370,8 +372,8 @@ __device__ __forceinline__ void departure(const DevSurf& s, double x, double y, 
         ddP = 2.0 * h + r2 * (4.0 * dh + r2 * ddh);
     }
     E = Ex = Ey = 0.0;
-    if (s.extra_kind == B2_EXTRA_POLY2D) poly2d_eval(s, x, y, E, Ex, Ey);
-    else if (s.extra_kind == B2_EXTRA_BICUBIC) bicubic_eval(s.extra, x, y, E, Ex, Ey);
+    if (extra_kind == B2_EXTRA_POLY2D) poly2d_eval(s, x, y, E, Ex, Ey);
+    else if (extra_kind == B2_EXTRA_BICUBIC) bicubic_eval(s.extra, x, y, E, Ex, Ey);
 }
 
 __device__ __forceinline__ bool obscured(const DevObsc& o, double x, double y) {
@@ -411,148 +413,220 @@ struct Ray {
     bool vignetted, failed;
 };
 
+// One interface of batoid's CompoundOptic.trace: transform into the surface frame, intersect, interact
+// (reflect / refract / detect), clear-aperture test.  The shape flags arrive as arguments: run-time
+// fields of the DevSurf in the generic loop, compile-time constants in a surface program (below), where
+// the branches fold away and every coefficient is a constant-bank operand at a fixed offset.
+struct MediaN {
+    double n[4], inv[4];
+};
+
+__device__ __forceinline__ double media_pick(const double v[4], int m) {
+    return m == 0 ? v[0] : (m == 1 ? v[1] : (m == 2 ? v[2] : v[3]));
+}
+
+__device__ __forceinline__ void surface_step(const DevSurf& s, const int kind, const int interact, const int med_in,
+                                             const int med_out, const int extra_kind, const bool simple_clear,
+                                             const bool small_poly, const MediaN& mn, Ray& r) {
+    // coordinate transformation: r' = drot^T (r - dr)
+    double dx = r.x - s.dr[0], dy = r.y - s.dr[1], dz = r.z - s.dr[2];
+    double x, y, z, vx, vy, vz;
+    if (s.rot_identity) {
+        x = dx; y = dy; z = dz;
+        vx = r.vx; vy = r.vy; vz = r.vz;
+    } else {
+        const double* M = s.drot;
+        x = dx * M[0] + dy * M[3] + dz * M[6];
+        y = dx * M[1] + dy * M[4] + dz * M[7];
+        z = dx * M[2] + dy * M[5] + dz * M[8];
+        vx = r.vx * M[0] + r.vy * M[3] + r.vz * M[6];
+        vy = r.vx * M[1] + r.vy * M[4] + r.vz * M[7];
+        vz = r.vx * M[2] + r.vy * M[5] + r.vz * M[8];
+    }
+    // intersection: go to the vertex plane first, then the near-vertex (small) root of the
+    // base conic x^2 + y^2 - 2 R z + k1 z^2 = 0
+    bool ok = (vz != 0.0);
+    double dt = -z * b2rcp(vz);
+    double px = x + vx * dt, py = y + vy * dt, pz = 0.0;
+    const bool curved = (kind != B2_SURF_PLANE);
+    if (curved) {
+        double A = vx * vx + vy * vy + s.k1 * vz * vz;
+        double B = 2.0 * (px * vx + py * vy - s.R * vz);
+        double C = px * px + py * py;
+        double disc = B * B - 4.0 * A * C;
+        ok = ok && (disc >= 0.0);
+        double q = -0.5 * (B + copysign(b2sqrt(disc), B));
+        double t1 = C * b2rcp(q);
+        dt += t1;
+        px += vx * t1;
+        py += vy * t1;
+        pz = vz * t1;
+    }
+    // zc: height of the base conic under the hit point (= pz unless the surface departs from it)
+    double zc = pz, gP = 0.0, Ex = 0.0, Ey = 0.0;
+    if (kind == B2_SURF_ASPHERE || extra_kind != B2_EXTRA_NONE) {
+        // Newton on the implicit form G(t) = r^2 - 2 R zc + k1 zc^2 with zc = z - P(r^2) - E(x, y):
+        // polynomial in the ray parameter, no square root; quadratic convergence from the conic hit
+        bool conv = false;
+        const bool pure = (extra_kind == B2_EXTRA_NONE);
+#pragma unroll 1
+        for (int it = 0; it < 8; ++it) {
+            double r2 = px * px + py * py;
+            double P, dP, ddP, E;
+            departure(s, kind, extra_kind, small_poly, px, py, r2, P, dP, ddP, E, Ex, Ey);
+            zc = pz - P - E;
+            double rv = px * vx + py * vy;
+            double dzc = vz - 2.0 * dP * rv - (Ex * vx + Ey * vy);
+            double G, dG;
+            if (curved) {
+                G = r2 - 2.0 * s.R * zc + s.k1 * zc * zc;
+                dG = 2.0 * rv - 2.0 * (s.R - s.k1 * zc) * dzc;
+            } else {
+                G = zc;
+                dG = dzc;
+            }
+            double step = -G * b2rcp(dG);
+            dt += step;
+            px += vx * step;
+            py += vy * step;
+            pz += vz * step;
+            zc += dzc * step;
+            gP = dP;
+            // The departure gradient was evaluated one step back; the normal needs it at the hit
+            // point to ~3e-14 rad (1e-10 px at the focal plane ~ 4e-13 rad).  Pure aspheres:
+            // refresh dP to first order with d2P once the step is small (second evaluation from
+            // the conic seed); summed Zernike / bicubic terms: iterate until the step is < 1e-13 m.
+            if (pure && fabs(step) < 1e-6) {
+                gP = dP + ddP * (2.0 * rv * step);
+                conv = true;
+                break;
+            }
+            if (fabs(step) < 1e-13) {
+                conv = true;
+                break;
+            }
+        }
+        ok = ok && conv;
+    }
+    if (!ok) {
+        r.failed = true;
+        r.vignetted = true;
+        r.x = x; r.y = y; r.z = z;
+        r.vx = vx; r.vy = vy; r.vz = vz;
+        return;
+    }
+    r.t += dt;
+    if (interact == B2_INT_MIRROR || interact == B2_INT_REFRACT) {
+        // un-normalised normal N = (-Zx, -Zy, g): the surface gradient scaled by g = R - k1 zc, so the
+        // conic part grad F = (x, y, k1 z - R) needs no division; the departure gradient is scaled to match
+        double g = 1.0, Zx = 2.0 * gP * px + Ex, Zy = 2.0 * gP * py + Ey;
+        if (curved) {
+            g = s.R - s.k1 * zc;
+            Zx = Zx * g + px;
+            Zy = Zy * g + py;
+        }
+        double NN = g * g + Zx * Zx + Zy * Zy;
+        double iNN = b2rcp(NN);
+        double vn = -Zx * vx - Zy * vy + g * vz;  // v.N
+        if (interact == B2_INT_MIRROR) {
+            double f = 2.0 * vn * iNN;
+            vx += f * Zx;
+            vy += f * Zy;
+            vz -= f * g;
+        } else {
+            double na = media_pick(mn.n, med_in), inb = media_pick(mn.inv, med_out);
+            // u = na v is the unit direction; orient N against u
+            double uN = na * vn;
+            double sgn = uN > 0.0 ? -1.0 : 1.0;
+            uN *= sgn;
+            double eta = na * inb;
+            // v' = (eta u - [eta uN + sqrt((1-eta^2) NN + eta^2 uN^2)]/NN N) / nb
+            double fac = (eta * uN + b2sqrt((1.0 - eta * eta) * NN + eta * eta * uN * uN)) * iNN * sgn;
+            double e2 = eta * na;
+            vx = (e2 * vx + fac * Zx) * inb;
+            vy = (e2 * vy + fac * Zy) * inb;
+            vz = (e2 * vz - fac * g) * inb;
+        }
+    }
+    if (simple_clear) {
+        double r2 = px * px + py * py;
+        if (!(s.clr_in2 <= r2 && r2 < s.clr_out2)) r.vignetted = true;
+    } else {
+        for (int k = 0; k < s.n_obsc; ++k)
+            if (obscured(s.obsc[k], px, py)) r.vignetted = true;
+    }
+    r.x = px; r.y = py; r.z = pz;
+    r.vx = vx; r.vy = vy; r.vz = vz;
+}
+
+// ---- surface programs: interface sequences known at compile time -----------------------------------
+// Program 0 is the generic interpreter over DevOptics::surf.  Program B2_PROG_LSST is the Rubin
+// layout (batoid LSST_[ugrizy].yaml): M1 M2 M3 aspheric mirrors, L1, L2 (exit aspheric), filter, L3
+// (each an entrance and an exit conic or plane), detector plane; media 0 = air, 1 = glass; one centred
+// annular / circular clear aperture per surface; no summed perturbation terms.  The host selects it
+// when the uploaded telescope has exactly this signature (rotations and decentres are free: camera
+// rotator, detector heights and rigid-body perturbations keep it); anything else runs program 0.
+struct SurfSpec {
+    bool asphere;  // base conic + even polynomial (Newton); otherwise plane / sphere / paraboloid / quadric,
+                   // told apart at run time by the uniform `kind` and k1 of the DevSurf
+    int interact, med_in, med_out;
+};
+#define B2_PROG_GENERIC 0
+#define B2_PROG_LSST 1
+#define B2_PROG_LSST_LEN 12
+
+__host__ __device__ constexpr SurfSpec lsst_spec(int i) {
+    switch (i) {
+        case 0: case 1: case 2: return SurfSpec{true, B2_INT_MIRROR, 0, 0};  // M1, M2, M3
+        case 3: return SurfSpec{false, B2_INT_REFRACT, 0, 1};                // L1 entrance
+        case 4: return SurfSpec{false, B2_INT_REFRACT, 1, 0};                // L1 exit
+        case 5: return SurfSpec{false, B2_INT_REFRACT, 0, 1};                // L2 entrance
+        case 6: return SurfSpec{true, B2_INT_REFRACT, 1, 0};                 // L2 exit (asphere)
+        case 7: return SurfSpec{false, B2_INT_REFRACT, 0, 1};                // filter entrance
+        case 8: return SurfSpec{false, B2_INT_REFRACT, 1, 0};                // filter exit
+        case 9: return SurfSpec{false, B2_INT_REFRACT, 0, 1};                // L3 entrance
+        case 10: return SurfSpec{false, B2_INT_REFRACT, 1, 0};               // L3 exit
+        default: return SurfSpec{false, B2_INT_DETECTOR, 0, 0};              // detector
+    }
+}
+
+template <int IS>
+__device__ __forceinline__ void lsst_steps(const DevOptics& o, const MediaN& mn, Ray& r) {
+    if constexpr (IS < B2_PROG_LSST_LEN) {
+        constexpr SurfSpec sp = lsst_spec(IS);
+        const DevSurf& s = o.surf[IS];
+        surface_step(s, sp.asphere ? B2_SURF_ASPHERE : s.kind, sp.interact, sp.med_in, sp.med_out, B2_EXTRA_NONE, true,
+                     true, mn, r);
+        lsst_steps<IS + 1>(o, mn, r);
+    }
+}
+
 // batoid CompoundOptic.trace: sequential interfaces
+template <int PROG>
 __device__ __forceinline__ void trace_ray(const DevOptics& o, Ray& r, double wl) {
     // refractive indices and their inverses, once per photon per medium
-    double n0 = medium_n(o.media[0], wl);
-    double n1 = o.n_media > 1 ? medium_n(o.media[1], wl) : 1.0;
-    double n2 = o.n_media > 2 ? medium_n(o.media[2], wl) : 1.0;
-    double n3 = o.n_media > 3 ? medium_n(o.media[3], wl) : 1.0;
-    double i0 = b2rcp(n0), i1 = b2rcp(n1), i2 = b2rcp(n2), i3 = b2rcp(n3);
+    MediaN mn;
+    if constexpr (PROG == B2_PROG_LSST) {
+        mn.n[0] = medium_n(o.media[0], wl);
+        mn.n[1] = medium_n(o.media[1], wl);
+        mn.n[2] = mn.n[3] = 1.0;
+        mn.inv[0] = b2rcp(mn.n[0]);
+        mn.inv[1] = b2rcp(mn.n[1]);
+        mn.inv[2] = mn.inv[3] = 1.0;
+        lsst_steps<0>(o, mn, r);
+    } else {
+        mn.n[0] = medium_n(o.media[0], wl);
+        mn.n[1] = o.n_media > 1 ? medium_n(o.media[1], wl) : 1.0;
+        mn.n[2] = o.n_media > 2 ? medium_n(o.media[2], wl) : 1.0;
+        mn.n[3] = o.n_media > 3 ? medium_n(o.media[3], wl) : 1.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mn.inv[k] = b2rcp(mn.n[k]);
 #pragma unroll 1
-    for (int is = 0; is < o.n_surf; ++is) {
-        const DevSurf& s = o.surf[is];
-        // coordinate transformation: r' = drot^T (r - dr)
-        double dx = r.x - s.dr[0], dy = r.y - s.dr[1], dz = r.z - s.dr[2];
-        double x, y, z, vx, vy, vz;
-        if (s.rot_identity) {
-            x = dx; y = dy; z = dz;
-            vx = r.vx; vy = r.vy; vz = r.vz;
-        } else {
-            const double* M = s.drot;
-            x = dx * M[0] + dy * M[3] + dz * M[6];
-            y = dx * M[1] + dy * M[4] + dz * M[7];
-            z = dx * M[2] + dy * M[5] + dz * M[8];
-            vx = r.vx * M[0] + r.vy * M[3] + r.vz * M[6];
-            vy = r.vx * M[1] + r.vy * M[4] + r.vz * M[7];
-            vz = r.vx * M[2] + r.vy * M[5] + r.vz * M[8];
+        for (int is = 0; is < o.n_surf; ++is) {
+            const DevSurf& s = o.surf[is];
+            surface_step(s, s.kind, s.interact, s.med_in, s.med_out, s.extra_kind, s.simple_clear != 0, s.n_coef <= 4,
+                         mn, r);
         }
-        // intersection: go to the vertex plane first, then the near-vertex (small) root of the
-        // base conic x^2 + y^2 - 2 R z + k1 z^2 = 0
-        bool ok = (vz != 0.0);
-        double dt = -z * b2rcp(vz);
-        double px = x + vx * dt, py = y + vy * dt, pz = 0.0;
-        const bool curved = (s.kind != B2_SURF_PLANE);
-        if (curved) {
-            double A = vx * vx + vy * vy + s.k1 * vz * vz;
-            double B = 2.0 * (px * vx + py * vy - s.R * vz);
-            double C = px * px + py * py;
-            double disc = B * B - 4.0 * A * C;
-            ok = ok && (disc >= 0.0);
-            double q = -0.5 * (B + copysign(b2sqrt(disc), B));
-            double t1 = C * b2rcp(q);
-            dt += t1;
-            px += vx * t1;
-            py += vy * t1;
-            pz = vz * t1;
-        }
-        // zc: height of the base conic under the hit point (= pz unless the surface departs from it)
-        double zc = pz, gP = 0.0, Ex = 0.0, Ey = 0.0;
-        if (s.kind == B2_SURF_ASPHERE || s.extra_kind != B2_EXTRA_NONE) {
-            // Newton on the implicit form G(t) = r^2 - 2 R zc + k1 zc^2 with zc = z - P(r^2) - E(x, y):
-            // polynomial in the ray parameter, no square root; quadratic convergence from the conic hit
-            bool conv = false;
-            const bool pure = (s.extra_kind == B2_EXTRA_NONE);
-#pragma unroll 1
-            for (int it = 0; it < 8; ++it) {
-                double r2 = px * px + py * py;
-                double P, dP, ddP, E;
-                departure(s, px, py, r2, P, dP, ddP, E, Ex, Ey);
-                zc = pz - P - E;
-                double rv = px * vx + py * vy;
-                double dzc = vz - 2.0 * dP * rv - (Ex * vx + Ey * vy);
-                double G, dG;
-                if (curved) {
-                    G = r2 - 2.0 * s.R * zc + s.k1 * zc * zc;
-                    dG = 2.0 * rv - 2.0 * (s.R - s.k1 * zc) * dzc;
-                } else {
-                    G = zc;
-                    dG = dzc;
-                }
-                double step = -G * b2rcp(dG);
-                dt += step;
-                px += vx * step;
-                py += vy * step;
-                pz += vz * step;
-                zc += dzc * step;
-                gP = dP;
-                // The departure gradient was evaluated one step back; the normal needs it at the hit
-                // point to ~3e-14 rad (1e-10 px at the focal plane ~ 4e-13 rad).  Pure aspheres:
-                // refresh dP to first order with d2P once the step is small (second evaluation from
-                // the conic seed); summed Zernike / bicubic terms: iterate until the step is < 1e-13 m.
-                if (pure && fabs(step) < 1e-6) {
-                    gP = dP + ddP * (2.0 * rv * step);
-                    conv = true;
-                    break;
-                }
-                if (fabs(step) < 1e-13) {
-                    conv = true;
-                    break;
-                }
-            }
-            ok = ok && conv;
-        }
-        if (!ok) {
-            r.failed = true;
-            r.vignetted = true;
-            r.x = x; r.y = y; r.z = z;
-            r.vx = vx; r.vy = vy; r.vz = vz;
-            continue;
-        }
-        r.t += dt;
-        if (s.interact == B2_INT_MIRROR || s.interact == B2_INT_REFRACT) {
-            // surface gradient: conic part from grad F = (x, y, k1 z - R) (no square root), plus departure
-            double zx = 2.0 * gP * px + Ex, zy = 2.0 * gP * py + Ey;
-            if (curved) {
-                double ig = b2rcp(s.R - s.k1 * zc);
-                zx += px * ig;
-                zy += py * ig;
-            }
-            double NN = 1.0 + zx * zx + zy * zy;
-            double iNN = b2rcp(NN);
-            double vn = -zx * vx - zy * vy + vz;  // v.N with N = (-zx, -zy, 1) unnormalised
-            if (s.interact == B2_INT_MIRROR) {
-                double f = 2.0 * vn * iNN;
-                vx += f * zx;
-                vy += f * zy;
-                vz -= f;
-            } else {
-                int mi = s.med_in, mo = s.med_out;
-                double na = mi == 0 ? n0 : (mi == 1 ? n1 : (mi == 2 ? n2 : n3));
-                double nb = mo == 0 ? n0 : (mo == 1 ? n1 : (mo == 2 ? n2 : n3));
-                double inb = mo == 0 ? i0 : (mo == 1 ? i1 : (mo == 2 ? i2 : i3));
-                // u = na v is the unit direction; orient N against u
-                double uN = na * vn;
-                double sgn = uN > 0.0 ? -1.0 : 1.0;
-                uN *= sgn;
-                double eta = na * inb;
-                // v' = (eta u - [eta uN + sqrt((1-eta^2) NN + eta^2 uN^2)]/NN N) / nb
-                double fac = (eta * uN + b2sqrt((1.0 - eta * eta) * NN + eta * eta * uN * uN)) * iNN * sgn;
-                double e2 = eta * na;
-                vx = (e2 * vx + fac * zx) * inb;
-                vy = (e2 * vy + fac * zy) * inb;
-                vz = (e2 * vz - fac) * inb;
-            }
-        }
-        if (s.simple_clear) {
-            double r2 = px * px + py * py;
-            if (!(s.clr_in2 <= r2 && r2 < s.clr_out2)) r.vignetted = true;
-        } else {
-            for (int k = 0; k < s.n_obsc; ++k)
-                if (obscured(s.obsc[k], px, py)) r.vignetted = true;
-        }
-        r.x = px; r.y = py; r.z = pz;
-        r.vx = vx; r.vy = vy; r.vz = vz;
     }
 }
 
@@ -577,6 +651,7 @@ struct OpticsOut {
     bool vig, fail, offz;
 };
 
+template <int PROG>
 __device__ __forceinline__ OpticsOut optics_photon(const DevOptics& o, const B2OpticsOptions& opt, double xi, double yi,
                                                    double wl_nm, double u, double v, double time, double flux,
                                                    double g) {
@@ -609,7 +684,7 @@ __device__ __forceinline__ OpticsOut optics_photon(const DevOptics& o, const B2O
     r.t = 0.0;
     r.vignetted = false;
     r.failed = false;
-    trace_ray(o, r, wl);
+    trace_ray<PROG>(o, r, wl);
     out.vig = r.vignetted;
     out.fail = r.failed;
     out.offz = !out.vig && !(fabs(r.z) < 1.0e-15);

@@ -19,7 +19,7 @@ struct PoolParams {
     int write_back;  // also store the traced photons (x, y, dxdz, dydz, flux) like the unfused ops
 };
 
-template <int MINB>
+template <int MINB, int PROG>
 __global__ void __launch_bounds__(256, MINB)
 k_pool_step(const __grid_constant__ DevOptics o, const __grid_constant__ B2OpticsOptions opt,
             const __grid_constant__ DevSensor s, const __grid_constant__ PoolParams pp, int64_t n,
@@ -39,7 +39,7 @@ k_pool_step(const __grid_constant__ DevOptics o, const __grid_constant__ B2Optic
         sample_time_pupil(pp.sampler_seed, idx, pp.t0, pp.exptime, pp.r_in, pp.r_out, time, pu, pv);
         double g = o.dif.enabled ? philox_normal(opt.seed, opt.photon_offset + (uint64_t)i, 0u) : 0.0;
         const double wl = wl_nm[i];
-        OpticsOut r = optics_photon(o, opt, x[i], y[i], wl, pu, pv, time, flux[i], g);
+        OpticsOut r = optics_photon<PROG>(o, opt, x[i], y[i], wl, pu, pv, time, flux[i], g);
         vig = r.vig;
         fail = r.fail;
         offz = r.offz;
@@ -73,14 +73,17 @@ k_pool_step(const __grid_constant__ DevOptics o, const __grid_constant__ B2Optic
     }
 }
 
-static int pool_occ() {
+static int pool_occ(int program) {
     static int occ = -1;
     if (occ < 0) {
         const char* e = getenv("B2_POOL_OCC");
-        occ = e ? atoi(e) : 4;  // measured on B200: 8.2 / 7.0 / 6.7 ms per 2^25 photons at 2 / 3 / 4 blocks per SM
-        if (occ < 2 || occ > 4) occ = 4;
+        occ = e ? atoi(e) : 0;
+        if (occ < 2 || occ > 5) occ = 0;
     }
-    return occ;
+    if (occ) return (program == B2_PROG_LSST || occ <= 4) ? occ : 4;
+    // measured on B200, ms per 2^25 photons at 2 / 3 / 4 (/ 5) blocks per SM: interpreter 8.2 / 7.0 / 6.7;
+    // LSST program (no spills down to 64 registers) - / 6.25 / 6.19 / 5.77
+    return program == B2_PROG_LSST ? 5 : 4;
 }
 
 // One photon batch of the pooled pipeline on device-resident arrays:
@@ -118,16 +121,22 @@ extern "C" int b2_pool_step(b2_ctx* ctx, b2_sensor* sensor, int64_t n, double* x
                 B2_CUDA(cudaEventCreate(&e1));
                 B2_CUDA(cudaEventRecord(e0, st));
             }
-            switch (pool_occ()) {
-                case 2:
-                    k_pool_step<2><<<blocks, 256, 0, st>>>(ctx->opt, *opt, sensor->d, pp, n, x, y, dxdz, dydz, flux, wl_nm, dostats, sensor->dstats, sensor->dadded, (SlowRec*)sensor->slow.ptr, sensor->dnslow);
-                    break;
-                case 4:
-                    k_pool_step<4><<<blocks, 256, 0, st>>>(ctx->opt, *opt, sensor->d, pp, n, x, y, dxdz, dydz, flux, wl_nm, dostats, sensor->dstats, sensor->dadded, (SlowRec*)sensor->slow.ptr, sensor->dnslow);
-                    break;
-                default:
-                    k_pool_step<3><<<blocks, 256, 0, st>>>(ctx->opt, *opt, sensor->d, pp, n, x, y, dxdz, dydz, flux, wl_nm, dostats, sensor->dstats, sensor->dadded, (SlowRec*)sensor->slow.ptr, sensor->dnslow);
+#define B2_LAUNCH_POOL(MINB, PROG)                                                                                \
+    k_pool_step<MINB, PROG><<<blocks, 256, 0, st>>>(ctx->opt, *opt, sensor->d, pp, n, x, y, dxdz, dydz, flux, wl_nm,   \
+                                                    dostats, sensor->dstats, sensor->dadded,                         \
+                                                    (SlowRec*)sensor->slow.ptr, sensor->dnslow)
+            const int occ = pool_occ(ctx->program);
+            if (ctx->program == B2_PROG_LSST) {
+                if (occ == 2) B2_LAUNCH_POOL(2, B2_PROG_LSST);
+                else if (occ == 3) B2_LAUNCH_POOL(3, B2_PROG_LSST);
+                else if (occ == 5) B2_LAUNCH_POOL(5, B2_PROG_LSST);
+                else B2_LAUNCH_POOL(4, B2_PROG_LSST);
+            } else {
+                if (occ == 2) B2_LAUNCH_POOL(2, B2_PROG_GENERIC);
+                else if (occ == 3) B2_LAUNCH_POOL(3, B2_PROG_GENERIC);
+                else B2_LAUNCH_POOL(4, B2_PROG_GENERIC);
             }
+#undef B2_LAUNCH_POOL
             B2_CHECK_LAUNCH();
             if (ctx->record_events) {
                 B2_CUDA(cudaEventRecord(e1, st));

@@ -251,6 +251,12 @@ int b2_telescope_upload(b2_ctx* ctx, const B2Telescope* tel);
    bicubic: data = [x0, dx, nx, y0, dy, ny] followed by 4 grids (z, dzdx, dzdy, d2zdxdy),
    each ny*nx row-major (batoid.Bicubic). */
 int b2_telescope_set_extra(b2_ctx* ctx, int surface_index, int extra_kind, const double* data, int64_t n);
+/* Surface program the trace kernels run for the uploaded telescope: 0 = generic interpreter over the
+   surface list, 1 = the Rubin layout compiled as straight-line code (3 aspheric mirrors, 4 two-surface
+   lenses with an aspheric L2 exit, detector; no summed perturbation terms).  Chosen by
+   b2_telescope_upload / b2_telescope_set_extra from the telescope's signature; environment B2_PROGRAM=0
+   forces the interpreter.  Both run the same arithmetic. */
+int b2_telescope_program(b2_ctx* ctx);
 /* replaces: base['current_image'].wcs, base['_icrf_to_field'] (imsim/photon_ops.py:407-408) */
 int b2_wcs_upload(b2_ctx* ctx, const B2TanSip* img_wcs, const B2TanSip* icrf_to_field);
 /* replaces: camera[det_name] as used by imsim/photon_ops.py:495-500 */

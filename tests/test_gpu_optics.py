@@ -95,6 +95,45 @@ def test_trace_rays_matches_oracle(rot):
     _close(arrs[6][ok], ref[6][ok])  # time of flight
 
 
+@pytest.mark.parametrize("rot", [0.0, np.radians(-25.0)])
+def test_surface_program_equals_interpreter(rot, monkeypatch):
+    """The Rubin layout compiled as straight-line code (program 1) and the generic interpreter over the
+    surface list (program 0) are the same arithmetic: identical flags, results equal to rounding."""
+    tel = rubin_like("i", rot_tel_pos=rot, detector_z_offset=1.5e-5)
+    rng = np.random.default_rng(17)
+    n = 200000
+    r = np.sqrt(rng.uniform(2.3**2, 4.3**2, n))
+    ph = rng.uniform(0, 2 * np.pi, n)
+    thx, thy = rng.uniform(-0.031, 0.031, n), rng.uniform(-0.031, 0.031, n)
+    wl = rng.uniform(320e-9, 1050e-9, n)
+    g = 1 / np.sqrt(1 + thx**2 + thy**2)
+    nair = tel.in_medium.n(wl)
+    base = [r * np.cos(ph), r * np.sin(ph), np.zeros(n), thx * g / nair, thy * g / nair, -g / nair, np.zeros(n), wl]
+    out = {}
+    for prog in (1, 0):
+        if prog == 0:
+            monkeypatch.setenv("B2_PROGRAM", "0")
+        ctx = _ctx()
+        ctx.set_telescope(tel)
+        assert ctx.program == prog
+        arrs = [np.ascontiguousarray(a.copy()) for a in base]
+        vig, fail = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        ctx.trace_rays(*arrs, vig, fail)
+        out[prog] = arrs, vig, fail
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+    assert 0.05 < out[1][1].mean() < 0.6
+    ok = out[1][2] == 0
+    for k, scale in ((0, 0.3), (1, 0.3), (3, 1.0), (4, 1.0), (5, 1.0), (6, 30.0)):
+        _close(out[1][0][k][ok], out[0][0][k][ok], scale=scale, rtol=1e-14)
+    # a perturbed mirror leaves the layout: interpreter
+    monkeypatch.delenv("B2_PROGRAM", raising=False)
+    ctx = _ctx()
+    poly = np.zeros((4, 4))
+    poly[2, 0] = poly[0, 2] = 1e-8
+    ctx.set_telescope(tel.with_surface_perturbation("M2", poly=poly, poly_scale=1 / 1.71))
+    assert ctx.program == 0
+
+
 def test_paraboloid_focus_exact():
     tel = paraboloid_test_telescope(10.0)
     ctx = _ctx()
