@@ -157,8 +157,47 @@ class B2AccumStats(C.Structure):
         return {name: getattr(self, name) for name, _ in self._fields_}
 
 
+PROF_DELTA, PROF_GAUSSIAN, PROF_RADIAL, PROF_KNOTS, PROF_BOX = range(5)
+B2_MAX_SCREENS = 8
+B2_STAGE1_NRAND = 12
+
+
+class B2Object(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("sed", C.c_int32), ("lut", C.c_int32), ("n_knots", C.c_int32),
+        ("x", C.c_double), ("y", C.c_double),
+        ("m", C.c_double * 4),
+        ("p0", C.c_double), ("p1", C.c_double),
+        ("thx", C.c_double), ("thy", C.c_double),
+        ("knot_seed", C.c_uint64),
+    ]
+
+
+class B2Psf(C.Structure):
+    _fields_ = [
+        ("n_screens", C.c_int32), ("npix", C.c_int32), ("screen_f32", C.c_int32), ("n_kick", C.c_int32),
+        ("screen_scale", C.c_double),
+        ("altitude", C.c_double * B2_MAX_SCREENS),
+        ("vx", C.c_double * B2_MAX_SCREENS), ("vy", C.c_double * B2_MAX_SCREENS),
+        ("t0", C.c_double), ("exptime", C.c_double),
+        ("r_inner", C.c_double), ("r_outer", C.c_double),
+        ("base_wavelength", C.c_double), ("exponent", C.c_double),
+        ("kick_delta_prob", C.c_double), ("kick_tmax", C.c_double),
+        ("gauss_sigma", C.c_double),
+        ("arcsec_to_pix", C.c_double * 4),
+    ]
+
+
+# numpy structured dtype with the layout of B2Object (object tables are built vectorised)
+import numpy as _np  # noqa: E402
+
+OBJECT_DTYPE = _np.dtype([("kind", "<i4"), ("sed", "<i4"), ("lut", "<i4"), ("n_knots", "<i4"), ("x", "<f8"), ("y", "<f8"),
+                          ("m", "<f8", (4,)), ("p0", "<f8"), ("p1", "<f8"), ("thx", "<f8"), ("thy", "<f8"),
+                          ("knot_seed", "<u8")])
+assert OBJECT_DTYPE.itemsize == C.sizeof(B2Object)
+
 # order of b2_sizeof(which)
 SIZEOF_ORDER = [
     B2Telescope, B2Surface, B2TanSip, B2Detector, B2Diffraction, B2OpticsOptions,
-    B2OpticsStats, B2SensorConfig, B2AccumStats, B2Obsc, B2Medium,
+    B2OpticsStats, B2SensorConfig, B2AccumStats, B2Obsc, B2Medium, B2Object, B2Psf,
 ]

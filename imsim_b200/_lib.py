@@ -16,14 +16,14 @@ import numpy as np
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SRC = [os.path.join(_HERE, "csrc", f) for f in ("abi.cu", "optics.cu", "sensor.cu", "pool.cu")]
+_SRC = [os.path.join(_HERE, "csrc", f) for f in ("abi.cu", "optics.cu", "sensor.cu", "pool.cu", "stage1.cu")]
 _HDR = [os.path.join(_HERE, "csrc", f) for f in ("b2_common.cuh", "optics_device.cuh", "sensor_device.cuh")] + \
     [os.path.join(os.path.dirname(_HERE), "include", "imsim_b200.h")]
 SO_PATH = os.path.join(_HERE, "_build", "libimsim_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "--threads", "0",
 ]
 
 
@@ -92,6 +92,10 @@ _SIGNATURES = {
     "b2_flat_photons": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp,
                                   C.c_int32, C.c_uint64, C.c_uint64]),
     "b2_object_photons": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32, vp, vp, C.c_int32,
+                                    C.c_uint64, C.c_uint64]),
+    "b2_psf_upload": (C.c_int, [vp, C.POINTER(_abi.B2Psf), C.POINTER(vp), vp]),
+    "b2_radial_luts_upload": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_double]),
+    "b2_stage1_photons": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int32, vp, vp, C.c_int32, C.c_int32, vp,
                                     C.c_uint64, C.c_uint64]),
     "b2_sensor_create": (C.c_int, [vp, C.POINTER(_abi.B2SensorConfig), vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
     "b2_sensor_destroy": (C.c_int, [vp]),

@@ -25,6 +25,8 @@ extern "C" int64_t b2_sizeof(int32_t which) {
         case 8: return sizeof(B2AccumStats);
         case 9: return sizeof(B2Obsc);
         case 10: return sizeof(B2Medium);
+        case 11: return sizeof(B2Object);
+        case 12: return sizeof(B2Psf);
     }
     return -1;
 }
@@ -65,6 +67,7 @@ extern "C" int b2_ctx_destroy(b2_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    b2_stage1_release(ctx);
     for (void* p : ctx->extras) cudaFree(p);
     if (ctx->scratch.ptr) cudaFree(ctx->scratch.ptr);
     if (ctx->stats.ptr) cudaFree(ctx->stats.ptr);

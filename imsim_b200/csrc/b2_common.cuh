@@ -131,6 +131,7 @@ struct b2_ctx {
 };
 
 int b2_scratch_reserve(b2_ctx* ctx, Scratch& s, size_t bytes);
+void b2_stage1_release(b2_ctx* ctx);  // stage1.cu: per-context PSF / profile tables
 
 // stage helper for B2_HOST calls: carve arrays out of the context scratch
 struct Stager {

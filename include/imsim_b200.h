@@ -212,6 +212,55 @@ typedef struct {
     uint64_t n_dropped_bottom;  /* zconv < 0 */
 } B2AccumStats;
 
+/* ------------------------------------------------------------------ */
+/* Stage 1: photons of catalogue objects generated in HBM              */
+/* ------------------------------------------------------------------ */
+
+/* unit profiles (before the object's 2x2 matrix):
+   DELTA    galsim.DeltaFunction                                   (imsim/instcat.py:483-484)
+   GAUSSIAN unit-sigma Gaussian
+   RADIAL   radial inverse-CDF table row `lut` (Sersic(n), Exponential ...; radius in units of the half-light
+            radius, tabulated on t = -log(1 - u))                   (instcat.py:496-520)
+   KNOTS    galsim.RandomKnots: one of n_knots points, each a unit-half-light-radius Gaussian deviate derived
+            from knot_seed                                          (instcat.py:522-545)
+   BOX      galsim.Box(p0, p1): uniform over p0 x p1                (instcat.py:486-494) */
+enum { B2_PROF_DELTA = 0, B2_PROF_GAUSSIAN = 1, B2_PROF_RADIAL = 2, B2_PROF_KNOTS = 3, B2_PROF_BOX = 4 };
+
+typedef struct {
+    int32_t kind;     /* B2_PROF_* */
+    int32_t sed;      /* row of the wavelength inverse-CDF table (SED x bandpass of this object) */
+    int32_t lut;      /* row of the radial table (B2_PROF_RADIAL) */
+    int32_t n_knots;  /* B2_PROF_KNOTS */
+    double x, y;      /* centre on the image [px] */
+    double m[4];      /* unit-profile offset -> pixels, row-major: size x shear(q, beta) x lens(g1, g2, mu) x
+                         local WCS (arcsec -> px) */
+    double p0, p1;    /* BOX: length, width in the units m maps from */
+    double thx, thy;  /* field angle of the object [rad] (atmospheric screens are offset by altitude * tan) */
+    uint64_t knot_seed;
+} B2Object;
+
+#define B2_MAX_SCREENS 8
+/* imsim.atmPSF.AtmosphericPSF.getPSF (imsim/atmPSF.py:298-336) as a photon kick: frozen-flow phase screens
+   (first kick, geometric), the SecondKick radial sampler, the optics Gaussian of config/imsim-config.yaml:239-256,
+   chromatic dilation (lambda / base_wavelength)^exponent applied to the atmospheric part. */
+typedef struct {
+    int32_t n_screens;            /* 0: no atmosphere */
+    int32_t npix;                 /* each screen npix x npix, periodic */
+    int32_t screen_f32;           /* 1: tables are float32, 0: float64 */
+    int32_t n_kick;               /* entries of the second-kick radial table, 0: none */
+    double screen_scale;          /* [m] */
+    double altitude[B2_MAX_SCREENS];  /* [m] */
+    double vx[B2_MAX_SCREENS], vy[B2_MAX_SCREENS];  /* wind [m/s] */
+    double t0, exptime;           /* the shooter's own time draw (overwritten later by TimeSampler: SURVEY Q1) */
+    double r_inner, r_outer;      /* its own pupil draw: annulus radii [m] (diam 8.36, obscuration 0.61) */
+    double base_wavelength;       /* [nm] */
+    double exponent;              /* -0.3 */
+    double kick_delta_prob;       /* probability that the second kick leaves the photon unmoved */
+    double kick_tmax;             /* radial table abscissa: t = -log(1 - u) in [0, kick_tmax] */
+    double gauss_sigma;           /* optics Gaussian sigma [arcsec], 0: none */
+    double arcsec_to_pix[4];      /* inverse local WCS Jacobian, row-major (one per pool: SURVEY Q2) */
+} B2Psf;
+
 #ifndef B2_STRUCTS_ONLY /* (the oracle's FLOP counter re-reads only the POD structs above) */
 typedef struct b2_ctx b2_ctx;
 typedef struct b2_sensor b2_sensor;
@@ -305,6 +354,20 @@ int b2_flat_photons(b2_ctx* ctx, int64_t n, double* x, double* y, double* flux, 
 int b2_object_photons(b2_ctx* ctx, int64_t n, double* x, double* y, double* flux, double* wl, const double* obj_x,
                       const double* obj_y, const double* obj_sigma, const int64_t* obj_cum, int32_t nobj,
                       const double* cdf, const double* cdf_wave, int32_t ncdf, uint64_t seed, uint64_t photon_offset);
+
+/* Stage 1 of the north star on the device: catalogue objects -> pooled photons (x, y, flux, wavelength), i.e.
+   build_stamps + drawImage(method='phot') + merge_photon_arrays (imsim/photon_pooling.py:151-152, stamp.py:727-743)
+   without the host.  Object j owns photons [obj_cum[j], obj_cum[j+1]).  Per photon: profile offset through the
+   object's matrix, wavelength from row `sed` of the inverse-CDF table (ncdf columns, shared abscissa cdf_wave
+   per row), then the PSF kicks of B2Psf (screens / second kick / Gaussian).  rand: NULL (Philox streams 7-10 of
+   `seed`, counted from photon_offset) or B2_STAGE1_NRAND uniforms per photon, rand[k * n + i], for parity tests.
+   DEVICE pointers only; screens[l] npix*npix row-major [y][x]. */
+#define B2_STAGE1_NRAND 12
+int b2_psf_upload(b2_ctx* ctx, const B2Psf* psf, const void* const* screens, const double* kick_table);
+int b2_radial_luts_upload(b2_ctx* ctx, const double* lut, int32_t n_lut, int32_t n_entries, double tmax);
+int b2_stage1_photons(b2_ctx* ctx, int64_t n, double* x, double* y, double* flux, double* wl, const B2Object* objects,
+                      const int64_t* obj_cum, int32_t nobj, const double* cdf, const double* cdf_wave, int32_t n_sed,
+                      int32_t ncdf, const double* rand, uint64_t seed, uint64_t photon_offset);
 
 /* ---- silicon sensor ---------------------------------------------------- */
 /* replaces galsim.SiliconSensor.__init__ (imsim/lsst_image.py:93-103,
