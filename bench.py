@@ -44,9 +44,9 @@ ALG_FLOP_TRACE = 3765.0
 # fused k_pool_step = trace + sensor fast path: SURVEY 8d adds 56 B (6 reads + 1 atomic RMW) and ~60 FLOP
 ALG_BYTES_POOL = 96.0 + 56.0
 ALG_FLOP_POOL = ALG_FLOP_TRACE + 60.0
-# DRAM traffic of k_pool_step<4> from `ncu --set full` (profiles/r01_k_pool_step_details.csv):
-# (1.188 GB read + 0.118 GB written) / 33554432 photons
-NCU_TRAFFIC_BYTES_PER_PHOTON_POOL = 38.9
+# DRAM traffic of k_pool_step<4, LSST program> from `ncu --set full` (profiles/r01_k_pool_step_program_details.csv):
+# (1.173 GB read + 0.032 GB written) / 33554432 photons
+NCU_TRAFFIC_BYTES_PER_PHOTON_POOL = 35.9
 DETECTORS = ["R22_S11", "R21_S11", "R23_S11", "R12_S11", "R32_S11", "R22_S00", "R22_S22", "R11_S11"]
 
 
@@ -219,7 +219,7 @@ def run_visit(args):
     from imsim_b200.detector import lsstcam_science_detectors
     from imsim_b200.flat import wavelength_cdf
     from imsim_b200.sharding import gather_visit_metadata, lpt_partition
-    from imsim_b200.visit import DetectorRunner, synthetic_objects
+    from imsim_b200.visit import DetectorRunner, synthetic_catalog, synthetic_objects
 
     rank, world, local = dist_info()
     if world > 1:
@@ -233,16 +233,27 @@ def run_visit(args):
     mine = lpt_partition(costs, world)[rank]
     models = {"e2v": helpers.sensor_model("lsst_e2v_50_4"), "itl": helpers.sensor_model("lsst_itl_50_4")}
     tr = helpers.tree_ring_table("R22_S11")
-    runner = DetectorRunner(local, models, helpers.absorption(), tree_rings={d: tr for d in mine})
+    psf = None
     wave = np.linspace(550.0, 690.0, 29)
     cdf = wavelength_cdf(wave, np.ones_like(wave))
+    if args.visit_catalog:
+        # stage 1 from catalogue rows: one atmosphere realisation per visit (6 screens of 8192^2 at 0.1 m), 8 SEDs
+        from imsim_b200.atmosphere import AtmosphericPSF
+
+        psf = AtmosphericPSF(1.2, 0.7, "r", rng=271828, device="cuda:%d" % local)
+        seds = [wavelength_cdf(wave, 1.0 + 0.8 * np.sin(wave / (15.0 + 5 * k))) for k in range(8)]
+        cdf = (np.array([c for c, _ in seds]), np.array([w for _, w in seds]))
+    runner = DetectorRunner(local, models, helpers.absorption(), tree_rings={d: tr for d in mine}, psf=psf)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     recs = []
     for k, d in enumerate(mine):
-        objs = synthetic_objects(20000, 4096, 4004, seed=dets.index(d), total_photons=costs[d])
+        if args.visit_catalog:
+            objs = synthetic_catalog(20000, 4096, 4004, seed=dets.index(d), total_photons=costs[d])
+        else:
+            objs = synthetic_objects(20000, 4096, 4004, seed=dets.index(d), total_photons=costs[d])
         rec, _ = runner.run(d, objs, nbatch=10, wavelength_cdf=cdf, det_index=dets.index(d))
         recs.append(rec)
     torch.cuda.synchronize()
@@ -254,7 +265,8 @@ def run_visit(args):
     if rank == 0:
         photons = sum(r["photons"] for r in allrec)
         gpu_s = max(sum(r["gpu_ms"] for r in allrec if r["device"] == g) for g in range(world)) * 1e-3
-        print(json.dumps({"mode": "visit", "n_gpus": world, "ccds": len(allrec), "photons": photons,
+        print(json.dumps({"mode": "visit", "stage1": "catalogue+atmosphere" if args.visit_catalog else "gaussian-points",
+                          "n_gpus": world, "ccds": len(allrec), "photons": photons,
                           "wall_s_max_rank": float(wt.item()), "gpu_s_max_rank": gpu_s,
                           "visits_per_hour_wall": 3600.0 / float(wt.item()),
                           "visits_per_hour_gpu_time": 3600.0 / gpu_s,
@@ -291,6 +303,9 @@ def main():
                     help="extra mode (not the headline line): simulate a synthetic LSSTCam visit, 189 CCDs sharded "
                          "by detector over the ranks, --visit-photons per CCD; prints one JSON line")
     ap.add_argument("--visit-photons", type=float, default=1e8)
+    ap.add_argument("--visit-catalog", action="store_true",
+                    help="with --visit: stage 1 from catalogue rows (stars + bulge/disc/knots galaxies, per-object SEDs) "
+                         "behind the atmospheric PSF (6 phase screens + second kick) instead of Gaussian point sources")
     ap.add_argument("--visit-ccds", type=int, default=189)
     ap.add_argument("--kernel-timing", action="store_true",
                     help="diagnostic: bracket every kernel with CUDA events (B2_TIMING=1) and print the breakdown "
@@ -459,7 +474,7 @@ def main():
                          "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                          "traffic": None if args.unfused else NCU_TRAFFIC_BYTES_PER_PHOTON_POOL * P,
                          "traffic_source": "ncu --set full capture of the same kernel, per launch scaled to this pool "
-                                           "size (profiles/r01_k_pool_step_details.csv)", "peak_source": peak_src,
+                                           "size (profiles/r01_k_pool_step_program_details.csv)", "peak_source": peak_src,
                          "kernel_ms": tr_ms, "share_of_step": tr_ms * K / total_ms,
                          "note": "kernel is FP64-pipe bound, see roofline_fp64"},
             "roofline_fp64": {"kernel": dominant, "bound": "fp64 fma pipe", "achieved": ach_tf,

@@ -102,24 +102,35 @@ class ObjectTable:
         self._push(r, flux, x, y, sed, thx, thy)
 
     def _galaxy_matrix(self, hlr, q, beta, g1, g2, mu):
-        return self.arcsec_to_pix @ lens_matrix(g1, g2, mu) @ shear_matrix(q=q, beta=beta) * hlr
+        """arcsec_to_pix @ lens(g1, g2, mu) @ shear(q, beta) * hlr, vectorised over objects -> (N, 4)."""
+        hlr, q, beta, g1, g2, mu = np.broadcast_arrays(*(np.atleast_1d(np.asarray(a, float))
+                                                         for a in (hlr, q, beta, g1, g2, mu)))
+        g = (1.0 - q) / (1.0 + q)
+        s1, s2 = g * np.cos(2.0 * beta), g * np.sin(2.0 * beta)
+        S = np.array([[1.0 + s1, s2], [s2, 1.0 - s1]]) / np.sqrt(1.0 - (s1 * s1 + s2 * s2))  # (2, 2, N)
+        L = np.array([[1.0 + g1, g2], [g2, 1.0 - g1]]) * (np.sqrt(mu) / np.sqrt(1.0 - (g1 * g1 + g2 * g2)))
+        M = np.einsum("ij,jkn,kln->nil", self.arcsec_to_pix, L, S) * hlr[:, None, None]
+        return M.reshape(-1, 4)
 
     def add_sersic(self, x, y, flux, hlr_arcsec, n, q=1.0, beta=0.0, g1=0.0, g2=0.0, mu=1.0, sed=0, thx=0.0, thy=0.0):
-        """``Sersic(n, half_light_radius)._shear(Shear(q, beta))._lens(g1, g2, mu)`` (instcat.py:496-520)."""
-        r = self._new(1)
+        """``Sersic(n, half_light_radius)._shear(Shear(q, beta))._lens(g1, g2, mu)`` (instcat.py:496-520);
+        scalars or arrays (one Sersic index per call)."""
+        m = self._galaxy_matrix(hlr_arcsec, q, beta, g1, g2, mu)
+        r = self._new(max(m.shape[0], np.atleast_1d(x).size))
         r["kind"] = _abi.PROF_RADIAL
         r["lut"] = self._lut_row(n)
-        r["m"] = self._galaxy_matrix(hlr_arcsec, q, beta, g1, g2, mu).ravel()
+        r["m"] = m
         self._push(r, flux, x, y, sed, thx, thy)
 
     def add_knots(self, x, y, flux, hlr_arcsec, npoints, q=1.0, beta=0.0, g1=0.0, g2=0.0, mu=1.0, sed=0, seed=0,
                   thx=0.0, thy=0.0):
-        """``RandomKnots(npoints, half_light_radius)`` sheared and lensed (instcat.py:522-545)."""
-        r = self._new(1)
+        """``RandomKnots(npoints, half_light_radius)`` sheared and lensed (instcat.py:522-545); scalars or arrays."""
+        m = self._galaxy_matrix(hlr_arcsec, q, beta, g1, g2, mu)
+        r = self._new(max(m.shape[0], np.atleast_1d(x).size))
         r["kind"] = _abi.PROF_KNOTS
-        r["n_knots"] = int(npoints)
-        r["knot_seed"] = np.uint64(seed)
-        r["m"] = self._galaxy_matrix(hlr_arcsec, q, beta, g1, g2, mu).ravel()
+        r["n_knots"] = npoints
+        r["knot_seed"] = np.asarray(seed, dtype=np.uint64)
+        r["m"] = m
         self._push(r, flux, x, y, sed, thx, thy)
 
     def add_streak(self, x, y, flux, length_arcsec, width_arcsec, position_angle=0.0, sed=0, thx=0.0, thy=0.0):

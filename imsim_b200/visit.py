@@ -48,12 +48,43 @@ def synthetic_objects(n_obj: int, nx: int, ny: int, seed: int, total_photons: fl
     return x, y, flux, sigma
 
 
+def synthetic_catalog(n_obj: int, nx: int, ny: int, seed: int, total_photons: float, galaxy_fraction: float = 0.6,
+                      arcsec_to_pix=None, n_sed: int = 8):
+    """A dense field as catalogue rows for stage 1 (``ObjectTable``): stars (DeltaFunction) and galaxies as the
+    reference's catalogues describe them -- a de Vaucouleurs bulge, an exponential disc and star-forming knots
+    (skyCatalogs ``Add([bulge, disk, knots])``, imsim/skycat.py:163-190; sersic2d / knots rows of instance
+    catalogues, imsim/instcat.py:496-545) -- with the flux function of ``synthetic_objects``."""
+    from .stage1 import ObjectTable
+
+    rng = np.random.default_rng(seed)
+    x, y, flux, _ = synthetic_objects(n_obj, nx, ny, seed, total_photons)
+    tab = ObjectTable(arcsec_to_pix=np.eye(2) / 0.2 if arcsec_to_pix is None else np.asarray(arcsec_to_pix, float))
+    is_gal = rng.random(n_obj) < galaxy_fraction
+    sed = rng.integers(0, n_sed, n_obj)
+    st = np.nonzero(~is_gal)[0]
+    tab.add_points(x[st], y[st], flux[st], sed=sed[st])
+    g = np.nonzero(is_gal)[0]
+    ng = g.size
+    hlr = np.exp(rng.normal(np.log(0.5), 0.5, ng))
+    q, beta = rng.uniform(0.2, 1.0, ng), rng.uniform(0, np.pi, ng)
+    g1, g2 = rng.normal(0, 0.01, ng), rng.normal(0, 0.01, ng)
+    bt = rng.uniform(0.1, 0.6, ng)  # bulge fraction
+    fb = np.maximum(np.round(flux[g] * bt), 1).astype(np.int64)
+    fk = np.maximum(np.round(flux[g] * 0.1), 1).astype(np.int64)
+    fd = np.maximum(flux[g] - fb - fk, 1)
+    tab.add_sersic(x[g], y[g], fb, 0.6 * hlr, 4.0, q=np.minimum(1.0, q + 0.2), beta=beta, g1=g1, g2=g2, sed=sed[g])
+    tab.add_sersic(x[g], y[g], fd, hlr, 1.0, q=q, beta=beta, g1=g1, g2=g2, sed=sed[g])
+    tab.add_knots(x[g], y[g], fk, hlr, rng.integers(5, 40, ng), q=q, beta=beta, g1=g1, g2=g2,
+                  sed=rng.integers(0, n_sed, ng), seed=rng.integers(1 << 62, size=ng))
+    return tab
+
+
 class DetectorRunner:
     """Reusable per-GPU state: one context, one sensor object per vendor model (re-bound per detector)."""
 
     def __init__(self, device: int, sensor_models: Dict[str, tuple], absorption_table, tree_rings=None,
                  band: str = "r", rot_tel_pos: float = np.radians(60.0), altitude=np.radians(67.0),
-                 azimuth=np.radians(213.0), exptime: float = 30.0, seed: int = 1):
+                 azimuth=np.radians(213.0), exptime: float = 30.0, seed: int = 1, psf=None):
         import torch
 
         self.torch = torch
@@ -66,6 +97,9 @@ class DetectorRunner:
         self.band, self.rot_tel_pos, self.exptime, self.seed = band, rot_tel_pos, exptime, seed
         self.dif = diffraction_config(latitude=RUBIN_LATITUDE, altitude=altitude, azimuth=azimuth)
         self._sensors: Dict[tuple, SiliconSensor] = {}
+        #: stage-1 PSF (``atmosphere.AtmosphericPSF`` / ``GaussianPSF``): one realisation per visit, shared by the
+        #: detectors of this GPU like the reference's ``atm_psf`` input object (imsim/atmPSF.py:339-347)
+        self.psf = psf
 
     def sensor_for(self, det_name: str) -> SiliconSensor:
         """One sensor object per vendor model, re-used across detectors: only the tree-ring table
@@ -96,15 +130,29 @@ class DetectorRunner:
         sensor = self.sensor_for(det_name)
         image = Image(np.zeros((det.ny, det.nx), np.float32), 0, 0)
         pool = PhotonPool(self.ctx, sensor, exptime=self.exptime, seed=self.seed + 1000 * det_index)
-        ox, oy, oflux, osig = objects
         gen = np.random.default_rng(self.seed + det_index)
-        counts = photon_batch_counts(oflux, np.zeros(len(oflux), bool), nbatch, gen.random)
-        d_ox = torch.as_tensor(ox, device=dev)
-        d_oy = torch.as_tensor(oy, device=dev)
-        d_os = torch.as_tensor(osig, device=dev)
+        catalogue = not (isinstance(objects, tuple) and len(objects) == 4)
         cdf = cdfw = None
-        if wavelength_cdf is not None:
-            cdf, cdfw = (torch.as_tensor(a, device=dev) for a in wavelength_cdf)
+        if catalogue:
+            # stage 1 from catalogue rows (stage1.ObjectTable): profiles, per-object SEDs, PSF kicks
+            from .stage1 import Stage1
+
+            rows, oflux = objects.build()
+            rows = rows.copy()
+            vx, vy, vz = self.ctx.xy_to_v(np.ascontiguousarray(rows["x"]), np.ascontiguousarray(rows["y"]))
+            rows["thx"], rows["thy"] = np.arctan2(vx, -vz), np.arctan2(vy, -vz)
+            cdf_np, cdfw_np = wavelength_cdf if wavelength_cdf is not None else (None, None)
+            stage1 = Stage1(self.ctx, rows, cdf_np, cdfw_np, objects.radial_tables())
+            if self.psf is not None:
+                self.psf.upload(self.ctx, objects.arcsec_to_pix)
+        else:
+            ox, oy, oflux, osig = objects
+            d_ox = torch.as_tensor(ox, device=dev)
+            d_oy = torch.as_tensor(oy, device=dev)
+            d_os = torch.as_tensor(osig, device=dev)
+            if wavelength_cdf is not None:
+                cdf, cdfw = (torch.as_tensor(a, device=dev) for a in wavelength_cdf)
+        counts = photon_batch_counts(oflux, np.zeros(len(oflux), bool), nbatch, gen.random)
         t_setup = time.perf_counter() - t0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -116,12 +164,15 @@ class DetectorRunner:
             n = int(cnt.sum())
             if n == 0:
                 continue
-            cum = torch.as_tensor(np.concatenate([[0], np.cumsum(cnt)]), device=dev)
-            sel = torch.as_tensor(idx, device=dev)
             dp = DevicePhotons(n, device=dev, fields=("x", "y", "flux", "wavelength"))
-            self.ctx.object_photons(dp.x, dp.y, dp.flux, dp.wavelength, d_ox[sel].contiguous(), d_oy[sel].contiguous(),
-                                    d_os[sel].contiguous(), cum, cdf, cdfw, seed=self.seed + 7 * det_index,
-                                    photon_offset=n_total)
+            if catalogue:
+                stage1.shoot(dp, cnt, seed=self.seed + 7 * det_index, photon_offset=n_total, select=idx)
+            else:
+                cum = torch.as_tensor(np.concatenate([[0], np.cumsum(cnt)]), device=dev)
+                sel = torch.as_tensor(idx, device=dev)
+                self.ctx.object_photons(dp.x, dp.y, dp.flux, dp.wavelength, d_ox[sel].contiguous(),
+                                        d_oy[sel].contiguous(), d_os[sel].contiguous(), cum, cdf, cdfw,
+                                        seed=self.seed + 7 * det_index, photon_offset=n_total)
             pool.process(dp, image, resume=(k > 0), recalc=(k > 0), fused=True)
             n_total += n
         sensor.read_image(image)

@@ -56,3 +56,41 @@ def test_detector_runner_conserves_photons():
     if 10 < cx < 4086 and 10 < cy < 3994:
         stamp = image.array[cy - 8:cy + 9, cx - 8:cx + 9]
         assert stamp.sum() > 0.7 * objs[2][k]
+
+
+def test_detector_runner_from_catalogue_rows_behind_the_atmosphere():
+    """Stage 1 (catalogue rows + atmospheric PSF) -> fused pooled step, all on the device."""
+    from imsim_b200.atmosphere import AtmosphericPSF
+    from imsim_b200.flat import wavelength_cdf
+    from imsim_b200.stage1 import ObjectTable
+    from imsim_b200.visit import DetectorRunner, synthetic_catalog
+
+    models = {"e2v": helpers.sensor_model("lsst_e2v_50_4"), "itl": helpers.sensor_model("lsst_itl_50_4")}
+    psf = AtmosphericPSF(1.2, 0.7, "r", rng=3, screen_size=102.4, screen_scale=0.1, device="cuda:0")
+    runner = DetectorRunner(0, models, helpers.absorption(), psf=psf)
+    wave = np.linspace(550, 690, 15)
+    seds = [wavelength_cdf(wave, 1.0 + 0.1 * k * (wave - 550) / 140) for k in range(8)]
+    cdf = (np.array([c for c, _ in seds]), np.array([w for _, w in seds]))
+    cat = synthetic_catalog(300, 4096, 4004, seed=2, total_photons=4e6)
+    rows, flux = cat.build()
+    assert set(np.unique(rows["kind"])) == {0, 2, 3} and len(cat) > 300
+    rec, image = runner.run("R22_S11", cat, nbatch=5, wavelength_cdf=cdf)
+    assert rec["photons"] == int(flux.sum())
+    assert 0.85 * rec["photons"] < rec["electrons"] <= rec["photons"]
+    # a bright star and a bright extended galaxy on an empty field: the galaxy image is wider
+    tab = ObjectTable()
+    tab.add_points([1000.0], [1000.0], [400000])
+    tab.add_sersic(3000.0, 2500.0, 400000, 1.5, 1.0, q=0.4, beta=0.3)
+    rec, image = runner.run("R22_S11", tab, nbatch=2, wavelength_cdf=cdf)
+
+    def width(cx, cy, h=40):
+        st = image.array[cy - h:cy + h + 1, cx - h:cx + h + 1].astype(np.float64)
+        yy, xx = np.mgrid[-h:h + 1, -h:h + 1]
+        mx, my = (st * xx).sum() / st.sum(), (st * yy).sum() / st.sum()
+        return np.sqrt((st * ((xx - mx) ** 2 + (yy - my) ** 2)).sum() / st.sum()), st.sum()
+
+    ws, fs = width(1000, 1000)
+    wg, fg = width(3000, 2500)
+    assert fs > 0.9 * 400000 * 0.95 and fg > 0.8 * 400000 * 0.95
+    # star: atmosphere 0.75'' FWHM + optics ~ 2-3 px rms; galaxy: exponential hlr 1.5'' = 7.5 px adds ~ 10 px rms
+    assert 1.0 < ws < 6.0 and wg > ws + 4.0
