@@ -773,25 +773,33 @@ extern "C" int b2_sensor_bind_image(b2_sensor* s, int32_t xmin, int32_t ymin, in
     b2_ctx* ctx = s->ctx;
     B2_CUDA(cudaSetDevice(ctx->device));
     DevSensor& d = s->d;
-    bool same = s->bound && d.nx == nx && d.ny == ny && d.dtype_bytes == dtype_bytes;
-    if (!same) {
+    // The per-image arrays are kept while the new image fits their capacity (per-object stamps of the
+    // classic pipeline rebind thousands of times with varying sizes); they only ever grow.
+    const int nv = d.nv;
+    const size_t nH = (size_t)(ny + 1) * nx * (nv + 2), nV = (size_t)ny * (nx + 1) * nv + nv;
+    const size_t npix = (size_t)nx * ny;
+    const size_t ntile = (size_t)((nx + B2_TILE - 1) / B2_TILE) * ((ny + B2_TILE - 1) / B2_TILE);
+    bool fits = s->bound && nH <= s->cap_H && nV <= s->cap_V && npix * 8 <= s->cap_pix_bytes && ntile <= s->cap_tiles;
+    if (!fits) {
         B2_CUDA(cudaStreamSynchronize(ctx->stream));
         free_list(s->image_owned);
-        const int nv = d.nv;
-        size_t nH = (size_t)(ny + 1) * nx * (nv + 2), nV = (size_t)ny * (nx + 1) * nv + nv;
-        size_t npix = (size_t)nx * ny;
+        s->cap_H = nH + nH / 4;
+        s->cap_V = nV + nV / 4;
+        const size_t cpix = npix + npix / 4;
+        s->cap_pix_bytes = cpix * 8;
+        s->cap_tiles = ntile + ntile / 4 + 1;
         void* p;
-        B2_CUDA(cudaMalloc(&p, nH * sizeof(float2))); s->image_owned.push_back(p); d.H = (float2*)p;
-        B2_CUDA(cudaMalloc(&p, nV * sizeof(float2))); s->image_owned.push_back(p); d.V = (float2*)p;
-        B2_CUDA(cudaMalloc(&p, npix * 4 * sizeof(double))); s->image_owned.push_back(p); d.inner = (double*)p;
-        B2_CUDA(cudaMalloc(&p, npix * 4 * sizeof(double))); s->image_owned.push_back(p); d.outer = (double*)p;
-        B2_CUDA(cudaMalloc(&p, npix * sizeof(double))); s->image_owned.push_back(p); d.delta = (double*)p;
-        B2_CUDA(cudaMalloc(&p, npix * dtype_bytes)); s->image_owned.push_back(p); d.target = p;
-        B2_CUDA(cudaMalloc(&p, npix)); s->image_owned.push_back(p); s->changed = (uint8_t*)p;
-        s->tnx = (nx + B2_TILE - 1) / B2_TILE;
-        s->tny = (ny + B2_TILE - 1) / B2_TILE;
-        B2_CUDA(cudaMalloc(&p, (size_t)s->tnx * s->tny)); s->image_owned.push_back(p); s->tiles = (uint8_t*)p;
+        B2_CUDA(cudaMalloc(&p, s->cap_H * sizeof(float2))); s->image_owned.push_back(p); d.H = (float2*)p;
+        B2_CUDA(cudaMalloc(&p, s->cap_V * sizeof(float2))); s->image_owned.push_back(p); d.V = (float2*)p;
+        B2_CUDA(cudaMalloc(&p, cpix * 4 * sizeof(double))); s->image_owned.push_back(p); d.inner = (double*)p;
+        B2_CUDA(cudaMalloc(&p, cpix * 4 * sizeof(double))); s->image_owned.push_back(p); d.outer = (double*)p;
+        B2_CUDA(cudaMalloc(&p, cpix * sizeof(double))); s->image_owned.push_back(p); d.delta = (double*)p;
+        B2_CUDA(cudaMalloc(&p, cpix * 8)); s->image_owned.push_back(p); d.target = p;  // float32 or float64 pixels
+        B2_CUDA(cudaMalloc(&p, cpix)); s->image_owned.push_back(p); s->changed = (uint8_t*)p;
+        B2_CUDA(cudaMalloc(&p, s->cap_tiles)); s->image_owned.push_back(p); s->tiles = (uint8_t*)p;
     }
+    s->tnx = (nx + B2_TILE - 1) / B2_TILE;
+    s->tny = (ny + B2_TILE - 1) / B2_TILE;
     d.xmin = xmin; d.ymin = ymin; d.nx = nx; d.ny = ny; d.dtype_bytes = dtype_bytes;
     size_t bytes = (size_t)nx * ny * dtype_bytes;
     if (pixels)

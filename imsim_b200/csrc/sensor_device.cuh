@@ -40,6 +40,7 @@ struct b2_sensor {
     unsigned long long* dstats = nullptr;  // device counters
     double* dadded = nullptr;
     Scratch cum;  // cumulative flux scratch
+    size_t cap_H = 0, cap_V = 0, cap_pix_bytes = 0, cap_tiles = 0;  // capacities of the per-image arrays
     Scratch slow;  // compact list of photons that need the full polygon / neighbour treatment
     unsigned long long* dnslow = nullptr;
 };

@@ -284,7 +284,7 @@ class PhotonPool:
         self.opt.seed = self.seed
 
     def process(self, dp: DevicePhotons, image, resume: bool, recalc: bool, sample=True, want_stats=False,
-                fused=None, write_back=False):
+                fused=None, write_back=False, prebound=False):
         """Run the chain on a device pool and accumulate onto the sensor's bound image.
 
         ``fused`` (default: whenever the sensor runs the pooled cadence ``nrecalc == 0``): one
@@ -304,7 +304,7 @@ class PhotonPool:
         dp._has.update(dxdz=True, dydz=True)
         self.offset += dp.n
         added = self.sensor.accumulate(dp, image, resume=resume, recalc=recalc, sync_image=False,
-                                       want_stats=want_stats)
+                                       want_stats=want_stats, prebound=prebound)
         return added, stats
 
     def _process_fused(self, dp, image, resume, recalc, want_stats, write_back):

@@ -314,8 +314,25 @@ class SiliconSensor:
                                                   _abi.B2_HOST))
         self._bound_shape = (ny, nx, arr.dtype)
 
+    def bind_stamp(self, xmin: int, ymin: int, nx: int, ny: int, dtype=np.float32):
+        """Bind an all-zero image of the given bounds that lives on the device only (per-object stamps of the
+        classic pipeline, imsim/stamp.py:562-572): no host array, no synchronisation.  Follow with
+        ``accumulate(..., image=<any token>, prebound=True)`` and ``snapshot_image``."""
+        _lib.check(self._lib.b2_sensor_bind_image(self._h, int(xmin), int(ymin), int(nx), int(ny),
+                                                  np.dtype(dtype).itemsize, None, _abi.B2_DEVICE))
+        self._bound_shape = (ny, nx, np.dtype(dtype))
+        self._last_image = None
+
+    def plain_accumulate_bound(self, photons):
+        """``sensor=None`` drawing (galsim.Sensor: bin by nominal pixel) onto the bound device image -- what the
+        reference does for objects below ``max_flux_simple`` (imsim/stamp.py:534-537,555-556)."""
+        added = C.c_double(0.0)
+        _lib.check(self._lib.b2_plain_accumulate(self._h, len(photons), _lib.ptr(photons.x), _lib.ptr(photons.y),
+                                                 _lib.ptr(photons.flux), _lib.where_of(photons.x), C.byref(added)))
+        return added.value
+
     def accumulate(self, photons, image, orig_center=None, resume=False, recalc=False, rand4=None,
-                   sync_image=True, want_stats=True):
+                   sync_image=True, want_stats=True, prebound=False):
         """Accumulate photons on the image; returns the flux that landed on it.
 
         ``photons``: a (GalSim or imsim_b200) ``PhotonArray`` on the host, or a
@@ -329,7 +346,7 @@ class SiliconSensor:
         n = photons.size() if hasattr(photons, 'size') and callable(photons.size) else len(photons)
         if n == 0:
             return 0.0
-        if not resume:
+        if not resume and not prebound:
             self._bind(image)
         x, y, flux = photons.x, photons.y, photons.flux
         where = _lib.where_of(x)
