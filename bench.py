@@ -254,7 +254,7 @@ def run_visit(args):
             objs = synthetic_catalog(20000, 4096, 4004, seed=dets.index(d), total_photons=costs[d])
         else:
             objs = synthetic_objects(20000, 4096, 4004, seed=dets.index(d), total_photons=costs[d])
-        rec, _ = runner.run(d, objs, nbatch=10, wavelength_cdf=cdf, det_index=dets.index(d))
+        rec, _ = runner.run(d, objs, nbatch=10, wavelength_cdf=cdf, det_index=dets.index(d), readout=args.visit_readout)
         recs.append(rec)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
@@ -266,6 +266,7 @@ def run_visit(args):
         photons = sum(r["photons"] for r in allrec)
         gpu_s = max(sum(r["gpu_ms"] for r in allrec if r["device"] == g) for g in range(world)) * 1e-3
         print(json.dumps({"mode": "visit", "stage1": "catalogue+atmosphere" if args.visit_catalog else "gaussian-points",
+                          "readout_on_device": bool(args.visit_readout),
                           "n_gpus": world, "ccds": len(allrec), "photons": photons,
                           "wall_s_max_rank": float(wt.item()), "gpu_s_max_rank": gpu_s,
                           "visits_per_hour_wall": 3600.0 / float(wt.item()),
@@ -303,6 +304,9 @@ def main():
                     help="extra mode (not the headline line): simulate a synthetic LSSTCam visit, 189 CCDs sharded "
                          "by detector over the ranks, --visit-photons per CCD; prints one JSON line")
     ap.add_argument("--visit-photons", type=float, default=1e8)
+    ap.add_argument("--visit-readout", action="store_true",
+                    help="with --visit: also run the electronics readout (bleed trails, dark current, crosstalk-free "
+                         "amp split, CTI, bias, read noise -> int32 segments) on the device for every CCD")
     ap.add_argument("--visit-catalog", action="store_true",
                     help="with --visit: stage 1 from catalogue rows (stars + bulge/disc/knots galaxies, per-object SEDs) "
                          "behind the atmospheric PSF (6 phase screens + second kick) instead of Gaussian point sources")

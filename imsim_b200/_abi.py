@@ -188,6 +188,15 @@ class B2Psf(C.Structure):
     ]
 
 
+class B2Amp(C.Structure):
+    _fields_ = [
+        ("x0", C.c_int32), ("y0", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32),
+        ("raw_nx", C.c_int32), ("raw_ny", C.c_int32), ("data_x0", C.c_int32), ("data_y0", C.c_int32),
+        ("flip_x", C.c_int32), ("flip_y", C.c_int32),
+        ("gain", C.c_double), ("bias_level", C.c_double), ("read_noise", C.c_double),
+    ]
+
+
 # numpy structured dtype with the layout of B2Object (object tables are built vectorised)
 import numpy as _np  # noqa: E402
 
@@ -199,5 +208,5 @@ assert OBJECT_DTYPE.itemsize == C.sizeof(B2Object)
 # order of b2_sizeof(which)
 SIZEOF_ORDER = [
     B2Telescope, B2Surface, B2TanSip, B2Detector, B2Diffraction, B2OpticsOptions,
-    B2OpticsStats, B2SensorConfig, B2AccumStats, B2Obsc, B2Medium, B2Object, B2Psf,
+    B2OpticsStats, B2SensorConfig, B2AccumStats, B2Obsc, B2Medium, B2Object, B2Psf, B2Amp,
 ]

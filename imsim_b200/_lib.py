@@ -16,7 +16,7 @@ import numpy as np
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SRC = [os.path.join(_HERE, "csrc", f) for f in ("abi.cu", "optics.cu", "sensor.cu", "pool.cu", "stage1.cu")]
+_SRC = [os.path.join(_HERE, "csrc", f) for f in ("abi.cu", "optics.cu", "sensor.cu", "pool.cu", "stage1.cu", "readout.cu")]
 _HDR = [os.path.join(_HERE, "csrc", f) for f in ("b2_common.cuh", "optics_device.cuh", "sensor_device.cuh")] + \
     [os.path.join(os.path.dirname(_HERE), "include", "imsim_b200.h")]
 SO_PATH = os.path.join(_HERE, "_build", "libimsim_b200.so")
@@ -97,6 +97,9 @@ _SIGNATURES = {
     "b2_radial_luts_upload": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_double]),
     "b2_stage1_photons": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int32, vp, vp, C.c_int32, C.c_int32, vp,
                                     C.c_uint64, C.c_uint64]),
+    "b2_bleed_trails": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int]),
+    "b2_readout": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.POINTER(_abi.B2Amp), C.c_int32, vp, vp, vp, C.c_int32,
+                             C.c_double, C.c_int32, C.c_double, C.c_uint64, vp, vp]),
     "b2_sensor_create": (C.c_int, [vp, C.POINTER(_abi.B2SensorConfig), vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
     "b2_sensor_destroy": (C.c_int, [vp]),
     "b2_sensor_set_treerings": (C.c_int, [vp, C.c_double, C.c_double, vp, vp, vp, C.c_int32]),

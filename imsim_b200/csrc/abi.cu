@@ -27,6 +27,7 @@ extern "C" int64_t b2_sizeof(int32_t which) {
         case 10: return sizeof(B2Medium);
         case 11: return sizeof(B2Object);
         case 12: return sizeof(B2Psf);
+        case 13: return sizeof(B2Amp);
     }
     return -1;
 }

@@ -97,6 +97,8 @@ class DetectorRunner:
         self.band, self.rot_tel_pos, self.exptime, self.seed = band, rot_tel_pos, exptime, seed
         self.dif = diffraction_config(latitude=RUBIN_LATITUDE, altitude=altitude, azimuth=azimuth)
         self._sensors: Dict[tuple, SiliconSensor] = {}
+        self._readouts: Dict[str, object] = {}
+        self.last_raw = None
         #: stage-1 PSF (``atmosphere.AtmosphericPSF`` / ``GaussianPSF``): one realisation per visit, shared by the
         #: detectors of this GPU like the reference's ``atm_psf`` input object (imsim/atmPSF.py:339-347)
         self.psf = psf
@@ -117,7 +119,8 @@ class DetectorRunner:
             s.set_treerings(func, center)
         return s
 
-    def run(self, det_name: str, objects, nbatch: int = 10, wavelength_cdf=None, det_index: int = 0) -> dict:
+    def run(self, det_name: str, objects, nbatch: int = 10, wavelength_cdf=None, det_index: int = 0,
+            readout: bool = False) -> dict:
         torch = self.torch
         dev = torch.device("cuda", self.device)
         t0 = time.perf_counter()
@@ -175,9 +178,26 @@ class DetectorRunner:
                                         seed=self.seed + 7 * det_index, photon_offset=n_total)
             pool.process(dp, image, resume=(k > 0), recalc=(k > 0), fused=True)
             n_total += n
+        raw = None
+        if readout:
+            # post-path on the device (imsim/readout.py:414-480): the e-image goes from the sensor's buffer to
+            # int32 amplifier segments without visiting the host; both are then copied back
+            from .readout import CcdReadout, lsstcam_like_amps
+
+            vendor = vendor_of(det_name)
+            ro = self._readouts.get(vendor)
+            if ro is None:
+                ro = self._readouts[vendor] = CcdReadout(self.ctx, lsstcam_like_amps(vendor), exptime=self.exptime,
+                                                         midline_stop=(vendor == "e2v"))
+            e = torch.empty((det.ny, det.nx), dtype=torch.float32, device=dev)
+            sensor.snapshot_image(e)
+            amp = lsstcam_like_amps(vendor)[0]
+            ex = e[: 2 * amp.ny, : 8 * amp.nx].contiguous() if (2 * amp.ny, 8 * amp.nx) != tuple(e.shape) else e
+            raw = ro.build_amp_images(ex, seed=self.seed + 13 * det_index).cpu().numpy()
         sensor.read_image(image)
         e1.record()
         torch.cuda.synchronize(dev)
+        self.last_raw = raw
         rec = {"det_name": det_name, "device": self.device, "photons": n_total, "nbatch": nbatch,
                "electrons": float(image.array.sum(dtype=np.float64)), "gpu_ms": float(e0.elapsed_time(e1)),
                "setup_ms": 1e3 * t_setup}

@@ -261,6 +261,22 @@ typedef struct {
     double arcsec_to_pix[4];      /* inverse local WCS Jacobian, row-major (one per pool: SURVEY Q2) */
 } B2Psf;
 
+/* ------------------------------------------------------------------ */
+/* Post-path electronics (readout)                                     */
+/* ------------------------------------------------------------------ */
+
+/* one amplifier segment (imsim/camera.py:19-92 Amp: bounds, raw_data_bounds, raw_bounds, gain, raw_flip_x/y,
+   bias_level, read_noise), 0-based pixel indices */
+typedef struct {
+    int32_t x0, y0, nx, ny;     /* imaging area of this amp in the e-image */
+    int32_t raw_nx, raw_ny;     /* full segment with prescan / overscan */
+    int32_t data_x0, data_y0;   /* position of the imaging area inside the raw segment */
+    int32_t flip_x, flip_y;     /* readout order flips */
+    double gain;                /* e- / ADU */
+    double bias_level;          /* ADU */
+    double read_noise;          /* ADU rms */
+} B2Amp;
+
 #ifndef B2_STRUCTS_ONLY /* (the oracle's FLOP counter re-reads only the POD structs above) */
 typedef struct b2_ctx b2_ctx;
 typedef struct b2_sensor b2_sensor;
@@ -368,6 +384,21 @@ int b2_radial_luts_upload(b2_ctx* ctx, const double* lut, int32_t n_lut, int32_t
 int b2_stage1_photons(b2_ctx* ctx, int64_t n, double* x, double* y, double* flux, double* wl, const B2Object* objects,
                       const int64_t* obj_cum, int32_t nobj, const double* cdf, const double* cdf_wave, int32_t n_sed,
                       int32_t ncdf, const double* rand, uint64_t seed, uint64_t photon_offset);
+
+/* imsim.bleed_trails.bleed_eimage (imsim/bleed_trails.py:26-60) on a float32 e-image [ny][nx], in place:
+   every channel (column; the two halves separately if midline_stop, e2v sensors, readout.py:427-431) spills
+   the charge above full_well alternately down and up the column.  Bit-identical to the reference. */
+int b2_bleed_trails(b2_ctx* ctx, float* eimage, int32_t nx, int32_t ny, double full_well, int32_t midline_stop,
+                    int where);
+/* CcdReadout.build_amp_images (imsim/readout.py:414-480) on a DEVICE e-image (modified in place by the bleed
+   trails, if full_well > 0, and the dark current, if dark_mean > 0): amp split / gain / flips, crosstalk
+   (xtalk: HOST namp x namp or NULL, readout.py:403-412), prescan / overscan, CTI (pband / sband: HOST band
+   form of cte_matrix, [raw_ny or raw_nx][ntransfers + 1], band[i][k] = matrix[i][i - k], or NULL;
+   readout.py:153-203,391-401), then bias + read noise -> int32.  segments (DEVICE float32 [namp][raw_ny][raw_nx],
+   before bias / noise) and raw (DEVICE int32, same shape) are optional outputs. */
+int b2_readout(b2_ctx* ctx, float* eimage, int32_t nx, int32_t ny, const B2Amp* amps, int32_t namp, const double* xtalk,
+               const double* pband, const double* sband, int32_t ntransfers, double full_well, int32_t midline_stop,
+               double dark_mean, uint64_t seed, float* segments, int32_t* raw);
 
 /* ---- silicon sensor ---------------------------------------------------- */
 /* replaces galsim.SiliconSensor.__init__ (imsim/lsst_image.py:93-103,

@@ -48,6 +48,17 @@ def test_detector_runner_conserves_photons():
     wave = np.linspace(550, 690, 15)
     rec, image = runner.run("R22_S11", objs, nbatch=10, wavelength_cdf=wavelength_cdf(wave, np.ones_like(wave)))
     assert rec["photons"] == int(objs[2].sum()) and rec["nbatch"] == 10
+    # same detector again with the electronics readout on the device: 16 int32 segments carrying the e-image
+    rec2, image2 = runner.run("R22_S11", objs, nbatch=10, wavelength_cdf=wavelength_cdf(wave, np.ones_like(wave)),
+                              readout=True)
+    raw = runner.last_raw
+    assert raw.shape == (16, 2048, 576) and raw.dtype == np.int32
+    npix = 16 * 2002 * 512
+    adu = (raw[:, :2002, 10:522].astype(np.float64) - 1000.0).sum()  # bias 1000 ADU
+    # gain 1.5 e-/ADU, dark current 0.02 e-/s x 32 s per pixel, truncation to int loses 0.5 ADU per pixel on
+    # average; read noise (5 ADU rms) and the charge deferred into the overscan by the CTI stay within 1e5 ADU
+    want = (image2.array[:4004].sum(dtype=np.float64) + 0.64 * npix) / 1.5 - 0.5 * npix
+    assert abs(adu - want) < 1.0e5, (adu, want)
     # r-band photons: nearly all convert; a few are vignetted or fall off the chip near the edges
     assert 0.9 * rec["photons"] < rec["electrons"] <= rec["photons"]
     # the brightest object shows up where it was put (optics keep photons within a few pixels)

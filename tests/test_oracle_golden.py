@@ -7,6 +7,8 @@ fix for this path:
   * tests/test_photon_ops.py:668-691 ray->pixel golden vector,
   * doc/validation/diffusion.rst diffusion-step formula evaluated on the sensor cfgs.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -176,3 +178,36 @@ def test_sensor_table_layout():
     th_file = np.where(th_file > np.pi, th_file - 2 * np.pi, th_file)
     np.testing.assert_allclose(th, th_file, atol=2e-3)
     np.testing.assert_allclose(bounds, [0, 1, 0, 1, 0, 1, 0, 1], atol=1e-7)
+
+
+def test_readout_oracle_matches_the_reference_functions():
+    """oracle/readout.py against outputs of the reference's own bleed_eimage / cte_matrix / apply_cte /
+    apply_crosstalk (tests/golden/make_golden_readout.py): bit-exact."""
+    from oracle import readout as R
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "readout.npz"))
+    for tag in "ab":
+        fw = float(g["bleed_fw_" + tag])
+        for mode, ms in (("mid", True), ("nomid", False)):
+            out = R.bleed_eimage(g["bleed_in_" + tag], fw, ms)
+            ref = g["bleed_%s_%s" % (mode, tag)]
+            assert np.array_equal(out, ref)
+            assert (ref != g["bleed_in_" + tag]).sum() > 500 and ref.max() <= np.float32(fw) * (1 + 2e-7)
+    band = R.cte_band(40, 1e-3)
+    M = g["cte_matrix_40_1e-3"]
+    for i in range(40):
+        for k in range(21):
+            if i - k >= 0:
+                assert band[i, k] == M[i, i - k]
+    assert np.array_equal(R.cte_band(64, 1e-6)[63, :21], g["cte_matrix_64_1e-6_band"][:21])
+    assert np.all(g["cte_matrix_64_1e-6_band"][21:] == 0)  # ntransfers = 20
+    for tag in ("both", "p_only", "s_only"):
+        p, s = g["cte_%s_cti" % tag]
+        out = np.array(R.apply_cte(list(g["amps_in"]), p, s))
+        assert np.array_equal(out, g["cte_" + tag])
+    out = np.array(R.apply_crosstalk(list(g["amps_in"]), g["xtalk"]))
+    assert np.array_equal(out, g["xtalk_out"])
+    # the product's band builder is the same arithmetic
+    from imsim_b200.readout import cte_band
+
+    assert np.array_equal(cte_band(40, 1e-3), band)
