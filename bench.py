@@ -254,7 +254,8 @@ def run_visit(args):
             objs = synthetic_catalog(20000, 4096, 4004, seed=dets.index(d), total_photons=costs[d])
         else:
             objs = synthetic_objects(20000, 4096, 4004, seed=dets.index(d), total_photons=costs[d])
-        rec, _ = runner.run(d, objs, nbatch=10, wavelength_cdf=cdf, det_index=dets.index(d), readout=args.visit_readout)
+        rec, _ = runner.run(d, objs, nbatch=10, wavelength_cdf=cdf, det_index=dets.index(d), readout=args.visit_readout,
+                            sky_level=args.visit_sky)
         recs.append(rec)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
@@ -266,7 +267,7 @@ def run_visit(args):
         photons = sum(r["photons"] for r in allrec)
         gpu_s = max(sum(r["gpu_ms"] for r in allrec if r["device"] == g) for g in range(world)) * 1e-3
         print(json.dumps({"mode": "visit", "stage1": "catalogue+atmosphere" if args.visit_catalog else "gaussian-points",
-                          "readout_on_device": bool(args.visit_readout),
+                          "readout_on_device": bool(args.visit_readout), "sky_level": args.visit_sky,
                           "n_gpus": world, "ccds": len(allrec), "photons": photons,
                           "wall_s_max_rank": float(wt.item()), "gpu_s_max_rank": gpu_s,
                           "visits_per_hour_wall": 3600.0 / float(wt.item()),
@@ -304,6 +305,9 @@ def main():
                     help="extra mode (not the headline line): simulate a synthetic LSSTCam visit, 189 CCDs sharded "
                          "by detector over the ranks, --visit-photons per CCD; prints one JSON line")
     ap.add_argument("--visit-photons", type=float, default=1e8)
+    ap.add_argument("--visit-sky", type=float, default=0.0,
+                    help="with --visit: sky level [e-/pixel] added through the sensor's pixel areas with exact Poisson "
+                         "noise on the device (a 30 s r-band dark sky is ~ 800)")
     ap.add_argument("--visit-readout", action="store_true",
                     help="with --visit: also run the electronics readout (bleed trails, dark current, crosstalk-free "
                          "amp split, CTI, bias, read noise -> int32 segments) on the device for every CCD")

@@ -519,11 +519,16 @@ __device__ __forceinline__ void surface_step(const DevSurf& s, const int kind, c
     if (interact == B2_INT_MIRROR || interact == B2_INT_REFRACT) {
         // un-normalised normal N = (-Zx, -Zy, g): the surface gradient scaled by g = R - k1 zc, so the
         // conic part grad F = (x, y, k1 z - R) needs no division; the departure gradient is scaled to match
-        double g = 1.0, Zx = 2.0 * gP * px + Ex, Zy = 2.0 * gP * py + Ey;
+        const bool departs = (kind == B2_SURF_ASPHERE || extra_kind != B2_EXTRA_NONE);
+        double g = 1.0, Zx = 0.0, Zy = 0.0;
+        if (departs) {
+            Zx = 2.0 * gP * px + Ex;
+            Zy = 2.0 * gP * py + Ey;
+        }
         if (curved) {
             g = s.R - s.k1 * zc;
-            Zx = Zx * g + px;
-            Zy = Zy * g + py;
+            Zx = departs ? Zx * g + px : px;  // a pure conic needs no multiplication at all
+            Zy = departs ? Zy * g + py : py;
         }
         double NN = g * g + Zx * Zx + Zy * Zy;
         double iNN = b2rcp(NN);

@@ -115,6 +115,72 @@ extern "C" int b2_bleed_trails(b2_ctx* ctx, float* eimage, int32_t nx, int32_t n
     return 0;
 }
 
+// ------------------------------------------------------------------ Poisson deviates
+// Exact Poisson sampler, counter based: inversion by sequential search below a mean of 30, Hoermann's
+// transformed rejection (PTRS, 1993 -- the algorithm behind numpy's and, via boost, GalSim's large-mean
+// generators) above.  Uniforms come from Philox(seed, index, stream) with the rejection round in the
+// high counter word, so a pixel's deviate depends only on (seed, pixel index).
+__device__ __forceinline__ double poisson_exact(double lam, uint64_t seed, uint64_t index, uint32_t stream) {
+    if (!(lam > 0.0)) return 0.0;
+    uint32_t r[4];
+    if (lam < 30.0) {
+        philox4(seed, index, stream, r);
+        const double u = u01(r[0], r[1]);
+        double p = exp(-lam), cdf = p;
+        int k = 0;
+        while (u > cdf && k < 400) {
+            ++k;
+            p *= lam / (double)k;
+            cdf += p;
+        }
+        return (double)k;
+    }
+    const double slam = sqrt(lam), loglam = log(lam);
+    const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+    const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (uint32_t round = 0; round < 64; ++round) {
+        philox4(seed ^ ((uint64_t)round << 40), index, stream + 1u, r);
+        const double U = u01(r[0], r[1]) - 0.5, V = u01(r[2], r[3]);
+        const double us = 0.5 - fabs(U);
+        const double k = floor((2.0 * a / us + b) * U + lam + 0.43);
+        if (us >= 0.07 && V <= vr) return k;
+        if (k < 0.0 || (us < 0.013 && V > us)) continue;
+        if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -lam + k * loglam - lgamma(k + 1.0)) return k;
+    }
+    return rint(lam);  // 64 rejections in a row: probability ~ 1e-60
+}
+
+// image += Poisson(sky_level * area * modulation): LSST_ImageBuilderBase.addNoise (imsim/lsst_image.py:128-199:
+// "image += sky", sky optionally multiplied by gradient / vignetting / fringing maps) followed by the config
+// CCD-noise builder, which for photon-shot images only has the sky's shot noise left to add; `areas` are the
+// tree-ring / brighter-fatter pixel areas of sensor.calculate_pixel_areas when the sky is drawn through the
+// sensor model (config/imsim-config.yaml:222-228).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_add_sky(T* __restrict__ image, size_t n, double sky_level, const double* __restrict__ areas,
+          const float* __restrict__ modulation, uint64_t seed) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double mean = sky_level;
+    if (areas) mean *= areas[i];
+    if (modulation) mean *= (double)modulation[i];
+    image[i] = (T)((double)image[i] + poisson_exact(mean, seed, (uint64_t)i, 22u));
+}
+
+extern "C" int b2_add_sky(b2_ctx* ctx, void* image, int32_t dtype_bytes, int64_t npix, double sky_level,
+                          const double* areas, const float* modulation, uint64_t seed) {
+    B2_REQUIRE(ctx && image && npix > 0, "b2_add_sky: bad argument");
+    B2_REQUIRE(dtype_bytes == 4 || dtype_bytes == 8, "b2_add_sky: image must be float32 or float64");
+    B2_REQUIRE(sky_level >= 0.0, "b2_add_sky: negative sky level");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    B2_TIMED("k_add_sky", ctx->stream);
+    unsigned nb = (unsigned)((npix + 255) / 256);
+    if (dtype_bytes == 4) k_add_sky<float><<<nb, 256, 0, ctx->stream>>>((float*)image, (size_t)npix, sky_level, areas, modulation, seed);
+    else k_add_sky<double><<<nb, 256, 0, ctx->stream>>>((double*)image, (size_t)npix, sky_level, areas, modulation, seed);
+    B2_CHECK_LAUNCH();
+    return 0;
+}
+
 // ------------------------------------------------------------------ readout
 // small-mean Poisson by inversion (dark current: 0.02 e-/s x 32 s), Gaussian approximation above 64
 __device__ __forceinline__ double poisson_draw(double mean, double u, double g) {

@@ -98,10 +98,17 @@ class DetectorRunner:
         self.dif = diffraction_config(latitude=RUBIN_LATITUDE, altitude=altitude, azimuth=azimuth)
         self._sensors: Dict[tuple, SiliconSensor] = {}
         self._readouts: Dict[str, object] = {}
+        self._pin: Dict[tuple, object] = {}
         self.last_raw = None
         #: stage-1 PSF (``atmosphere.AtmosphericPSF`` / ``GaussianPSF``): one realisation per visit, shared by the
         #: detectors of this GPU like the reference's ``atm_psf`` input object (imsim/atmPSF.py:339-347)
         self.psf = psf
+
+    def _pinned(self, key, shape, dtype):
+        t = self._pin.get((key, shape))
+        if t is None:
+            t = self._pin[(key, shape)] = self.torch.empty(shape, dtype=dtype).pin_memory()
+        return t
 
     def sensor_for(self, det_name: str) -> SiliconSensor:
         """One sensor object per vendor model, re-used across detectors: only the tree-ring table
@@ -120,7 +127,7 @@ class DetectorRunner:
         return s
 
     def run(self, det_name: str, objects, nbatch: int = 10, wavelength_cdf=None, det_index: int = 0,
-            readout: bool = False) -> dict:
+            readout: bool = False, sky_level: float = 0.0) -> dict:
         torch = self.torch
         dev = torch.device("cuda", self.device)
         t0 = time.perf_counter()
@@ -131,7 +138,9 @@ class DetectorRunner:
         self.ctx.set_detector(su.detector)
         self.ctx.set_diffraction(self.dif)
         sensor = self.sensor_for(det_name)
-        image = Image(np.zeros((det.ny, det.nx), np.float32), 0, 0)
+        # the returned e-image (and raw segments) live in pinned buffers of the runner, reused by the next run()
+        image = Image(self._pinned("img", (det.ny, det.nx), torch.float32).numpy(), 0, 0)
+        image.array[:, :] = 0.0
         pool = PhotonPool(self.ctx, sensor, exptime=self.exptime, seed=self.seed + 1000 * det_index)
         gen = np.random.default_rng(self.seed + det_index)
         catalogue = not (isinstance(objects, tuple) and len(objects) == 4)
@@ -179,6 +188,16 @@ class DetectorRunner:
             pool.process(dp, image, resume=(k > 0), recalc=(k > 0), fused=True)
             n_total += n
         raw = None
+        e = torch.empty((det.ny, det.nx), dtype=torch.float32, device=dev)
+        sensor.snapshot_image(e)
+        electrons = e.sum(dtype=torch.float64)  # collected source charge, before sky / dark current
+        if sky_level > 0.0:
+            # sky background through the sensor model (imsim/lsst_image.py:128-199): level x pixel areas (tree
+            # rings + the accumulated charge), exact Poisson noise, all on the device
+            from .sky import add_sky, pixel_areas_device
+
+            areas = pixel_areas_device(sensor, use_flux=True)
+            add_sky(self.ctx, e, sky_level, seed=self.seed + 17 * det_index, areas=areas)
         if readout:
             # post-path on the device (imsim/readout.py:414-480): the e-image goes from the sensor's buffer to
             # int32 amplifier segments without visiting the host; both are then copied back
@@ -189,16 +208,18 @@ class DetectorRunner:
             if ro is None:
                 ro = self._readouts[vendor] = CcdReadout(self.ctx, lsstcam_like_amps(vendor), exptime=self.exptime,
                                                          midline_stop=(vendor == "e2v"))
-            e = torch.empty((det.ny, det.nx), dtype=torch.float32, device=dev)
-            sensor.snapshot_image(e)
             amp = lsstcam_like_amps(vendor)[0]
             ex = e[: 2 * amp.ny, : 8 * amp.nx].contiguous() if (2 * amp.ny, 8 * amp.nx) != tuple(e.shape) else e
-            raw = ro.build_amp_images(ex, seed=self.seed + 13 * det_index).cpu().numpy()
-        sensor.read_image(image)
+            draw = ro.build_amp_images(ex, seed=self.seed + 13 * det_index)
+            praw = self._pinned("raw", tuple(draw.shape), torch.int32)
+            praw.copy_(draw, non_blocking=True)
+            raw = praw.numpy()
+        # with the readout, e is the e-image after bleed trails and dark current, like CcdReadout.eimage
+        self._pinned("img", (det.ny, det.nx), torch.float32).copy_(e, non_blocking=True)
         e1.record()
         torch.cuda.synchronize(dev)
         self.last_raw = raw
         rec = {"det_name": det_name, "device": self.device, "photons": n_total, "nbatch": nbatch,
-               "electrons": float(image.array.sum(dtype=np.float64)), "gpu_ms": float(e0.elapsed_time(e1)),
+               "electrons": float(electrons.item()), "gpu_ms": float(e0.elapsed_time(e1)),
                "setup_ms": 1e3 * t_setup}
         return rec, image

@@ -399,6 +399,12 @@ int b2_bleed_trails(b2_ctx* ctx, float* eimage, int32_t nx, int32_t ny, double f
 int b2_readout(b2_ctx* ctx, float* eimage, int32_t nx, int32_t ny, const B2Amp* amps, int32_t namp, const double* xtalk,
                const double* pband, const double* sband, int32_t ntransfers, double full_well, int32_t midline_stop,
                double dark_mean, uint64_t seed, float* segments, int32_t* raw);
+/* LSST_ImageBuilderBase.addNoise (imsim/lsst_image.py:128-199) for a photon-shot e-image on the DEVICE:
+   image[i] += Poisson(sky_level * areas[i] * modulation[i]) with exact Poisson deviates (Philox).  areas: DEVICE
+   float64 pixel areas from b2_sensor_pixel_areas (tree rings / brighter-fatter) or NULL; modulation: DEVICE
+   float32 map (sky gradient x vignetting x fringing) or NULL. */
+int b2_add_sky(b2_ctx* ctx, void* image, int32_t dtype_bytes, int64_t npix, double sky_level, const double* areas,
+               const float* modulation, uint64_t seed);
 
 /* ---- silicon sensor ---------------------------------------------------- */
 /* replaces galsim.SiliconSensor.__init__ (imsim/lsst_image.py:93-103,

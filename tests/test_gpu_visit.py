@@ -55,9 +55,11 @@ def test_detector_runner_conserves_photons():
     assert raw.shape == (16, 2048, 576) and raw.dtype == np.int32
     npix = 16 * 2002 * 512
     adu = (raw[:, :2002, 10:522].astype(np.float64) - 1000.0).sum()  # bias 1000 ADU
-    # gain 1.5 e-/ADU, dark current 0.02 e-/s x 32 s per pixel, truncation to int loses 0.5 ADU per pixel on
-    # average; read noise (5 ADU rms) and the charge deferred into the overscan by the CTI stay within 1e5 ADU
-    want = (image2.array[:4004].sum(dtype=np.float64) + 0.64 * npix) / 1.5 - 0.5 * npix
+    # the returned e-image is the one the readout digitised (after bleed trails and the dark current, 0.02 e-/s x
+    # 32 s per pixel); gain 1.5 e-/ADU, truncation to int loses 0.5 ADU per pixel on average; read noise (5 ADU
+    # rms) and the charge deferred into the overscan by the CTI stay within 1e5 ADU
+    assert abs(image2.array.sum(dtype=np.float64) - (rec2["electrons"] + 0.64 * npix)) < 0.002 * 0.64 * npix
+    want = image2.array[:4004].sum(dtype=np.float64) / 1.5 - 0.5 * npix
     assert abs(adu - want) < 1.0e5, (adu, want)
     # r-band photons: nearly all convert; a few are vignetted or fall off the chip near the edges
     assert 0.9 * rec["photons"] < rec["electrons"] <= rec["photons"]
