@@ -168,7 +168,7 @@ class B2Object(C.Structure):
         ("x", C.c_double), ("y", C.c_double),
         ("m", C.c_double * 4),
         ("p0", C.c_double), ("p1", C.c_double),
-        ("thx", C.c_double), ("thy", C.c_double),
+        ("tanx", C.c_double), ("tany", C.c_double),
         ("knot_seed", C.c_uint64),
     ]
 
@@ -201,7 +201,7 @@ class B2Amp(C.Structure):
 import numpy as _np  # noqa: E402
 
 OBJECT_DTYPE = _np.dtype([("kind", "<i4"), ("sed", "<i4"), ("lut", "<i4"), ("n_knots", "<i4"), ("x", "<f8"), ("y", "<f8"),
-                          ("m", "<f8", (4,)), ("p0", "<f8"), ("p1", "<f8"), ("thx", "<f8"), ("thy", "<f8"),
+                          ("m", "<f8", (4,)), ("p0", "<f8"), ("p1", "<f8"), ("tanx", "<f8"), ("tany", "<f8"),
                           ("knot_seed", "<u8")])
 assert OBJECT_DTYPE.itemsize == C.sizeof(B2Object)
 

@@ -78,6 +78,23 @@ __device__ __forceinline__ void screen_gradient(const T* __restrict__ tab, int n
     gy = ((f01 - f00) * (1.0 - fx) + (f11 - f10) * fx) * inv_scale;
 }
 
+// quad-packed float32 screens: one 16-byte load holds the four corners of the cell
+__device__ __forceinline__ void screen_gradient_quads(const float4* __restrict__ tab, int npix, double inv_scale, double X,
+                                                      double Y, double& gx, double& gy) {
+    double ax = X * inv_scale, ay = Y * inv_scale;
+    double fx0 = floor(ax), fy0 = floor(ay);
+    double fx = ax - fx0, fy = ay - fy0;
+    double np_d = (double)npix;
+    int ix0 = (int)(fx0 - np_d * floor(fx0 / np_d));
+    int iy0 = (int)(fy0 - np_d * floor(fy0 / np_d));
+    ix0 = min(max(ix0, 0), npix - 1);
+    iy0 = min(max(iy0, 0), npix - 1);
+    const float4 q = __ldg(tab + (size_t)iy0 * npix + ix0);
+    const double f00 = (double)q.x, f10 = (double)q.y, f01 = (double)q.z, f11 = (double)q.w;
+    gx = ((f10 - f00) * (1.0 - fy) + (f11 - f01) * fy) * inv_scale;
+    gy = ((f01 - f00) * (1.0 - fx) + (f11 - f10) * fx) * inv_scale;
+}
+
 __global__ void __launch_bounds__(256)
 k_stage1_photons(const __grid_constant__ DevStage1 s, int64_t n, double* __restrict__ x, double* __restrict__ y,
                  double* __restrict__ flux, double* __restrict__ wl, const B2Object* __restrict__ objects,
@@ -179,20 +196,21 @@ k_stage1_photons(const __grid_constant__ DevStage1 s, int64_t n, double* __restr
         sincospi(2.0 * r[5], &sn, &cs);
         double pu = rr * cs, pv = rr * sn;
         double t = s.psf.t0 + s.psf.exptime * r[6];
-        double tx = tan(ob.thx), ty = tan(ob.thy);
+        const double tx = ob.tanx, ty = ob.tany;
         double gx = 0.0, gy = 0.0;
         const double inv_scale = 1.0 / s.psf.screen_scale;
         for (int l = 0; l < s.psf.n_screens; ++l) {
             double X = pu - s.psf.vx[l] * t + s.psf.altitude[l] * tx;
             double Y = pv - s.psf.vy[l] * t + s.psf.altitude[l] * ty;
             double ax, ay;
-            if (s.psf.screen_f32) screen_gradient((const float*)s.screens[l], s.psf.npix, inv_scale, X, Y, ax, ay);
+            if (s.psf.screen_f32 == 2) screen_gradient_quads((const float4*)s.screens[l], s.psf.npix, inv_scale, X, Y, ax, ay);
+            else if (s.psf.screen_f32 == 1) screen_gradient((const float*)s.screens[l], s.psf.npix, inv_scale, X, Y, ax, ay);
             else screen_gradient((const double*)s.screens[l], s.psf.npix, inv_scale, X, Y, ax, ay);
             gx += ax;
             gy += ay;
         }
         // wavefront gradient [nm / m] -> angle; chromatic dilation of the atmospheric part
-        double chrom = (ncdf >= 2 && s.psf.exponent != 0.0) ? pow(wave / s.psf.base_wavelength, s.psf.exponent) : 1.0;
+        double chrom = (ncdf >= 2 && s.psf.exponent != 0.0) ? exp(s.psf.exponent * log(wave / s.psf.base_wavelength)) : 1.0;
         double sc = 1e-9 * ARCSEC_PER_RAD * chrom;
         kx += gx * sc;
         ky += gy * sc;

@@ -82,24 +82,24 @@ class ObjectTable:
             self.sersic_n.append(n)
         return self.sersic_n.index(n)
 
-    def _push(self, r, flux, x, y, sed, thx, thy):
-        r["x"], r["y"], r["sed"], r["thx"], r["thy"] = x, y, sed, thx, thy
+    def _push(self, r, flux, x, y, sed, tanx, tany):
+        r["x"], r["y"], r["sed"], r["tanx"], r["tany"] = x, y, sed, tanx, tany
         self.rows.append(r)
         self.flux.append(np.broadcast_to(np.asarray(flux, dtype=np.float64), r.shape).copy())
 
-    def add_points(self, x, y, flux, sed=0, thx=0.0, thy=0.0):
+    def add_points(self, x, y, flux, sed=0, tanx=0.0, tany=0.0):
         """``galsim.DeltaFunction`` (stars)."""
         x = np.atleast_1d(np.asarray(x, float))
         r = self._new(x.size)
         r["kind"] = _abi.PROF_DELTA
-        self._push(r, flux, x, y, sed, thx, thy)
+        self._push(r, flux, x, y, sed, tanx, tany)
 
-    def add_gaussians(self, x, y, flux, sigma_arcsec, sed=0, thx=0.0, thy=0.0):
+    def add_gaussians(self, x, y, flux, sigma_arcsec, sed=0, tanx=0.0, tany=0.0):
         x = np.atleast_1d(np.asarray(x, float))
         r = self._new(x.size)
         r["kind"] = _abi.PROF_GAUSSIAN
         r["m"] = (np.asarray(sigma_arcsec, float).reshape(-1, 1, 1) * self.arcsec_to_pix).reshape(-1, 4)
-        self._push(r, flux, x, y, sed, thx, thy)
+        self._push(r, flux, x, y, sed, tanx, tany)
 
     def _galaxy_matrix(self, hlr, q, beta, g1, g2, mu):
         """arcsec_to_pix @ lens(g1, g2, mu) @ shear(q, beta) * hlr, vectorised over objects -> (N, 4)."""
@@ -112,7 +112,7 @@ class ObjectTable:
         M = np.einsum("ij,jkn,kln->nil", self.arcsec_to_pix, L, S) * hlr[:, None, None]
         return M.reshape(-1, 4)
 
-    def add_sersic(self, x, y, flux, hlr_arcsec, n, q=1.0, beta=0.0, g1=0.0, g2=0.0, mu=1.0, sed=0, thx=0.0, thy=0.0):
+    def add_sersic(self, x, y, flux, hlr_arcsec, n, q=1.0, beta=0.0, g1=0.0, g2=0.0, mu=1.0, sed=0, tanx=0.0, tany=0.0):
         """``Sersic(n, half_light_radius)._shear(Shear(q, beta))._lens(g1, g2, mu)`` (instcat.py:496-520);
         scalars or arrays (one Sersic index per call)."""
         m = self._galaxy_matrix(hlr_arcsec, q, beta, g1, g2, mu)
@@ -120,10 +120,10 @@ class ObjectTable:
         r["kind"] = _abi.PROF_RADIAL
         r["lut"] = self._lut_row(n)
         r["m"] = m
-        self._push(r, flux, x, y, sed, thx, thy)
+        self._push(r, flux, x, y, sed, tanx, tany)
 
     def add_knots(self, x, y, flux, hlr_arcsec, npoints, q=1.0, beta=0.0, g1=0.0, g2=0.0, mu=1.0, sed=0, seed=0,
-                  thx=0.0, thy=0.0):
+                  tanx=0.0, tany=0.0):
         """``RandomKnots(npoints, half_light_radius)`` sheared and lensed (instcat.py:522-545); scalars or arrays."""
         m = self._galaxy_matrix(hlr_arcsec, q, beta, g1, g2, mu)
         r = self._new(max(m.shape[0], np.atleast_1d(x).size))
@@ -131,16 +131,16 @@ class ObjectTable:
         r["n_knots"] = npoints
         r["knot_seed"] = np.asarray(seed, dtype=np.uint64)
         r["m"] = m
-        self._push(r, flux, x, y, sed, thx, thy)
+        self._push(r, flux, x, y, sed, tanx, tany)
 
-    def add_streak(self, x, y, flux, length_arcsec, width_arcsec, position_angle=0.0, sed=0, thx=0.0, thy=0.0):
+    def add_streak(self, x, y, flux, length_arcsec, width_arcsec, position_angle=0.0, sed=0, tanx=0.0, tany=0.0):
         """``Box(length, width).rotate(position_angle)`` (instcat.py:486-494)."""
         r = self._new(1)
         r["kind"] = _abi.PROF_BOX
         r["p0"], r["p1"] = length_arcsec, width_arcsec
         c, s = np.cos(position_angle), np.sin(position_angle)
         r["m"] = (self.arcsec_to_pix @ np.array([[c, -s], [s, c]])).ravel()
-        self._push(r, flux, x, y, sed, thx, thy)
+        self._push(r, flux, x, y, sed, tanx, tany)
 
     # ------------------------------------------------------------------
     def build(self):
@@ -202,7 +202,7 @@ def read_instcat_objects(file_name: str, flip_g2: bool = True, skip_invalid: boo
 
 
 def add_instcat_object(table: ObjectTable, obj: InstCatObject, x: float, y: float, flux: float, sed: int = 0,
-                       flip_g2: bool = True, knot_seed: int = 0, thx: float = 0.0, thy: float = 0.0) -> bool:
+                       flip_g2: bool = True, knot_seed: int = 0, tanx: float = 0.0, tany: float = 0.0) -> bool:
     """``InstCatalog.getObj`` (imsim/instcat.py:465-561) for one catalogue entry placed at image position
     (x, y) with ``flux`` photons.  Returns False for entries the reference skips (magnorm >= 50) and raises
     for FITS-image sources (``InterpolatedImage``), which stage 1 does not generate on the device."""
@@ -211,9 +211,9 @@ def add_instcat_object(table: ObjectTable, obj: InstCatObject, x: float, y: floa
     if obj.magnorm >= 50:
         return False
     if kind == "point":
-        table.add_points(x, y, flux, sed=sed, thx=thx, thy=thy)
+        table.add_points(x, y, flux, sed=sed, tanx=tanx, tany=tany)
     elif kind == "streak":
-        table.add_streak(x, y, flux, float(p[1]), float(p[2]), np.radians(float(p[3])), sed=sed, thx=thx, thy=thy)
+        table.add_streak(x, y, flux, float(p[1]), float(p[2]), np.radians(float(p[3])), sed=sed, tanx=tanx, tany=tany)
     elif kind in ("sersic2d", "knots"):
         a, b, pa = float(p[1]), float(p[2]), float(p[3])
         assert a >= b
@@ -221,11 +221,11 @@ def add_instcat_object(table: ObjectTable, obj: InstCatObject, x: float, y: floa
         hlr = (a * b) ** 0.5
         g1, g2, mu = lens_params(*obj.lens)
         if kind == "sersic2d":
-            table.add_sersic(x, y, flux, hlr, float(p[4]), q=b / a, beta=beta, g1=g1, g2=g2, mu=mu, sed=sed, thx=thx,
-                             thy=thy)
+            table.add_sersic(x, y, flux, hlr, float(p[4]), q=b / a, beta=beta, g1=g1, g2=g2, mu=mu, sed=sed, tanx=tanx,
+                             tany=tany)
         else:
             table.add_knots(x, y, flux, hlr, int(p[4]), q=b / a, beta=beta, g1=g1, g2=g2, mu=mu, sed=sed, seed=knot_seed,
-                            thx=thx, thy=thy)
+                            tanx=tanx, tany=tany)
     else:
         raise RuntimeError("Do not know how to handle object type on the device: %s" % p[0])
     return True

@@ -152,7 +152,7 @@ class DetectorRunner:
             rows, oflux = objects.build()
             rows = rows.copy()
             vx, vy, vz = self.ctx.xy_to_v(np.ascontiguousarray(rows["x"]), np.ascontiguousarray(rows["y"]))
-            rows["thx"], rows["thy"] = np.arctan2(vx, -vz), np.arctan2(vy, -vz)
+            rows["tanx"], rows["tany"] = vx / -vz, vy / -vz  # tangents of the field angle
             cdf_np, cdfw_np = wavelength_cdf if wavelength_cdf is not None else (None, None)
             stage1 = Stage1(self.ctx, rows, cdf_np, cdfw_np, objects.radial_tables())
             if self.psf is not None:

@@ -235,7 +235,7 @@ typedef struct {
     double m[4];      /* unit-profile offset -> pixels, row-major: size x shear(q, beta) x lens(g1, g2, mu) x
                          local WCS (arcsec -> px) */
     double p0, p1;    /* BOX: length, width in the units m maps from */
-    double thx, thy;  /* field angle of the object [rad] (atmospheric screens are offset by altitude * tan) */
+    double tanx, tany;  /* tangents of the object's field angle: the screens are looked up at altitude * tan(theta) */
     uint64_t knot_seed;
 } B2Object;
 
@@ -246,7 +246,9 @@ typedef struct {
 typedef struct {
     int32_t n_screens;            /* 0: no atmosphere */
     int32_t npix;                 /* each screen npix x npix, periodic */
-    int32_t screen_f32;           /* 1: tables are float32, 0: float64 */
+    int32_t screen_f32;           /* 0: float64 [npix][npix]; 1: float32 [npix][npix]; 2: float32 quads [npix][npix][4] =
+                                     (f[y][x], f[y][x+1], f[y+1][x], f[y+1][x+1]) with periodic neighbours, so that a
+                                     bilinear gradient is one 16-byte load per screen */
     int32_t n_kick;               /* entries of the second-kick radial table, 0: none */
     double screen_scale;          /* [m] */
     double altitude[B2_MAX_SCREENS];  /* [m] */

@@ -131,7 +131,7 @@ def stage1_photons(objects, counts, r, cdf=None, cdf_wave=None, psf=None, screen
             rr = np.sqrt(ri2 + (ro2 - ri2) * r[4])
             pu, pv = rr * np.cos(2 * np.pi * r[5]), rr * np.sin(2 * np.pi * r[5])
             t = psf.t0 + psf.exptime * r[6]
-            tx, ty = np.tan(ob["thx"]), np.tan(ob["thy"])
+            tx, ty = ob["tanx"], ob["tany"]
             gx, gy = np.zeros(n), np.zeros(n)
             for l in range(psf.n_screens):
                 X = pu - psf.vx[l] * t + psf.altitude[l] * tx

@@ -20,9 +20,9 @@ def _setup(psf=None, n_sed=3):
     tab = ObjectTable(arcsec_to_pix=a2p)
     rng = np.random.default_rng(2)
     tab.add_points(rng.uniform(0, 4000, 5), rng.uniform(0, 4000, 5), [3000, 10, 1, 2500, 700], sed=[0, 1, 2, 0, 1],
-                   thx=rng.uniform(-0.02, 0.02, 5), thy=rng.uniform(-0.02, 0.02, 5))
+                   tanx=rng.uniform(-0.02, 0.02, 5), tany=rng.uniform(-0.02, 0.02, 5))
     tab.add_gaussians([100.0, 900.0], [50.0, 10.0], [4000, 5000], [0.3, 1.1], sed=1)
-    tab.add_sersic(500.0, 600.0, 20000, 0.8, 4.0, q=0.6, beta=0.4, g1=0.02, g2=-0.01, mu=1.1, sed=2, thx=0.01, thy=-0.02)
+    tab.add_sersic(500.0, 600.0, 20000, 0.8, 4.0, q=0.6, beta=0.4, g1=0.02, g2=-0.01, mu=1.1, sed=2, tanx=0.01, tany=-0.02)
     tab.add_sersic(1500.0, 1600.0, 15000, 1.3, 1.0, q=0.9, beta=2.0, sed=0)
     tab.add_knots(2500.0, 700.0, 9000, 0.9, 17, q=0.5, beta=1.0, sed=1, seed=99)
     tab.add_streak(3000.0, 3000.0, 6000, 40.0, 0.4, position_angle=0.7, sed=2)
