@@ -88,6 +88,12 @@ class OpticsContext:
         _lib.check(self._lib.b2_fma_peak(self._h, int(bool(fp64)), C.byref(out)))
         return out.value
 
+    def atomic_peak(self, fp64=True, pattern=0, nx=4096, ny=4004, n=1 << 26) -> float:
+        """Measured atomicAdd throughput [atomics/s] on an image-sized buffer (0 uniform, 1 hot pixel, 2 stars)."""
+        out = C.c_double(0.0)
+        _lib.check(self._lib.b2_atomic_peak(self._h, int(bool(fp64)), int(pattern), nx, ny, int(n), C.byref(out)))
+        return out.value
+
     # -- photon ops ---------------------------------------------------------
     def xy_to_v(self, x, y, out=None):
         where = _lib.where_of(x)

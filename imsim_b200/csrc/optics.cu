@@ -689,6 +689,62 @@ extern "C" int b2_fma_peak(b2_ctx* ctx, int32_t fp64, double* tflops) {
     return 0;
 }
 
+// atomicAdd throughput on an image-sized buffer: the ceiling of the charge deposit (roofline denominator of
+// the accumulate kernels).  pattern 0: uniform random pixels, 1: every thread hits the same pixel,
+// 2: Gaussian blobs (1000 stars, sigma 1.5 px) like the bright-star workload.
+template <typename T>
+__global__ void __launch_bounds__(256) k_atomic_peak(T* img, int nx, int ny, int64_t n, int pattern, uint64_t seed) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t r[4];
+    philox4(seed, (uint64_t)i, 30u, r);
+    size_t k;
+    if (pattern == 0) {
+        k = (size_t)(r[0] % (uint32_t)nx) + (size_t)(r[1] % (uint32_t)ny) * nx;
+    } else if (pattern == 1) {
+        k = (size_t)(ny / 2) * nx + nx / 2;
+    } else {
+        uint32_t star = r[2] % 1000u;
+        uint32_t q[4];
+        philox4(seed + 1, (uint64_t)star, 31u, q);
+        float u1 = ((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        float sn, cs;
+        sincospif(2.0f * u2, &sn, &cs);
+        float rad = 1.5f * sqrtf(-2.0f * logf(u1));
+        int px = (int)(q[0] % (uint32_t)(nx - 40)) + 20 + (int)lrintf(rad * cs);
+        int py = (int)(q[1] % (uint32_t)(ny - 40)) + 20 + (int)lrintf(rad * sn);
+        k = (size_t)py * nx + px;
+    }
+    atomicAdd(&img[k], (T)1);
+}
+
+extern "C" int b2_atomic_peak(b2_ctx* ctx, int32_t fp64, int32_t pattern, int32_t nx, int32_t ny, int64_t n,
+                              double* atomics_per_s) {
+    B2_REQUIRE(ctx && atomics_per_s && nx > 64 && ny > 64 && n > 0, "b2_atomic_peak: bad argument");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    if (b2_scratch_reserve(ctx, ctx->scratch, (size_t)nx * ny * 8)) return 1;
+    B2_CUDA(cudaMemsetAsync(ctx->scratch.ptr, 0, (size_t)nx * ny * 8, ctx->stream));
+    cudaEvent_t e0, e1;
+    B2_CUDA(cudaEventCreate(&e0));
+    B2_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        B2_CUDA(cudaEventRecord(e0, ctx->stream));
+        if (fp64) k_atomic_peak<double><<<nblocks(n), 256, 0, ctx->stream>>>((double*)ctx->scratch.ptr, nx, ny, n, pattern, 7 + rep);
+        else k_atomic_peak<float><<<nblocks(n), 256, 0, ctx->stream>>>((float*)ctx->scratch.ptr, nx, ny, n, pattern, 7 + rep);
+        B2_CHECK_LAUNCH();
+        B2_CUDA(cudaEventRecord(e1, ctx->stream));
+        B2_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        B2_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *atomics_per_s = (double)n / (best * 1e-3);
+    return 0;
+}
+
 extern "C" int b2_flat_photons(b2_ctx* ctx, int64_t n, double* x, double* y, double* flux, double* wl, double xlo,
                                double xhi, double ylo, double yhi, const double* cdf, const double* cdf_wave,
                                int32_t ncdf, uint64_t seed, uint64_t offset) {

@@ -302,6 +302,9 @@ int b2_ctx_synchronize(b2_ctx* ctx);
    non-tensor FMA rate (fp64 != 0: double, else float) in TFLOP/s.  The roofline
    denominator of the compute-bound trace kernel (MEASURED_PEAKS.json has none). */
 int b2_fma_peak(b2_ctx* ctx, int32_t fp64, double* tflops);
+/* measured atomicAdd throughput [atomics/s] on an nx x ny image (fp64: double, else float): pattern 0 uniform random
+   pixels, 1 one hot pixel, 2 a thousand Gaussian star images -- the ceiling of the charge deposit */
+int b2_atomic_peak(b2_ctx* ctx, int32_t fp64, int32_t pattern, int32_t nx, int32_t ny, int64_t n, double* atomics_per_s);
 /* measurement aid: with B2_TIMING=1 in the environment every kernel launch is bracketed by CUDA
    events on its stream; this returns {"kernel": [launches, total_ms], ...} as JSON and clears the log */
 int b2_timing_report(char* buf, int64_t cap);
