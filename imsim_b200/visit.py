@@ -99,6 +99,7 @@ class DetectorRunner:
         self._sensors: Dict[tuple, SiliconSensor] = {}
         self._readouts: Dict[str, object] = {}
         self._pin: Dict[tuple, object] = {}
+        self.last_incident_flux = None
         self.last_raw = None
         #: stage-1 PSF (``atmosphere.AtmosphericPSF`` / ``GaussianPSF``): one realisation per visit, shared by the
         #: detectors of this GPU like the reference's ``atm_psf`` input object (imsim/atmPSF.py:339-347)
@@ -219,6 +220,9 @@ class DetectorRunner:
         e1.record()
         torch.cuda.synchronize(dev)
         self.last_raw = raw
+        # per-object sum of the photon fluxes shot over all batches: the ``incident_flux`` column of the
+        # photon_pooling_truth output (imsim/photon_pooling.py:472-511, stamp.py:743)
+        self.last_incident_flux = np.asarray(counts, dtype=np.int64).sum(axis=0).astype(np.float64)
         rec = {"det_name": det_name, "device": self.device, "photons": n_total, "nbatch": nbatch,
                "electrons": float(electrons.item()), "gpu_ms": float(e0.elapsed_time(e1)),
                "setup_ms": 1e3 * t_setup}

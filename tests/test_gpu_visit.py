@@ -48,6 +48,7 @@ def test_detector_runner_conserves_photons():
     wave = np.linspace(550, 690, 15)
     rec, image = runner.run("R22_S11", objs, nbatch=10, wavelength_cdf=wavelength_cdf(wave, np.ones_like(wave)))
     assert rec["photons"] == int(objs[2].sum()) and rec["nbatch"] == 10
+    assert np.array_equal(runner.last_incident_flux, objs[2].astype(np.float64))  # truth column incident_flux
     # same detector again with the electronics readout on the device: 16 int32 segments carrying the e-image
     rec2, image2 = runner.run("R22_S11", objs, nbatch=10, wavelength_cdf=wavelength_cdf(wave, np.ones_like(wave)),
                               readout=True)
