@@ -156,3 +156,60 @@ def test_no_angles_no_wavelengths_and_strength_scaling():
     added = s.accumulate(pa, img)
     assert added == img.array.sum() == n
     assert s.last_stats.n_updates == 4 and s.last_stats.n_dropped_bottom == 0
+
+
+def test_restart_from_a_checkpointed_image_rebuilds_the_boundaries():
+    """checkpoints hold the image but not the sensor's pixel boundaries; after a restart the first
+    accumulate runs with resume=False on the restored image and rebuilds them from it in one step
+    (imsim/photon_pooling.py:159,447-466).  The distortions are linear in the charge, so the restarted run
+    lands (to rounding of the float32 boundary points) the same electrons as the uninterrupted one."""
+    import torch
+
+    from imsim_b200 import OpticsContext
+    from imsim_b200.photon_pooling import DevicePhotons, PhotonPool
+    from imsim_b200.synthetic import synthetic_photons
+
+    su = helpers.oracle_setup()
+    cfg, dat = helpers.sensor_model("lsst_e2v_50_4")
+    tr = helpers.tree_ring_table()
+    n = 1_500_000
+    x, y, wl, flux = synthetic_photons(2 * n, kind="stars", n_stars=12, seed=21)
+
+    def make():
+        ctx = OpticsContext(device=0, stream=torch.cuda.current_stream())
+        ctx.set_telescope(su.telescope)
+        ctx.set_wcs(su.img_wcs, su.icrf_to_field)
+        ctx.set_detector(su.detector)
+        ctx.set_diffraction(helpers.default_diffraction())
+        sensor = SiliconSensor(config=cfg, vertex_data=dat, nrecalc=0, strength=1.0, rng=77, treering_func=tr[1],
+                               treering_center=tr[0], absorption_table=helpers.absorption(), context=ctx)
+        return ctx, sensor, PhotonPool(ctx, sensor, exptime=30.0, seed=5)
+
+    def batch(k):
+        dp = DevicePhotons(n)
+        for f, a in (("x", x), ("y", y), ("wavelength", wl), ("flux", flux)):
+            getattr(dp, f).copy_(torch.as_tensor(a[k * n:(k + 1) * n]))
+        return dp
+
+    # uninterrupted: two batches, boundaries updated from the first batch's charge at the start of the second
+    ctx, sensor, pool = make()
+    img = Image(np.zeros((su.detector.ny, su.detector.nx), np.float32), 0, 0)
+    pool.process(batch(0), img, resume=False, recalc=False)
+    sensor.read_image(img)
+    checkpoint = img.array.copy()
+    pool.process(batch(1), img, resume=True, recalc=True)
+    sensor.read_image(img)
+    full = img.array.copy()
+    sensor.close()
+    # restart: a fresh sensor, the checkpointed image, resume=False, the pool's photon counter restored
+    ctx2, sensor2, pool2 = make()
+    pool2.offset = n
+    sensor2._photon_offset = n
+    img2 = Image(checkpoint.copy(), 0, 0)
+    pool2.process(batch(1), img2, resume=False, recalc=False)
+    sensor2.read_image(img2)
+    assert checkpoint.sum() > 0.9 * n and abs(img2.array.sum() - full.sum()) <= 2
+    diff = np.abs(img2.array.astype(np.float64) - full)
+    # identical up to the few photons within a float32 ulp of a moved boundary
+    assert diff.sum() <= 20 and diff.max() <= 2, (diff.sum(), diff.max())
+    assert not np.array_equal(full, checkpoint)
