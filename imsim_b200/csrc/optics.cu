@@ -307,7 +307,8 @@ extern "C" int b2_telescope_upload(b2_ctx* ctx, const B2Telescope* tel) {
         memset(&d, 0, sizeof(d));
         d.kind = s.surf_kind;
         d.interact = s.interact;
-        B2_REQUIRE(s.interact != B2_INT_PASS, "b2_telescope_upload: OPDScreen-like interfaces are not supported yet");
+        B2_REQUIRE(s.interact != B2_INT_PASS || s.surf_kind == B2_SURF_PLANE,
+                   "b2_telescope_upload: OPDScreen interfaces are supported on a Plane surface only");
         d.med_in = s.medium_in;
         d.med_out = s.medium_out;
         d.n_coef = s.n_coef;

@@ -489,7 +489,8 @@ __device__ __forceinline__ void surface_step(const DevSurf& s, const int kind, c
     }
     // zc: height of the base conic under the hit point (= pz unless the surface departs from it)
     double zc = pz, gP = 0.0, Ex = 0.0, Ey = 0.0;
-    if (kind == B2_SURF_ASPHERE || extra_kind != B2_EXTRA_NONE) {
+    const bool screen = (interact == B2_INT_PASS);  // batoid.OPDScreen: the summed term is an OPD, not sag
+    if (!screen && (kind == B2_SURF_ASPHERE || extra_kind != B2_EXTRA_NONE)) {
         // Newton on the implicit form G(t) = r^2 - 2 R zc + k1 zc^2 with zc = z - P(r^2) - E(x, y):
         // polynomial in the ray parameter, no square root; quadratic convergence from the conic hit
         bool conv = false;
@@ -541,6 +542,23 @@ __device__ __forceinline__ void surface_step(const DevSurf& s, const int kind, c
         return;
     }
     r.t += dt;
+    if (screen) {
+        // thin phase screen on a plane: the tangential part of the unit direction n v gains grad W, the path W
+        double P, dP, ddP, W = 0.0, Wx = 0.0, Wy = 0.0;
+        departure(s, B2_SURF_PLANE, extra_kind, true, px, py, px * px + py * py, P, dP, ddP, W, Wx, Wy);
+        const double ux = vx * rf.na + Wx, uy = vy * rf.na + Wy;
+        const double w2 = 1.0 - ux * ux - uy * uy;
+        if (w2 <= 0.0) {
+            r.failed = true;
+            r.vignetted = true;
+        } else {
+            const double inv = b2rcp(rf.na);
+            vx = ux * inv;
+            vy = uy * inv;
+            vz = copysign(b2sqrt(w2), vz) * inv;
+            r.t += W;
+        }
+    }
     if (interact == B2_INT_MIRROR || interact == B2_INT_REFRACT) {
         // un-normalised normal N = (-Zx, -Zy, g): the surface gradient scaled by g = R - k1 zc, so the
         // conic part grad F = (x, y, k1 z - R) needs no division; the departure gradient is scaled to match

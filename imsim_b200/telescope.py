@@ -183,6 +183,22 @@ class Telescope:
                 return new
         raise KeyError(name)
 
+    def with_inserted_screen(self, before: str, poly=None, poly_scale=1.0, bicubic=None, coord_sys=None,
+                             obscurations=None, name: str = "Screen") -> "Telescope":
+        """``withInsertedOptic(before=..., item=batoid.OPDScreen(surface=Plane(), screen=Zernike | Bicubic,
+        coordSys=stopSurface.coordSys, obscuration=...))`` (tests/test_telescope_loader.py:641-653): a thin
+        phase plate whose optical path difference [m] is the xy polynomial / bicubic grid."""
+        new = copy.deepcopy(self)
+        k = next((i for i, it in enumerate(new.items) if it.name == before), None)
+        if k is None:
+            raise KeyError(before)
+        med = new.items[k].in_medium
+        surf = Surface("plane", poly=None if poly is None else np.asarray(poly, float), poly_scale=float(poly_scale),
+                       bicubic=bicubic)
+        cs = coord_sys if coord_sys is not None else CoordSys(new.stop.origin.copy(), new.stop.rot.copy())
+        new.items.insert(k, Interface(name, surf, "pass", cs, med, med, list(obscurations or [])))
+        return new
+
     # -- flattening -------------------------------------------------------
     def flatten(self):
         """Return ``(B2Telescope, extras)``; ``extras[i]`` is ``None`` or

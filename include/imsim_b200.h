@@ -49,7 +49,8 @@ extern "C" {
 
 /* surface kinds (batoid.Plane/Sphere/Paraboloid/Quadric/Asphere) */
 enum { B2_SURF_PLANE = 0, B2_SURF_SPHERE = 1, B2_SURF_PARABOLOID = 2, B2_SURF_QUADRIC = 3, B2_SURF_ASPHERE = 4 };
-/* interaction kinds (batoid.Detector/Mirror/RefractiveInterface/OPDScreen) */
+/* interaction kinds (batoid.Detector/Mirror/RefractiveInterface/OPDScreen); PASS = OPDScreen on a Plane: the
+   surface's extra term is the optical path difference W(x, y) [m] of a thin phase plate, not sag */
 enum { B2_INT_DETECTOR = 0, B2_INT_MIRROR = 1, B2_INT_REFRACT = 2, B2_INT_PASS = 3 };
 /* extra (summed) sag term: batoid.Sum([base, Zernike]) or Sum([base, Bicubic]) */
 enum { B2_EXTRA_NONE = 0, B2_EXTRA_POLY2D = 1, B2_EXTRA_BICUBIC = 2 };

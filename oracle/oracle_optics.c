@@ -557,7 +557,14 @@ void orc_trace_one(const B2Telescope* tel, const OrcExtra* extras, double r[3], 
         double vy = v[0] * M[1] + v[1] * M[4] + v[2] * M[7];
         double vz = v[0] * M[2] + v[1] * M[5] + v[2] * M[8];
         double dt;
-        if (!surf_time(s, e, x, y, z, vx, vy, vz, &dt)) {
+        B2Surface base;
+        const B2Surface* geom = s;
+        if (s->interact == B2_INT_PASS) { /* batoid.OPDScreen: the summed term is the screen, the surface stays bare */
+            base = *s;
+            base.extra_kind = B2_EXTRA_NONE;
+            geom = &base;
+        }
+        if (!surf_time(geom, e, x, y, z, vx, vy, vz, &dt)) {
             *failed = 1;
             *vignetted = 1;
             r[0] = x, r[1] = y, r[2] = z;
@@ -568,6 +575,27 @@ void orc_trace_one(const B2Telescope* tel, const OrcExtra* extras, double r[3], 
         y += vy * dt;
         z += vz * dt;
         *t += dt;
+        if (s->interact == B2_INT_PASS) {
+            /* thin phase screen on a plane (batoid.OPDScreen with surface=Plane, tests/test_telescope_loader.py:
+               641-653): the eikonal gains W(x, y), so the tangential part of the unit direction n v gains grad W
+               and the path length gains W; restated from the definition, batoid's refractScreen is not in the tree */
+            double W = 0.0, Wx = 0.0, Wy = 0.0;
+            if (s->extra_kind == B2_EXTRA_POLY2D && e && e->poly) poly2d_eval(s, e->poly, x, y, &W, &Wx, &Wy);
+            else if (s->extra_kind == B2_EXTRA_BICUBIC && e && e->bicubic) bicubic_eval(e->bicubic, x, y, &W, &Wx, &Wy);
+            double n1 = nmed[s->medium_in];
+            double ux = vx * n1 + Wx, uy = vy * n1 + Wy, uz = vz * n1;
+            double w2 = 1.0 - ux * ux - uy * uy;
+            if (w2 <= 0.0) {
+                *failed = 1;
+                *vignetted = 1;
+            } else {
+                uz = (uz < 0.0 ? -1.0 : 1.0) * sqrt(w2);
+                vx = ux / n1;
+                vy = uy / n1;
+                vz = uz / n1;
+                *t += W;
+            }
+        }
         if (s->interact == B2_INT_MIRROR || s->interact == B2_INT_REFRACT) {
             double sz, zx, zy;
             surf_sag_grad(s, e, x, y, &sz, &zx, &zy);

@@ -338,3 +338,89 @@ def test_fused_photon_dcr():
     ok = (flux > 0) & (f2 > 0)
     np.testing.assert_allclose(x[ok], x2[ok], rtol=0, atol=4e-7)
     np.testing.assert_allclose(y[ok], y2[ok], rtol=0, atol=4e-7)
+
+
+def test_opd_screen():
+    """batoid.OPDScreen on a plane (tests/test_telescope_loader.py:641-653): parity with the oracle, the
+    physics of a thin phase plate (a tilt W = a x deflects by a, a defocus W = a r^2 focuses at 1 / (2 a)),
+    and a null screen changing nothing."""
+    from oracle import oracle as orc
+
+    from imsim_b200.telescope import (AIR, CoordSys, Interface, Obscuration, Surface, Telescope)
+
+    # 1. plate + detector plane 10 m below, in vacuum-like air: analytic checks
+    def plate(poly, scale=1.0):
+        stop = CoordSys(np.zeros(3), np.eye(3))
+        items = [Interface("Screen", Surface("plane", poly=np.asarray(poly, float), poly_scale=scale), "pass",
+                           CoordSys(np.array([0.0, 0.0, -1.0]), np.eye(3)), AIR, AIR,
+                           [Obscuration("circle", (5.0, 0.0, 0.0), negate=True)]),
+                 Interface("Detector", Surface("plane"), "detector", CoordSys(np.array([0.0, 0.0, -11.0]), np.eye(3)),
+                           AIR, AIR, [])]
+        return Telescope(stop, items)
+
+    rng = np.random.default_rng(2)
+    n = 5000
+    x0, y0 = rng.uniform(-3, 3, n), rng.uniform(-3, 3, n)
+    wl = np.full(n, 600e-9)
+    nair = AIR.n(wl)
+
+    def shoot(tel):
+        ctx = _ctx()
+        ctx.set_telescope(tel)
+        assert ctx.program == 0
+        arrs = [x0.copy(), y0.copy(), np.zeros(n), np.zeros(n), np.zeros(n), -1.0 / nair, np.zeros(n), wl.copy()]
+        vig, fail = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        ctx.trace_rays(*arrs, vig, fail)
+        ref = orc.trace_rays(*tel.flatten(), x0, y0, np.zeros(n), np.zeros(n), np.zeros(n), -1.0 / nair, np.zeros(n), wl)
+        for k in range(7):
+            _close(arrs[k], ref[k], scale=max(1.0, float(np.abs(ref[k]).max())), rtol=1e-13)
+        assert np.array_equal(vig, ref[7]) and np.array_equal(fail, ref[8])
+        return arrs
+
+    a = 1e-4
+    tilt = np.zeros((2, 2))
+    tilt[1, 0] = a  # W = a x
+    out = shoot(plate(tilt))
+    np.testing.assert_allclose(out[0] - x0, 10.0 * a / np.sqrt(1 - a * a), rtol=1e-12)  # deflected by asin(a) over 10 m
+    np.testing.assert_allclose(out[1], y0, atol=1e-15)
+    np.testing.assert_allclose(out[6] - (11.0 * nair), a * x0 + 10.0 * nair * (1 / np.sqrt(1 - a * a) - 1), rtol=0, atol=1e-12)
+    foc = np.zeros((3, 3))
+    foc[2, 0] = foc[0, 2] = -1.0 / 20.0  # W = -r^2 / (2 f), f = 10 m: a converging plate
+    out = shoot(plate(foc))
+    r0 = np.hypot(x0, y0)
+    r_out = r0 - 10.0 * np.tan(np.arcsin(r0 / 10.0))  # sin(theta) = r / f exactly for this plate
+    np.testing.assert_allclose(out[0], x0 * r_out / r0, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(out[1], y0 * r_out / r0, rtol=0, atol=1e-12)
+    assert np.abs(out[0][r0 < 0.3]).max() < 2e-4  # paraxial focus 10 m behind the plate
+    null = shoot(plate(np.zeros((2, 2))))
+    np.testing.assert_array_equal(null[0], x0)
+    # 2. a Zernike-like screen in front of M1 of the Rubin-like telescope (telescope_loader's use): oracle parity,
+    #    and the image shifts by focal length x wavefront tilt
+    tel = rubin_like("r")
+    scr = np.zeros((3, 3))
+    scr[1, 0] = 2e-7  # tilt in units of R_outer
+    scr[1, 1] = 1e-7
+    tels = tel.with_inserted_screen("M1", poly=scr, poly_scale=1 / 4.18,
+                                    obscurations=[Obscuration("annulus", (2.558, 4.18, 0.0, 0.0), negate=True)])
+    assert [it.name for it in tels.items][:2] == ["Screen", "M1"]
+    rr = np.sqrt(rng.uniform(2.6**2, 4.1**2, n))
+    ph = rng.uniform(0, 2 * np.pi, n)
+    base = [rr * np.cos(ph), rr * np.sin(ph), np.zeros(n), np.full(n, 1e-3) / nair, np.zeros(n), -np.sqrt(1 - 1e-6) / nair,
+            np.zeros(n), wl]
+    res = {}
+    for name, t in (("plain", tel), ("screen", tels)):
+        ctx = _ctx()
+        ctx.set_telescope(t)
+        arrs = [np.ascontiguousarray(b.copy()) for b in base]
+        vig, fail = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        ctx.trace_rays(*arrs, vig, fail)
+        ref = orc.trace_rays(*t.flatten(), *[b.copy() for b in base])
+        ok = fail == 0
+        _close(arrs[0][ok], ref[0][ok], scale=0.3)
+        _close(arrs[1][ok], ref[1][ok], scale=0.3)
+        assert np.array_equal(vig, ref[7])
+        res[name] = arrs, vig
+    good = (res["plain"][1] == 0) & (res["screen"][1] == 0)
+    shift = np.median(res["screen"][0][0][good] - res["plain"][0][0][good])
+    # wavefront tilt 2e-7 / 4.18 rad x effective focal length 10.31 m ~ 4.9e-7 m, sign set by the three mirrors
+    assert 3e-7 < abs(shift) < 7e-7
