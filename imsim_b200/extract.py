@@ -138,6 +138,29 @@ def _walk(optic, out):
             _walk(it, out)
         return
     name = _cls(optic)
+    if name == "OPDScreen":
+        # batoid.OPDScreen(surface=Plane(), screen=Zernike | Bicubic, ...) as telescope_loader inserts it
+        # (tests/test_telescope_loader.py:641-653): a 'pass' interface whose summed term is the OPD
+        if _cls(optic.surface) != "Plane":
+            raise ExtractError("OPDScreen is supported on a Plane surface only")
+        screen, sn = optic.screen, _cls(optic.screen)
+        surf = Surface("plane")
+        if sn == "Zernike":
+            c, scale = _zernike_xy(screen)
+            n = max(c.shape)
+            surf.poly = np.zeros((n, n))
+            surf.poly[: c.shape[0], : c.shape[1]] = c
+            surf.poly_scale = scale
+        elif sn == "Bicubic":
+            surf.bicubic = dict(xs=np.array(screen.xs), ys=np.array(screen.ys), zs=np.array(screen.zs),
+                                dzdxs=np.array(screen.dzdxs), dzdys=np.array(screen.dzdys),
+                                d2zdxdys=np.array(screen.d2zdxdys))
+        elif sn != "Plane":
+            raise ExtractError("unsupported OPDScreen screen %s" % sn)
+        out.append(Interface(name=str(optic.name), surface=surf, interact="pass", coord_sys=_coordsys(optic.coordSys),
+                             in_medium=medium_from_batoid(optic.inMedium), out_medium=medium_from_batoid(optic.outMedium),
+                             obscurations=_obsc_list(getattr(optic, "obscuration", None))))
+        return
     kinds = {"Mirror": "mirror", "RefractiveInterface": "refract", "Detector": "detector", "Baffle": "detector"}
     if name not in kinds:
         raise ExtractError("unsupported batoid optic %s (%s)" % (name, getattr(optic, "name", "?")))
