@@ -124,6 +124,23 @@ def test_extract_on_duck_typed_batoid():
     assert pod.n_surfaces == 3 and pod.n_media == 2 and pod.surf[1].interact == _abi.INT_REFRACT
     with pytest.raises(extract.ExtractError):
         extract.surface_from_batoid(mk("Tilted"))
+    # an OPDScreen inserted in front of M1 (tests/test_telescope_loader.py:641-653) becomes a 'pass' interface
+    xy = np.zeros((3, 3))
+    xy[1, 0] = 1e-6
+    screen = mk("OPDScreen", name="Screen", surface=mk("Plane"), screen=mk("Zernike", _xycoef=xy), coordSys=cs0,
+                inMedium=air, outMedium=air, obscuration=clear, skip=False)
+    optic2 = mk("CompoundOptic", name="T", items=[screen, m1, lens, det], inMedium=air,
+                stopSurface=mk("Interface", surface=mk("Plane"), coordSys=cs0))
+    tel2 = extract.telescope_from_batoid(optic2)
+    pod2, extras2 = tel2.flatten()
+    assert tel2.items[0].interact == "pass" and pod2.surf[0].interact == _abi.INT_PASS
+    assert pod2.surf[0].surf_kind == _abi.SURF_PLANE and pod2.surf[0].extra_kind == _abi.EXTRA_POLY2D
+    assert extras2[0][1].reshape(3, 3)[1, 0] == 1e-6 and pod2.surf[0].medium_in == pod2.surf[0].medium_out
+    with pytest.raises(extract.ExtractError):
+        extract.telescope_from_batoid(mk("CompoundOptic", name="T", inMedium=air, items=[
+            mk("OPDScreen", name="S", surface=mk("Sphere", R=3.0), screen=mk("Plane"), coordSys=cs0, inMedium=air,
+               outMedium=air, obscuration=None, skip=False), det],
+            stopSurface=mk("Interface", surface=mk("Plane"), coordSys=cs0)))
     # galsim-like WCS
     w = mk("GSFitsWCS", wcs_type="TAN-SIP", pv=None, ab=np.zeros((2, 4, 4)), crpix=np.array([1.0, 2.0]),
            cd=np.eye(2) * 5e-5, center=mk("CelestialCoord", ra=mk("Angle", rad=0.1), dec=mk("Angle", rad=-0.2)))
