@@ -6,8 +6,9 @@ border, ``niter = ceil(counts / max_counts_per_iter)`` iterations per section:
 
 * no ``sed`` (examples/flat.yaml): ``area = sensor.calculate_pixel_areas(section)``,
   ``temp = base * area / mean(area)``, Poisson realisation, ``section += temp``
-  (flat.py:220-237) -- the areas come from ``k_pixel_areas``; the Poisson draw is
-  host numpy in this round;
+  (flat.py:220-237) -- the areas come from ``k_pixel_areas`` and the Poisson realisation from the exact
+  counter-based sampler of ``k_add_sky``, the section never leaves HBM (``fused=False``: numpy Poisson on the
+  host, the first version);
 * ``sed`` given (examples/flat_with_sed.yaml): Poisson number of photons uniform
   over the bordered section, wavelengths from SED x bandpass,
   ``sensor.accumulate(photons, section, resume=(it > 0))`` with
@@ -78,7 +79,33 @@ def build_flat(image: Image, counts_per_pixel: float, sensor: Optional[SiliconSe
             # section with border (flat.py:209-213); it may stick out of the image like the reference's
             bx0, bx1, by0, by1 = xmin - buffer_size, xmax + buffer_size, ymin - buffer_size, ymax + buffer_size
             sec = Image(np.zeros((by1 - by0 + 1, bx1 - bx0 + 1), dtype=image.array.dtype), bx0, by0)
-            for it in range(niter):
+            if sed_cdf is None and sensor is not None and fused:
+                # pixel-area branch entirely on the device: the section stays in HBM, each iteration computes
+                # the areas from the charge collected so far (b2_sensor_pixel_areas) and adds
+                # Poisson(counts * base * area / mean(area)) with the exact counter-based sampler (b2_add_sky)
+                import torch
+
+                from .sky import add_sky, pixel_areas_device
+
+                dev = "cuda:%d" % sensor.ctx.device
+                tdt = torch.float32 if sec.array.dtype == np.float32 else torch.float64
+                sec_dev = torch.zeros(sec.array.shape, dtype=tdt, device=dev)
+                mod = None
+                if base_level is not None:
+                    mod = torch.as_tensor(np.ascontiguousarray(base_level(sec), dtype=np.float32), device=dev)
+                for it in range(niter):
+                    _lib.check(_lib.load().b2_sensor_bind_image(sensor._h, sec.xmin, sec.ymin, sec.array.shape[1],
+                                                                sec.array.shape[0], sec.array.dtype.itemsize,
+                                                                C.c_void_p(sec_dev.data_ptr()), 1))
+                    sensor._bound_shape = (sec.array.shape[0], sec.array.shape[1], sec.array.dtype)
+                    areas = pixel_areas_device(sensor, use_flux=True)
+                    add_sky(sensor.ctx, sec_dev, counts_per_iter / float(areas.mean()), seed=int(gen.integers(1 << 62)),
+                            areas=areas, modulation=mod)
+                sec.array[:, :] = sec_dev.cpu().numpy()
+                niter_host = 0
+            else:
+                niter_host = niter
+            for it in range(niter_host):
                 if sed_cdf is None:
                     area = sensor.calculate_pixel_areas(sec) if sensor is not None else 1.0
                     temp = np.full(sec.array.shape, counts_per_iter, dtype=np.float64)

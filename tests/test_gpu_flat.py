@@ -16,13 +16,16 @@ def _cov(a):
     return (np.mean(f[1:, :] * f[:-1, :]), np.mean(f[:, 1:] * f[:, :-1]), np.mean(f[1:, 1:] * f[:-1, :-1]))
 
 
-def test_silicon_flat_area_branch():
-    """tests/test_flats.py:69-111: BF correlates neighbours, more along y, variance drops below the mean."""
+@pytest.mark.parametrize("fused", [True, False])
+def test_silicon_flat_area_branch(fused):
+    """tests/test_flats.py:69-111: BF correlates neighbours, more along y, variance drops below the mean.
+    fused: areas and Poisson realisation on the device; otherwise numpy Poisson on the host."""
     cfg, dat = helpers.sensor_model("lsst_itl_50_8")
     sensor = SiliconSensor(config=cfg, vertex_data=dat, rng=1234, absorption_table=helpers.absorption())
     tot = 80_000
-    img = Image(np.zeros((256, 256), np.float32), 1, 1)
-    build_flat(img, tot, sensor, rng=1234, max_counts_per_iter=4000)
+    size = 1024 if fused else 256  # the covariance estimates carry a noise of var / size: go large where it is cheap
+    img = Image(np.zeros((size, size), np.float32), 1, 1)
+    build_flat(img, tot, sensor, rng=1234, max_counts_per_iter=4000, fused=fused)
     a = img.array.astype(float)
     np.testing.assert_allclose(a.mean(), tot, rtol=1e-2)
     np.testing.assert_allclose(a.var(), tot, rtol=1e-1)
@@ -33,7 +36,8 @@ def test_silicon_flat_area_branch():
     assert cov10 > cov01 > cov11
 
 
-def test_treerings_flat_area_branch():
+@pytest.mark.parametrize("fused", [True, False])
+def test_treerings_flat_area_branch(fused):
     """tests/test_flats.py:113-165: cosine tree rings of amplitude A, period P (+ BF) give
     var ~ 1/2 (N A 2pi / P)^2 + N to 3 %, and large covariances in every direction."""
     cfg, dat = helpers.sensor_model("lsst_itl_50_8")
@@ -42,7 +46,7 @@ def test_treerings_flat_area_branch():
                            treering_center=(-100.0, -100.0), absorption_table=helpers.absorption())
     tot = 100_000
     img = Image(np.zeros((256, 256), np.float32), 1, 1)
-    build_flat(img, tot, sensor, rng=1234, max_counts_per_iter=10_000)
+    build_flat(img, tot, sensor, rng=1234, max_counts_per_iter=10_000, fused=fused)
     a = img.array.astype(float)
     pred_var = 0.5 * (tot * amp * 2 * np.pi / period) ** 2 + tot
     np.testing.assert_allclose(a.mean(), tot, rtol=1e-2)
