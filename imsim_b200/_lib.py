@@ -98,6 +98,7 @@ _SIGNATURES = {
     "b2_stage1_photons": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int32, vp, vp, C.c_int32, C.c_int32, vp,
                                     C.c_uint64, C.c_uint64]),
     "b2_atomic_peak": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_double)]),
+    "b2_scatter_add": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, vp, vp, vp]),
     "b2_add_sky": (C.c_int, [vp, vp, C.c_int32, C.c_int64, C.c_double, vp, vp, C.c_uint64]),
     "b2_bleed_trails": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int]),
     "b2_readout": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.POINTER(_abi.B2Amp), C.c_int32, vp, vp, vp, C.c_int32,

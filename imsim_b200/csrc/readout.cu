@@ -181,6 +181,38 @@ extern "C" int b2_add_sky(b2_ctx* ctx, void* image, int32_t dtype_bytes, int64_t
     return 0;
 }
 
+// ------------------------------------------------------------------ cosmic rays
+// image[iy][ix] += value for a list of pixels with numpy's indexing rules: CosmicRays.paint_cr
+// (imsim/cosmic_rays.py:74-111) adds span values inside "try: image_array[y, x] += value / except IndexError",
+// so a negative index wraps around and only an index beyond the array is skipped.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_scatter_add(T* __restrict__ image, int nx, int ny, int64_t n, const int32_t* __restrict__ iy,
+              const int32_t* __restrict__ ix, const float* __restrict__ values) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int y = iy[i], x = ix[i];
+    if (y < -ny || y >= ny || x < -nx || x >= nx) return;  // IndexError -> pass
+    if (y < 0) y += ny;
+    if (x < 0) x += nx;
+    atomicAdd(&image[(size_t)y * nx + x], (T)values[i]);
+}
+
+extern "C" int b2_scatter_add(b2_ctx* ctx, void* image, int32_t dtype_bytes, int32_t nx, int32_t ny, int64_t n,
+                              const int32_t* iy, const int32_t* ix, const float* values) {
+    B2_REQUIRE(ctx && image && nx > 0 && ny > 0, "b2_scatter_add: bad argument");
+    B2_REQUIRE(dtype_bytes == 4 || dtype_bytes == 8, "b2_scatter_add: image must be float32 or float64");
+    if (n <= 0) return 0;
+    B2_REQUIRE(iy && ix && values, "b2_scatter_add: null pixel list");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    B2_TIMED("k_scatter_add", ctx->stream);
+    unsigned nb = (unsigned)((n + 255) / 256);
+    if (dtype_bytes == 4) k_scatter_add<float><<<nb, 256, 0, ctx->stream>>>((float*)image, nx, ny, n, iy, ix, values);
+    else k_scatter_add<double><<<nb, 256, 0, ctx->stream>>>((double*)image, nx, ny, n, iy, ix, values);
+    B2_CHECK_LAUNCH();
+    return 0;
+}
+
 // ------------------------------------------------------------------ readout
 // small-mean Poisson by inversion (dark current: 0.02 e-/s x 32 s), Gaussian approximation above 64
 __device__ __forceinline__ double poisson_draw(double mean, double u, double g) {

@@ -411,6 +411,11 @@ int b2_readout(b2_ctx* ctx, float* eimage, int32_t nx, int32_t ny, const B2Amp* 
    float32 map (sky gradient x vignetting x fringing) or NULL. */
 int b2_add_sky(b2_ctx* ctx, void* image, int32_t dtype_bytes, int64_t npix, double sky_level, const double* areas,
                const float* modulation, uint64_t seed);
+/* CosmicRays.paint_cr (imsim/cosmic_rays.py:74-111) for a flattened list of span pixels: image[iy][ix] += value on a
+   DEVICE image with numpy's indexing rules (negative indices wrap, indices beyond the array are skipped).
+   iy, ix, values: DEVICE arrays of n entries. */
+int b2_scatter_add(b2_ctx* ctx, void* image, int32_t dtype_bytes, int32_t nx, int32_t ny, int64_t n, const int32_t* iy,
+                   const int32_t* ix, const float* values);
 
 /* ---- silicon sensor ---------------------------------------------------- */
 /* replaces galsim.SiliconSensor.__init__ (imsim/lsst_image.py:93-103,

@@ -118,3 +118,23 @@ def apply_crosstalk(amps, xtalk):
             acc = acc + x * np.float64(y)
         out.append(amps[i] + acc)
     return out
+
+
+def paint_cosmic_rays(image, crs, uniforms, num_crs):
+    """imsim/cosmic_rays.py:74-111 (CosmicRays.paint_cr) restated as plain loops: per hit three uniforms (catalogue
+    index, x, y), then ``image[y, x] += value`` under numpy's indexing rules.  crs: list of lists of (x0, y0, values)."""
+    img = np.array(image, copy=True)
+    ny, nx = img.shape
+    k = 0
+    for _ in range(num_crs):
+        index = int(uniforms[k] * len(crs))
+        px, py = int(uniforms[k + 1] * nx), int(uniforms[k + 2] * ny)
+        k += 3
+        cr = crs[index]
+        for x0, y0, values in cr:
+            for dx, value in enumerate(values):
+                y, x = py + y0 - cr[0][1], px + x0 - cr[0][0] + dx
+                if y < -ny or y >= ny or x < -nx or x >= nx:
+                    continue
+                img[y, x] += value
+    return img

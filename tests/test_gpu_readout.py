@@ -152,3 +152,25 @@ def test_full_size_readout_statistics():
     assert abs(over.mean() - 999.5) < 0.05 and abs(over.std() - 5.0) < 0.1
     data = r[3, 100:1900, 20:500].astype(np.float64)
     assert abs(data.mean() - (1200.64 - 0.5)) < 0.2
+
+
+def test_cosmic_rays_match_reference_paint():
+    """The one-launch scatter against the reference's own paint_cr loop (tests/golden/cosmic_rays.npz): same draws
+    (injected), same wrap-around at the image edges, same skipped pixels."""
+    import torch
+
+    from imsim_b200.cosmic_rays import CosmicRays
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cosmic_rays.npz"))
+    crs = CosmicRays.from_spans(g["fp_id"], g["x0"], g["y0"], g["pixel_values"], span_len=g["span_len"], exptime=100.0)
+    assert len(crs) == 40 and abs(crs.ccd_rate - 0.4) < 1e-12
+    it = iter(g["uniforms"])
+    img = torch.as_tensor(g["image_in"].copy(), device="cuda")
+    crs.paint(_ctx(), img, lambda: next(it), num_crs=int(g["num_crs"]))
+    torch.cuda.synchronize()
+    assert np.array_equal(img.cpu().numpy(), g["image_out"])
+    # the number of hits follows exptime * rate * area fraction (cosmic_rays.py:66-69)
+    big = torch.zeros((4000, 4000), dtype=torch.float32, device="cuda")
+    crs.paint(_ctx(), big, np.random.default_rng(3), exptime=3000.0)
+    hit = int((big > 0).sum())
+    assert 0.5 * 1200 * 20 < hit < 2.0 * 1200 * 60  # ~1200 hits of 20..60 pixels each

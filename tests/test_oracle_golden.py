@@ -211,3 +211,17 @@ def test_readout_oracle_matches_the_reference_functions():
     from imsim_b200.readout import cte_band
 
     assert np.array_equal(cte_band(40, 1e-3), band)
+
+
+def test_cosmic_ray_oracle_matches_the_reference_function():
+    from collections import defaultdict
+
+    from oracle import readout as R
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cosmic_rays.npz"))
+    edges = np.concatenate([[0], np.cumsum(g["span_len"])])
+    crs = defaultdict(list)
+    for k, fid in enumerate(g["fp_id"]):
+        crs[int(fid)].append((int(g["x0"][k]), int(g["y0"][k]), g["pixel_values"][edges[k]:edges[k + 1]]))
+    out = R.paint_cosmic_rays(g["image_in"], list(crs.values()), g["uniforms"], int(g["num_crs"]))
+    assert np.array_equal(out, g["image_out"]) and (out != g["image_in"]).sum() > 5000
