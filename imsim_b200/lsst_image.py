@@ -24,7 +24,6 @@ from typing import Optional
 
 import numpy as np
 
-from . import _abi
 from .photon_pooling import DevicePhotons, PhotonPool
 from .sensor import Image
 from .stage1 import Stage1

@@ -11,9 +11,6 @@ brighter-fatter if ``use_flux_sky_areas``; config/imsim-config.yaml:222-228).  H
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional
-
-import numpy as np
 
 from . import _abi, _lib
 

@@ -16,7 +16,7 @@ from __future__ import annotations
 import ctypes as C
 import gzip
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence
+from typing import List, Optional
 
 import numpy as np
 

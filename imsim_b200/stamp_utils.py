@@ -18,7 +18,7 @@ from functools import lru_cache
 import numpy as np
 
 from . import _abi
-from .atmosphere import ARCSEC, WLEN_EFF
+from .atmosphere import WLEN_EFF
 
 FT_DEFAULT = 5.0e-3          # galsim.GSParams().folding_threshold
 STEPK_MINIMUM_HLR = 5.0      # galsim.GSParams().stepk_minimum_hlr

@@ -14,11 +14,10 @@ No collective on the photon path; ``sharding.gather_visit_metadata`` collects pe
 from __future__ import annotations
 
 import time
-from typing import Dict, List, Optional, Sequence
+from typing import Dict
 
 import numpy as np
 
-from . import _abi
 from .context import OpticsContext
 from .detector import lsstcam_like
 from .diffraction import RUBIN_LATITUDE, diffraction_config
