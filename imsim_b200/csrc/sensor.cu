@@ -459,6 +459,71 @@ k_update_bounds(const __grid_constant__ DevSensor s, const uint8_t* __restrict__
     *reinterpret_cast<double4*>(s.inner + pix * 4) = make_double4(ixmin, ixmax, iymin, iymax);
 }
 
+// The same computation for NV = 4 / 8 with the pixel's polygon held in registers: all four edge segments are loaded
+// up front (independent loads in flight together), the outer box is a float min / max per edge (the stored points
+// are floats, conversion and the +1 offsets of the right / top edges are monotone, so the result is the same
+// double), and the inner box walks the registers instead of global memory a second time.
+template <int NV>
+__global__ void __launch_bounds__(256)
+k_update_bounds_t(const __grid_constant__ DevSensor s, const uint8_t* __restrict__ changed, int all) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= s.nx) return;
+    size_t pix = (size_t)y * s.nx + x;
+    if (!all && !changed[pix]) return;
+    const float2* hb = s.H + Hidx(s, x, y);
+    const float2* ht = s.H + Hidx(s, x, y + 1);
+    const float2* vl = s.V + Vidx(s, x, y);
+    const float2* vr = vl + NV;
+    float2 B[NV + 2], T[NV + 2], L[NV], R[NV];
+#pragma unroll
+    for (int k = 0; k < NV + 2; ++k) B[k] = hb[k];
+#pragma unroll
+    for (int k = 0; k < NV + 2; ++k) T[k] = ht[k];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) L[k] = vl[k];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) R[k] = vr[k];
+    // outer box
+    float bx0 = B[0].x, bx1 = B[0].x, by0 = B[0].y, by1 = B[0].y;
+    float tx0 = T[0].x, tx1 = T[0].x, ty0 = T[0].y, ty1 = T[0].y;
+    float lx0 = L[0].x, lx1 = L[0].x, ly0 = L[0].y, ly1 = L[0].y;
+    float rx0 = R[0].x, rx1 = R[0].x, ry0 = R[0].y, ry1 = R[0].y;
+#pragma unroll
+    for (int k = 1; k < NV + 2; ++k) {
+        bx0 = fminf(bx0, B[k].x); bx1 = fmaxf(bx1, B[k].x); by0 = fminf(by0, B[k].y); by1 = fmaxf(by1, B[k].y);
+        tx0 = fminf(tx0, T[k].x); tx1 = fmaxf(tx1, T[k].x); ty0 = fminf(ty0, T[k].y); ty1 = fmaxf(ty1, T[k].y);
+    }
+#pragma unroll
+    for (int k = 1; k < NV; ++k) {
+        lx0 = fminf(lx0, L[k].x); lx1 = fmaxf(lx1, L[k].x); ly0 = fminf(ly0, L[k].y); ly1 = fmaxf(ly1, L[k].y);
+        rx0 = fminf(rx0, R[k].x); rx1 = fmaxf(rx1, R[k].x); ry0 = fminf(ry0, R[k].y); ry1 = fmaxf(ry1, R[k].y);
+    }
+    const double oxmin = fmin((double)fminf(fminf(bx0, tx0), lx0), (double)rx0 + 1.0);
+    const double oxmax = fmax((double)fmaxf(fmaxf(bx1, tx1), lx1), (double)rx1 + 1.0);
+    const double oymin = fmin((double)fminf(fminf(by0, ly0), ry0), (double)ty0 + 1.0);
+    const double oymax = fmax((double)fmaxf(fmaxf(by1, ly1), ry1), (double)ty1 + 1.0);
+    const double cx = (oxmin + oxmax) / 2.0, cy = (oymin + oymax) / 2.0;
+    double ixmin = oxmin, ixmax = oxmax, iymin = oymin, iymax = oymax;
+    auto inner = [&](double px, double py) {
+        if (px - cx >= fabs(py - cy) && px < ixmax) ixmax = px;
+        if (px - cx <= -fabs(py - cy) && px > ixmin) ixmin = px;
+        if (py - cy >= fabs(px - cx) && py < iymax) iymax = py;
+        if (py - cy <= -fabs(px - cx) && py > iymin) iymin = py;
+    };
+    // same order as walk_polygon (the updates are order independent minima / maxima, kept for clarity)
+#pragma unroll
+    for (int k = 0; k < NV + 2; ++k) inner((double)B[k].x, (double)B[k].y);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) inner((double)R[k].x + 1.0, (double)R[k].y);
+#pragma unroll
+    for (int k = NV + 1; k >= 0; --k) inner((double)T[k].x, (double)T[k].y + 1.0);
+#pragma unroll
+    for (int k = NV - 1; k >= 0; --k) inner((double)L[k].x, (double)L[k].y);
+    *reinterpret_cast<double4*>(s.outer + pix * 4) = make_double4(oxmin, oxmax, oymin, oymax);
+    *reinterpret_cast<double4*>(s.inner + pix * 4) = make_double4(ixmin, ixmax, iymin, iymax);
+}
+
 // target (+/-)= delta, optionally clearing delta (Silicon::addDelta / subtractDelta / update)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -895,8 +960,13 @@ static int launch_bounds_update(b2_sensor* s, int all) {
     B2_TIMED("k_update_bounds", s->ctx->stream);
     DevSensor& d = s->d;
     const bool tiled = (d.nv == 4 || d.nv == 8) && d.qdist <= 7 && getenv("B2_UPDATE_GENERIC") == nullptr;
-    k_update_bounds<<<grid2(d.nx, d.ny, 256), 256, 0, s->ctx->stream>>>(d, s->changed, all, tiled ? nullptr : s->tiles,
-                                                                       s->tnx, s->tny);
+    if (tiled && d.nv == 4 && getenv("B2_BOUNDS_GENERIC") == nullptr)
+        k_update_bounds_t<4><<<grid2(d.nx, d.ny, 256), 256, 0, s->ctx->stream>>>(d, s->changed, all);
+    else if (tiled && d.nv == 8 && getenv("B2_BOUNDS_GENERIC") == nullptr)
+        k_update_bounds_t<8><<<grid2(d.nx, d.ny, 256), 256, 0, s->ctx->stream>>>(d, s->changed, all);
+    else
+        k_update_bounds<<<grid2(d.nx, d.ny, 256), 256, 0, s->ctx->stream>>>(d, s->changed, all, tiled ? nullptr : s->tiles,
+                                                                           s->tnx, s->tny);
     B2_CHECK_LAUNCH();
     return 0;
 }
