@@ -70,6 +70,7 @@ k_accumulate(const __grid_constant__ DevSensor s, int64_t i1, int64_t i2, int64_
     }
 }
 
+template <int NVT>
 __global__ void __launch_bounds__(256)
 k_accumulate_slow(const __grid_constant__ DevSensor s, const SlowRec* __restrict__ slow,
                   const unsigned long long* __restrict__ nslow, unsigned long long* __restrict__ stats,
@@ -87,7 +88,7 @@ k_accumulate_slow(const __grid_constant__ DevSensor s, const SlowRec* __restrict
             int ix = r.ix, iy = r.iy;
             const double x = r.x, y = r.y, zconv = r.zconv;
             bool off_edge = false;
-            bool found = inside_pixel(s, ix, iy, x, y, zconv, &off_edge, npoly);
+            bool found = inside_pixel<NVT>(s, ix, iy, x, y, zconv, &off_edge, npoly);
             bool drop = (!found && off_edge);
             if (!drop) {
                 int step = 0;
@@ -102,7 +103,7 @@ k_accumulate_slow(const __grid_constant__ DevSensor s, const SlowRec* __restrict
                     for (int m = 1; m < 9; ++m) {
                         int ix_off = ix + c_xoff[nn], iy_off = iy + c_yoff[nn];
                         double x_off = x - c_xoff[nn], y_off = y - c_yoff[nn];
-                        if (inside_pixel(s, ix_off, iy_off, x_off, y_off, zconv, nullptr, npoly)) {
+                        if (inside_pixel<NVT>(s, ix_off, iy_off, x_off, y_off, zconv, nullptr, npoly)) {
                             ix = ix_off;
                             iy = iy_off;
                             found = true;
@@ -661,6 +662,13 @@ k_find_chunks(const double* __restrict__ flux, int64_t n, const double* __restri
 }
 
 // ------------------------------------------------------------------ host side
+static void launch_slow(unsigned blocks, cudaStream_t st, const DevSensor& d, const SlowRec* slow,
+                        const unsigned long long* nslow, unsigned long long* stats, double* added) {
+    if (d.nv == 4) k_accumulate_slow<4><<<blocks, 256, 0, st>>>(d, slow, nslow, stats, added);
+    else if (d.nv == 8) k_accumulate_slow<8><<<blocks, 256, 0, st>>>(d, slow, nslow, stats, added);
+    else k_accumulate_slow<0><<<blocks, 256, 0, st>>>(d, slow, nslow, stats, added);
+}
+
 static inline dim3 grid2(int nxslots, int ny, int bs) { return dim3((nxslots + bs - 1) / bs, ny, 1); }
 
 template <typename T>
@@ -1109,7 +1117,7 @@ extern "C" int b2_sensor_accumulate(b2_sensor* s, int64_t n, const double* x, co
                 B2_TIMED("k_accumulate_slow", st);
                 int64_t want = (cnt + 255) / 256;
                 unsigned blocks = (unsigned)(want < (int64_t)s->sm_count * 8 ? want : (int64_t)s->sm_count * 8);
-                k_accumulate_slow<<<blocks, 256, 0, st>>>(d, (const SlowRec*)s->slow.ptr, s->dnslow, s->dstats,
+                launch_slow(blocks, st, d, (const SlowRec*)s->slow.ptr, s->dnslow, s->dstats,
                                                           s->dadded);
                 B2_CHECK_LAUNCH();
             }
@@ -1172,7 +1180,7 @@ int b2_sensor_run_slow(b2_sensor* s, int64_t n) {
     int64_t want = (n + 255) / 256;
     unsigned blocks = (unsigned)(want < (int64_t)s->sm_count * 8 ? want : (int64_t)s->sm_count * 8);
     if (blocks == 0) return 0;
-    k_accumulate_slow<<<blocks, 256, 0, st>>>(s->d, (const SlowRec*)s->slow.ptr, s->dnslow, s->dstats, s->dadded);
+    launch_slow(blocks, st, s->d, (const SlowRec*)s->slow.ptr, s->dnslow, s->dstats, s->dadded);
     B2_CHECK_LAUNCH();
     return 0;
 }

@@ -92,9 +92,10 @@ __device__ __forceinline__ double table_spline(int n, const double* __restrict__
 
 // walk the polygon of pixel (ax, ay) counter-clockwise starting at the BL corner and
 // call f(n_is, px, py, ex, ey) with the stored point (pixel frame) and the undistorted one
-template <typename F>
+// (NVT > 0: vertex count known at compile time, loops unrolled and the loads independent)
+template <int NVT = 0, typename F>
 __device__ __forceinline__ void walk_polygon(const DevSensor& s, int ax, int ay, F&& f) {
-    const int nv = s.nv;
+    const int nv = NVT > 0 ? NVT : s.nv;
     const float2* hb = s.H + Hidx(s, ax, ay);
     const float2* ht = s.H + Hidx(s, ax, ay + 1);
     const float2* vl = s.V + Vidx(s, ax, ay);
@@ -104,6 +105,7 @@ __device__ __forceinline__ void walk_polygon(const DevSensor& s, int ax, int ay,
         float2 p = hb[0];
         f((double)p.x, (double)p.y, 0.0, 0.0);
     }
+#pragma unroll
     for (int k = 0; k < nv; ++k) {
         float2 p = hb[k + 1];
         f((double)p.x, (double)p.y, s.frac[k], 0.0);
@@ -112,6 +114,7 @@ __device__ __forceinline__ void walk_polygon(const DevSensor& s, int ax, int ay,
         float2 p = hb[nv + 1];
         f((double)p.x, (double)p.y, 1.0, 0.0);
     }
+#pragma unroll
     for (int k = 0; k < nv; ++k) {
         float2 p = vr[k];
         f((double)p.x + 1.0, (double)p.y, 1.0, s.frac[k]);
@@ -120,6 +123,7 @@ __device__ __forceinline__ void walk_polygon(const DevSensor& s, int ax, int ay,
         float2 p = ht[nv + 1];
         f((double)p.x, (double)p.y + 1.0, 1.0, 1.0);
     }
+#pragma unroll
     for (int k = nv - 1; k >= 0; --k) {
         float2 p = ht[k + 1];
         f((double)p.x, (double)p.y + 1.0, s.frac[k], 1.0);
@@ -128,6 +132,7 @@ __device__ __forceinline__ void walk_polygon(const DevSensor& s, int ax, int ay,
         float2 p = ht[0];
         f((double)p.x, (double)p.y + 1.0, 0.0, 1.0);
     }
+#pragma unroll
     for (int k = nv - 1; k >= 0; --k) {
         float2 p = vl[k];
         f((double)p.x, (double)p.y, 0.0, s.frac[k]);
@@ -135,6 +140,7 @@ __device__ __forceinline__ void walk_polygon(const DevSensor& s, int ax, int ay,
 }
 
 // Silicon::insidePixel.  ix, iy: image coordinates.  Returns inside; sets *off_edge like GalSim.
+template <int NVT = 0>
 __device__ __forceinline__ bool inside_pixel(const DevSensor& s, int ix, int iy, double x, double y, double zconv,
                                              bool* off_edge, unsigned& npoly) {
     int ax = ix - s.xmin, ay = iy - s.ymin;
@@ -171,7 +177,7 @@ __device__ __forceinline__ bool inside_pixel(const DevSensor& s, int ix, int iy,
                     }
                 }
             };
-            walk_polygon(s, ax, ay, [&](double px, double py, double ex, double ey) {
+            walk_polygon<NVT>(s, ax, ay, [&](double px, double py, double ex, double ey) {
                 double qx = __dadd_rn(ex, __dmul_rn(__dsub_rn(px, ex), zfactor));
                 double qy = __dadd_rn(ey, __dmul_rn(__dsub_rn(py, ey), zfactor));
                 if (first) {
