@@ -360,30 +360,30 @@ k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __rest
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int cxk = (s.nx9 - 1) / 2, cyk = (s.ny9 - 1) / 2;
+    // Each slot's window of charged pixels is packed once into one 64-bit word, 8 bits per halo row (qdist <= 3:
+    // at most 8 rows of at most 8 columns), lowest bit = first pixel in the reference's (row, column) order, so
+    // the loop below visits exactly the charged pixels with one find-first-set each and no per-row scanning.
     // ---- horizontal slot: rows j = y-q-1 .. y+q (halo rows ty .. ty+2q+1), cols i = x-q .. x+q
     if (x < nx && y <= ny) {
-        const unsigned wmask = (1u << (2 * q + 1)) - 1u;
-        bool any = false;
-        for (int dj = 0; dj < 2 * q + 2; ++dj) any |= ((unsigned)(rowbits[ty + dj] >> (tx + 1)) & wmask) != 0u;
-        if (any) {
+        const unsigned long long wmask = (1ull << (2 * q + 1)) - 1ull;
+        unsigned long long bits = 0ull;
+        for (int dj = 0; dj < 2 * q + 2; ++dj) bits |= ((rowbits[ty + dj] >> (tx + 1)) & wmask) << (8 * dj);
+        if (bits) {
             float2* hp = s.H + Hidx(s, x, y);
             float2 h[NV + 2];
 #pragma unroll
             for (int k = 0; k < NV + 2; ++k) h[k] = hp[k];
-#pragma unroll 1
-            for (int dj = 0; dj < 2 * q + 2; ++dj) {
-                unsigned bits = (unsigned)(rowbits[ty + dj] >> (tx + 1)) & wmask;
-                while (bits) {
-                    int di = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    double c = sc[(ty + dj) * HW + tx + 1 + di];
-                    const float2* kh = KH + ((q + 1 - dj + cyk) * s.nx9 + (q - di + cxk)) * (NV + 2);
+            while (bits) {
+                const int pos = __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+                const int dj = pos >> 3, di = pos & 7;
+                const double c = sc[(ty + dj) * HW + tx + 1 + di];
+                const float2* kh = KH + ((q + 1 - dj + cyk) * s.nx9 + (q - di + cxk)) * (NV + 2);
 #pragma unroll
-                    for (int k = 0; k < NV + 2; ++k) {
-                        float2 d = kh[k];
-                        h[k].x = (float)__dadd_rn((double)h[k].x, __dmul_rn((double)d.x, c));
-                        h[k].y = (float)__dadd_rn((double)h[k].y, __dmul_rn((double)d.y, c));
-                    }
+                for (int k = 0; k < NV + 2; ++k) {
+                    float2 d = kh[k];
+                    h[k].x = (float)__dadd_rn((double)h[k].x, __dmul_rn((double)d.x, c));
+                    h[k].y = (float)__dadd_rn((double)h[k].y, __dmul_rn((double)d.y, c));
                 }
             }
 #pragma unroll
@@ -394,28 +394,25 @@ k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __rest
     }
     // ---- vertical slot: rows j = y-q .. y+q (halo rows ty+1 .. ty+2q+1), cols i = x-q-1 .. x+q
     if (x <= nx && y < ny) {
-        const unsigned wmask = (1u << (2 * q + 2)) - 1u;
-        bool any = false;
-        for (int dj = 1; dj < 2 * q + 2; ++dj) any |= ((unsigned)(rowbits[ty + dj] >> tx) & wmask) != 0u;
-        if (any) {
+        const unsigned long long wmask = (1ull << (2 * q + 2)) - 1ull;
+        unsigned long long bits = 0ull;
+        for (int dj = 1; dj < 2 * q + 2; ++dj) bits |= ((rowbits[ty + dj] >> tx) & wmask) << (8 * (dj - 1));
+        if (bits) {
             float2* vp = s.V + Vidx(s, x, y);
             float2 v[NV];
 #pragma unroll
             for (int k = 0; k < NV; ++k) v[k] = vp[k];
-#pragma unroll 1
-            for (int dj = 1; dj < 2 * q + 2; ++dj) {
-                unsigned bits = (unsigned)(rowbits[ty + dj] >> tx) & wmask;
-                while (bits) {
-                    int di = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    double c = sc[(ty + dj) * HW + tx + di];
-                    const float2* kv = KV + ((q + 1 - dj + cyk) * s.nx9 + (q + 1 - di + cxk)) * NV;
+            while (bits) {
+                const int pos = __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+                const int dj = (pos >> 3) + 1, di = pos & 7;
+                const double c = sc[(ty + dj) * HW + tx + di];
+                const float2* kv = KV + ((q + 1 - dj + cyk) * s.nx9 + (q + 1 - di + cxk)) * NV;
 #pragma unroll
-                    for (int k = 0; k < NV; ++k) {
-                        float2 d = kv[k];
-                        v[k].x = (float)__dadd_rn((double)v[k].x, __dmul_rn((double)d.x, c));
-                        v[k].y = (float)__dadd_rn((double)v[k].y, __dmul_rn((double)d.y, c));
-                    }
+                for (int k = 0; k < NV; ++k) {
+                    float2 d = kv[k];
+                    v[k].x = (float)__dadd_rn((double)v[k].x, __dmul_rn((double)d.x, c));
+                    v[k].y = (float)__dadd_rn((double)v[k].y, __dmul_rn((double)d.y, c));
                 }
             }
 #pragma unroll
@@ -934,7 +931,7 @@ static int launch_update_distortions(b2_sensor* s, bool from_target) {
     cudaStream_t st = ctx->stream;
     B2_TIMED("update_distortions(total)", st);
     B2_CUDA(cudaMemsetAsync(s->changed, 0, (size_t)d.nx * d.ny, st));
-    const bool tiled = (d.nv == 4 || d.nv == 8) && d.qdist <= 7 && getenv("B2_UPDATE_GENERIC") == nullptr;
+    const bool tiled = (d.nv == 4 || d.nv == 8) && d.qdist <= 3 && getenv("B2_UPDATE_GENERIC") == nullptr;
     if (tiled) {
         if (!from_target) return launch_update_tiled<double>(s, d.delta);
         if (d.dtype_bytes == 4) return launch_update_tiled<float>(s, (const float*)d.target);
@@ -967,7 +964,7 @@ static int launch_update_distortions(b2_sensor* s, bool from_target) {
 static int launch_bounds_update(b2_sensor* s, int all) {
     B2_TIMED("k_update_bounds", s->ctx->stream);
     DevSensor& d = s->d;
-    const bool tiled = (d.nv == 4 || d.nv == 8) && d.qdist <= 7 && getenv("B2_UPDATE_GENERIC") == nullptr;
+    const bool tiled = (d.nv == 4 || d.nv == 8) && d.qdist <= 3 && getenv("B2_UPDATE_GENERIC") == nullptr;
     if (tiled && d.nv == 4 && getenv("B2_BOUNDS_GENERIC") == nullptr)
         k_update_bounds_t<4><<<grid2(d.nx, d.ny, 256), 256, 0, s->ctx->stream>>>(d, s->changed, all);
     else if (tiled && d.nv == 8 && getenv("B2_BOUNDS_GENERIC") == nullptr)
