@@ -328,9 +328,10 @@ k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __rest
     const int hcols = TX + 2 * q + 1;  // <= HW
     double* sc = reinterpret_cast<double*>(smem_raw);                       // [hrows][HW]
     unsigned long long* rowbits = reinterpret_cast<unsigned long long*>(sc + MAXHR * HW);  // [MAXHR]
-    float2* KH = reinterpret_cast<float2*>(rowbits + MAXHR);
-    const int nKH = s.nx9 * s.ny9 * (NV + 2), nKV = s.nx9 * s.ny9 * NV;
-    float2* KV = KH + nKH;
+    // the 9 x 9 distortion tables (6.5 / 11.7 KB) are read through the L1 / read-only path: every block touches
+    // all of them, so they stay cached, and not staging them saves a pass and a barrier per tile
+    const float2* __restrict__ KH = s.KH;
+    const float2* __restrict__ KV = s.KV;
     const int tid = threadIdx.y * TX + threadIdx.x;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
     const int nx = s.nx, ny = s.ny;
@@ -354,9 +355,6 @@ k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __rest
         any_local |= (bits != 0ull);
     }
     if (!__syncthreads_or(any_local)) return;  // no charge within reach of this tile
-    for (int k = tid; k < nKH; k += 256) KH[k] = s.KH[k];
-    for (int k = tid; k < nKV; k += 256) KV[k] = s.KV[k];
-    __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int cxk = (s.nx9 - 1) / 2, cyk = (s.ny9 - 1) / 2;
@@ -381,7 +379,7 @@ k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __rest
                 const float2* kh = KH + ((q + 1 - dj + cyk) * s.nx9 + (q - di + cxk)) * (NV + 2);
 #pragma unroll
                 for (int k = 0; k < NV + 2; ++k) {
-                    float2 d = kh[k];
+                    float2 d = __ldg(kh + k);
                     h[k].x = (float)__dadd_rn((double)h[k].x, __dmul_rn((double)d.x, c));
                     h[k].y = (float)__dadd_rn((double)h[k].y, __dmul_rn((double)d.y, c));
                 }
@@ -410,7 +408,7 @@ k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __rest
                 const float2* kv = KV + ((q + 1 - dj + cyk) * s.nx9 + (q + 1 - di + cxk)) * NV;
 #pragma unroll
                 for (int k = 0; k < NV; ++k) {
-                    float2 d = kv[k];
+                    float2 d = __ldg(kv + k);
                     v[k].x = (float)__dadd_rn((double)v[k].x, __dmul_rn((double)d.x, c));
                     v[k].y = (float)__dadd_rn((double)v[k].y, __dmul_rn((double)d.y, c));
                 }
@@ -909,8 +907,7 @@ template <typename CT>
 static int launch_update_tiled(b2_sensor* s, const CT* charge) {
     DevSensor& d = s->d;
     cudaStream_t st = s->ctx->stream;
-    size_t smem = (size_t)24 * 64 * sizeof(double) + 24 * sizeof(unsigned long long) +
-                  (size_t)d.nx9 * d.ny9 * (2 * d.nv + 2) * sizeof(float2);
+    size_t smem = (size_t)24 * 64 * sizeof(double) + 24 * sizeof(unsigned long long);
     dim3 block(32, 8, 1);
     dim3 grid((d.nx + 1 + 31) / 32, (d.ny + 1 + 7) / 8, 1);
     if (d.nv == 4) {
