@@ -355,69 +355,116 @@ k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __rest
         any_local |= (bits != 0ull);
     }
     if (!__syncthreads_or(any_local)) return;  // no charge within reach of this tile
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    const int tx = threadIdx.x, ty = threadIdx.y;
     const int cxk = (s.nx9 - 1) / 2, cyk = (s.ny9 - 1) / 2;
     // Each slot's window of charged pixels is packed once into one 64-bit word, 8 bits per halo row (qdist <= 3:
     // at most 8 rows of at most 8 columns), lowest bit = first pixel in the reference's (row, column) order, so
     // the loop below visits exactly the charged pixels with one find-first-set each and no per-row scanning.
-    // ---- horizontal slot: rows j = y-q-1 .. y+q (halo rows ty .. ty+2q+1), cols i = x-q .. x+q
-    if (x < nx && y <= ny) {
-        const unsigned long long wmask = (1ull << (2 * q + 1)) - 1ull;
+    // Slots without charge in reach (about half of them under star fields) are squeezed out first: the active
+    // slots of the tile are compacted into a list in shared memory and the threads take them in order, so the
+    // lanes of a warp all have work and only differ in how many pixels their slot sees.
+    __shared__ unsigned long long s_bits[TX * TY];
+    __shared__ unsigned short s_slot[TX * TY];
+    constexpr int NBIN = 32;
+    __shared__ int s_bin[NBIN];
+    __shared__ int s_total;
+    const int tx0 = threadIdx.x, ty0 = threadIdx.y;
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {  // 0: horizontal slots, 1: vertical slots
         unsigned long long bits = 0ull;
-        for (int dj = 0; dj < 2 * q + 2; ++dj) bits |= ((rowbits[ty + dj] >> (tx + 1)) & wmask) << (8 * dj);
-        if (bits) {
-            float2* hp = s.H + Hidx(s, x, y);
-            float2 h[NV + 2];
-#pragma unroll
-            for (int k = 0; k < NV + 2; ++k) h[k] = hp[k];
-            while (bits) {
-                const int pos = __ffsll((long long)bits) - 1;
-                bits &= bits - 1;
-                const int dj = pos >> 3, di = pos & 7;
-                const double c = sc[(ty + dj) * HW + tx + 1 + di];
-                const float2* kh = KH + ((q + 1 - dj + cyk) * s.nx9 + (q - di + cxk)) * (NV + 2);
-#pragma unroll
-                for (int k = 0; k < NV + 2; ++k) {
-                    float2 d = __ldg(kh + k);
-                    h[k].x = (float)__dadd_rn((double)h[k].x, __dmul_rn((double)d.x, c));
-                    h[k].y = (float)__dadd_rn((double)h[k].y, __dmul_rn((double)d.y, c));
+        {
+            const int x = x0 + tx0, y = y0 + ty0;
+            if (phase == 0) {
+                // rows j = y-q-1 .. y+q (halo rows ty .. ty+2q+1), cols i = x-q .. x+q
+                if (x < nx && y <= ny) {
+                    const unsigned long long wmask = (1ull << (2 * q + 1)) - 1ull;
+                    for (int dj = 0; dj < 2 * q + 2; ++dj) bits |= ((rowbits[ty0 + dj] >> (tx0 + 1)) & wmask) << (8 * dj);
+                }
+            } else {
+                // rows j = y-q .. y+q (halo rows ty+1 .. ty+2q+1), cols i = x-q-1 .. x+q
+                if (x <= nx && y < ny) {
+                    const unsigned long long wmask = (1ull << (2 * q + 2)) - 1ull;
+                    for (int dj = 1; dj < 2 * q + 2; ++dj) bits |= ((rowbits[ty0 + dj] >> tx0) & wmask) << (8 * (dj - 1));
                 }
             }
-#pragma unroll
-            for (int k = 0; k < NV + 2; ++k) hp[k] = h[k];
-            if (y < ny) changed[(size_t)y * nx + x] = 1;
-            if (y > 0) changed[(size_t)(y - 1) * nx + x] = 1;
         }
-    }
-    // ---- vertical slot: rows j = y-q .. y+q (halo rows ty+1 .. ty+2q+1), cols i = x-q-1 .. x+q
-    if (x <= nx && y < ny) {
-        const unsigned long long wmask = (1ull << (2 * q + 2)) - 1ull;
-        unsigned long long bits = 0ull;
-        for (int dj = 1; dj < 2 * q + 2; ++dj) bits |= ((rowbits[ty + dj] >> tx) & wmask) << (8 * (dj - 1));
-        if (bits) {
-            float2* vp = s.V + Vidx(s, x, y);
-            float2 v[NV];
-#pragma unroll
-            for (int k = 0; k < NV; ++k) v[k] = vp[k];
-            while (bits) {
-                const int pos = __ffsll((long long)bits) - 1;
-                bits &= bits - 1;
-                const int dj = (pos >> 3) + 1, di = pos & 7;
-                const double c = sc[(ty + dj) * HW + tx + di];
-                const float2* kv = KV + ((q + 1 - dj + cyk) * s.nx9 + (q + 1 - di + cxk)) * NV;
-#pragma unroll
-                for (int k = 0; k < NV; ++k) {
-                    float2 d = __ldg(kv + k);
-                    v[k].x = (float)__dadd_rn((double)v[k].x, __dmul_rn((double)d.x, c));
-                    v[k].y = (float)__dadd_rn((double)v[k].y, __dmul_rn((double)d.y, c));
-                }
+        // counting sort of the active slots by the number of charged pixels they see (descending), so that the
+        // 32 slots a warp takes have similar trip counts: the loop below then runs with nearly full warps
+        const int cnt = __popcll(bits);
+        const int bin = cnt == 0 ? -1 : (NBIN - 1 - min(cnt - 1, NBIN - 1));  // bin 0 = most pixels
+        if (tid < NBIN) s_bin[tid] = 0;
+        __syncthreads();
+        int rank = 0;
+        if (bin >= 0) rank = atomicAdd(&s_bin[bin], 1);
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int b = 0; b < NBIN; ++b) {
+                int c = s_bin[b];
+                s_bin[b] = t;
+                t += c;
             }
-#pragma unroll
-            for (int k = 0; k < NV; ++k) vp[k] = v[k];
-            if (x < nx) changed[(size_t)y * nx + x] = 1;
-            if (x > 0) changed[(size_t)y * nx + x - 1] = 1;
+            s_total = t;
         }
+        __syncthreads();
+        if (bin >= 0) {
+            const int k = s_bin[bin] + rank;
+            s_bits[k] = bits;
+            s_slot[k] = (unsigned short)tid;
+        }
+        __syncthreads();
+        const int total = s_total;
+        if (tid < total) {
+            bits = s_bits[tid];
+            const int sid = s_slot[tid];
+            const int tx = sid & 31, ty = sid >> 5;
+            const int x = x0 + tx, y = y0 + ty;
+            if (phase == 0) {
+                float2* hp = s.H + Hidx(s, x, y);
+                float2 h[NV + 2];
+#pragma unroll
+                for (int k = 0; k < NV + 2; ++k) h[k] = hp[k];
+                while (bits) {
+                    const int pos = __ffsll((long long)bits) - 1;
+                    bits &= bits - 1;
+                    const int dj = pos >> 3, di = pos & 7;
+                    const double c = sc[(ty + dj) * HW + tx + 1 + di];
+                    const float2* kh = KH + ((q + 1 - dj + cyk) * s.nx9 + (q - di + cxk)) * (NV + 2);
+#pragma unroll
+                    for (int k = 0; k < NV + 2; ++k) {
+                        float2 d = __ldg(kh + k);
+                        h[k].x = (float)__dadd_rn((double)h[k].x, __dmul_rn((double)d.x, c));
+                        h[k].y = (float)__dadd_rn((double)h[k].y, __dmul_rn((double)d.y, c));
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NV + 2; ++k) hp[k] = h[k];
+                if (y < ny) changed[(size_t)y * nx + x] = 1;
+                if (y > 0) changed[(size_t)(y - 1) * nx + x] = 1;
+            } else {
+                float2* vp = s.V + Vidx(s, x, y);
+                float2 v[NV];
+#pragma unroll
+                for (int k = 0; k < NV; ++k) v[k] = vp[k];
+                while (bits) {
+                    const int pos = __ffsll((long long)bits) - 1;
+                    bits &= bits - 1;
+                    const int dj = (pos >> 3) + 1, di = pos & 7;
+                    const double c = sc[(ty + dj) * HW + tx + di];
+                    const float2* kv = KV + ((q + 1 - dj + cyk) * s.nx9 + (q + 1 - di + cxk)) * NV;
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) {
+                        float2 d = __ldg(kv + k);
+                        v[k].x = (float)__dadd_rn((double)v[k].x, __dmul_rn((double)d.x, c));
+                        v[k].y = (float)__dadd_rn((double)v[k].y, __dmul_rn((double)d.y, c));
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NV; ++k) vp[k] = v[k];
+                if (x < nx) changed[(size_t)y * nx + x] = 1;
+                if (x > 0) changed[(size_t)y * nx + x - 1] = 1;
+            }
+        }
+        __syncthreads();  // the lists are reused by the next phase
     }
 }
 
