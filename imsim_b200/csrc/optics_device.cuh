@@ -229,8 +229,12 @@ __device__ __forceinline__ void diffraction_kick(const B2Diffraction& c, double 
         px = cs * pu - sn * pv;  // R^T pos
         py = sn * pu + cs * pv;
     }
+    // fixed trip counts (B2Diffraction holds at most 8 lines and 4 circles; Rubin has 4 and 2): unrolled, so the
+    // distances are independent instruction streams instead of a loop with a branch per vane
     double min_line = INFINITY, lnx = 0.0, lny = 0.0;
-    for (int k = 0; k < c.n_lines; ++k) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (k >= c.n_lines) break;
         double d = fabs(fabs(c.lines[k][0] * px + c.lines[k][1] * py - c.lines[k][2]) - c.lines[k][3]);
         if (d < min_line) {
             min_line = d;
@@ -239,7 +243,9 @@ __device__ __forceinline__ void diffraction_kick(const B2Diffraction& c, double 
         }
     }
     double min_circ = INFINITY, cdx = 0.0, cdy = 0.0, icnrm = 1.0;
-    for (int k = 0; k < c.n_circles; ++k) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k >= c.n_circles) break;
         double dx = px - c.circles[k][0], dy = py - c.circles[k][1];
         double r2 = dx * dx + dy * dy;
         double inr = b2rsqrt(r2);

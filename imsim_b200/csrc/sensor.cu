@@ -820,6 +820,15 @@ extern "C" int b2_sensor_create(b2_ctx* ctx, const B2SensorConfig* cfg, const do
         B2_REQUIRE(abs_w && abs_l, "b2_sensor_create: absorption table missing");
         if (dev_upload(ctx, s->owned, abs_w, (size_t)d.nabs, &d.abs_w)) return 1;
         if (dev_upload(ctx, s->owned, abs_l, (size_t)d.nabs, &d.abs_l)) return 1;
+        // uniformly spaced wavelengths (GalSim's absorption.dat is, 5 nm): index by arithmetic instead of a search
+        d.abs_x0 = abs_w[0];
+        d.abs_inv_dx = 0.0;
+        if (d.nabs >= 3) {
+            const double dx = (abs_w[d.nabs - 1] - abs_w[0]) / (d.nabs - 1);
+            bool uniform = dx > 0.0;
+            for (int k = 1; k < d.nabs && uniform; ++k) uniform = fabs(abs_w[k] - (abs_w[0] + k * dx)) <= 1e-9 * dx;
+            if (uniform) d.abs_inv_dx = 1.0 / dx;
+        }
     }
     void* p = nullptr;
     B2_CUDA(cudaMalloc(&p, ST_N * sizeof(unsigned long long) + 64));

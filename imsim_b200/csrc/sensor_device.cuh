@@ -16,6 +16,7 @@ struct DevSensor {
     double tr_max;
     const double *tr_r, *tr_f, *tr_y2;
     const double *abs_w, *abs_l;
+    double abs_x0, abs_inv_dx;  // uniform absorption table: direct index (inv_dx = 0: binary search)
     const float2 *KH, *KV;
     float2 *H, *V;
     double *inner, *outer;
@@ -66,11 +67,25 @@ __device__ __forceinline__ int table_index(int n, const double* __restrict__ x, 
     return hi;
 }
 
+// the same index for a uniformly spaced table without the search: a guess from the spacing, corrected against
+// the table itself so that it is exactly the index the search returns (first node above a)
+__device__ __forceinline__ int table_index_uniform(int n, const double* __restrict__ x, double a, double x0,
+                                                   double inv_dx) {
+    if (a <= __ldg(x)) return 1;
+    if (a >= __ldg(x + n - 1)) return n - 1;
+    int i = (int)((a - x0) * inv_dx) + 1;
+    i = min(max(i, 1), n - 1);
+    if (a < __ldg(x + i - 1)) --i;
+    else if (a >= __ldg(x + i)) ++i;
+    return min(max(i, 1), n - 1);
+}
+
 // GalSim Table.cpp linear / spline interpolation; explicit _rn ops: no FMA contraction,
 // so the values match the host (non-FMA) evaluation bit for bit
-__device__ __forceinline__ double table_linear(int n, const double* __restrict__ x, const double* __restrict__ f, double a) {
+__device__ __forceinline__ double table_linear(int n, const double* __restrict__ x, const double* __restrict__ f, double a,
+                                               double x0 = 0.0, double inv_dx = 0.0) {
     a = fmin(fmax(a, __ldg(x)), __ldg(x + n - 1));
-    int i = table_index(n, x, a);
+    int i = inv_dx != 0.0 ? table_index_uniform(n, x, a, x0, inv_dx) : table_index(n, x, a);
     double xi = __ldg(x + i), xm = __ldg(x + i - 1);
     double ax = __ddiv_rn(__dsub_rn(xi, a), __dsub_rn(xi, xm));
     double bx = __dsub_rn(1.0, ax);
@@ -229,7 +244,7 @@ __device__ __forceinline__ bool sensor_fast_path(const DevSensor& s, double x0, 
     // calculateConversionDepth
     double dz;
     if (has_wl) {
-        double abs_length = table_linear(s.nabs, s.abs_w, s.abs_l, wl_nm);
+        double abs_length = table_linear(s.nabs, s.abs_w, s.abs_l, wl_nm, s.abs_x0, s.abs_inv_dx);
         double si_length = __dmul_rn(-abs_length, log(__dsub_rn(1.0, udep)));
         if (has_angles) {
             double nrm = sqrt(__dadd_rn(__dadd_rn(1.0, __dmul_rn(a, a)), __dmul_rn(b, b)));
