@@ -43,7 +43,7 @@ k_trace_rays(const __grid_constant__ DevOptics o, int64_t n, double* x, double* 
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Ray r{x[i], y[i], z[i], vx[i], vy[i], vz[i], t[i], vig[i] != 0, fail[i] != 0};
-    trace_ray<PROG>(o, r, wl[i]);
+    trace_ray<PROG>(o, media_of<PROG>(o, wl[i]), r);
     x[i] = r.x; y[i] = r.y; z[i] = r.z;
     vx[i] = r.vx; vy[i] = r.vy; vz[i] = r.vz;
     t[i] = r.t;
@@ -300,7 +300,14 @@ extern "C" int b2_telescope_upload(b2_ctx* ctx, const B2Telescope* tel) {
     o.n_surf = tel->n_surfaces;
     o.n_media = tel->n_media;
     o.medium_stop = tel->medium_stop;
-    for (int m = 0; m < tel->n_media; ++m) o.media[m] = tel->media[m];
+    for (int m = 0; m < tel->n_media; ++m) {
+        o.media[m] = tel->media[m];
+        if (o.media[m].kind == B2_MED_AIR) {  // photon-independent factors of batoid.Air, see medium_n()
+            const double P = o.media[m].p[0] * 7.50061683, T = o.media[m].p[1] - 273.15, W = o.media[m].p[2] * 7.50061683;
+            o.media[m].p[3] = P * (1.0 + (1.049 - 0.0157 * T) * 1.e-6 * P) / (720.883 * (1.0 + 0.003661 * T));
+            o.media[m].p[4] = W * 1.e-6 / (1.0 + 0.003661 * T);
+        }
+    }
     for (int i = 0; i < tel->n_surfaces; ++i) {
         const B2Surface& s = tel->surf[i];
         DevSurf& d = o.surf[i];

@@ -58,14 +58,13 @@ __device__ __forceinline__ double medium_n(const B2Medium& m, double wl) {
             double y = b2rcp(x);
             return b2sqrt(m.p[0] + m.p[1] * x + y * (m.p[2] + y * (m.p[3] + y * (m.p[4] + y * m.p[5]))));
         }
-        default: {  // B2_MED_AIR; the pressure / temperature factors are uniform and hoisted by the compiler
-            double P = m.p[0] * 7.50061683;
-            double T = m.p[1] - 273.15;
-            double W = m.p[2] * 7.50061683;
+        default: {  // B2_MED_AIR; the pressure / temperature factors do not depend on the photon: p[3], p[4] hold
+                    // P (1 + (1.049 - 0.0157 T) 1e-6 P) / (720.883 (1 + 0.003661 T)) and W 1e-6 / (1 + 0.003661 T),
+                    // filled in by b2_telescope_upload
             double s2 = 1e-12 * b2rcp(wl * wl);
             double nm1 = (64.328 + 29498.1 * b2rcp(146.0 - s2) + 255.4 * b2rcp(41.0 - s2)) * 1.e-6;
-            nm1 *= P * (1.0 + (1.049 - 0.0157 * T) * 1.e-6 * P) / (720.883 * (1.0 + 0.003661 * T));
-            nm1 -= (0.0624 - 0.000680 * s2) / (1.0 + 0.003661 * T) * W * 1.e-6;
+            nm1 *= m.p[3];
+            nm1 -= (0.0624 - 0.000680 * s2) * m.p[4];
             return 1.0 + nm1;
         }
     }
@@ -653,10 +652,9 @@ __device__ __forceinline__ void lsst_steps(const DevOptics& o, const Refr& air_g
     }
 }
 
-// batoid CompoundOptic.trace: sequential interfaces
+// refractive indices and their inverses, once per photon per medium
 template <int PROG>
-__device__ __forceinline__ void trace_ray(const DevOptics& o, Ray& r, double wl) {
-    // refractive indices and their inverses, once per photon per medium
+__device__ __forceinline__ MediaN media_of(const DevOptics& o, double wl) {
     MediaN mn;
     if constexpr (PROG == B2_PROG_LSST) {
         mn.n[0] = medium_n(o.media[0], wl);
@@ -665,8 +663,6 @@ __device__ __forceinline__ void trace_ray(const DevOptics& o, Ray& r, double wl)
         mn.inv[0] = b2rcp(mn.n[0]);
         mn.inv[1] = b2rcp(mn.n[1]);
         mn.inv[2] = mn.inv[3] = 1.0;
-        const Refr ag = make_refr(mn, 0, 1), ga = make_refr(mn, 1, 0);
-        lsst_steps<0>(o, ag, ga, r);
     } else {
         mn.n[0] = medium_n(o.media[0], wl);
         mn.n[1] = o.n_media > 1 ? medium_n(o.media[1], wl) : 1.0;
@@ -674,6 +670,17 @@ __device__ __forceinline__ void trace_ray(const DevOptics& o, Ray& r, double wl)
         mn.n[3] = o.n_media > 3 ? medium_n(o.media[3], wl) : 1.0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) mn.inv[k] = b2rcp(mn.n[k]);
+    }
+    return mn;
+}
+
+// batoid CompoundOptic.trace: sequential interfaces
+template <int PROG>
+__device__ __forceinline__ void trace_ray(const DevOptics& o, const MediaN& mn, Ray& r) {
+    if constexpr (PROG == B2_PROG_LSST) {
+        const Refr ag = make_refr(mn, 0, 1), ga = make_refr(mn, 1, 0);
+        lsst_steps<0>(o, ag, ga, r);
+    } else {
 #pragma unroll 1
         for (int is = 0; is < o.n_surf; ++is) {
             const DevSurf& s = o.surf[is];
@@ -726,7 +733,8 @@ __device__ __forceinline__ OpticsOut optics_photon(const DevOptics& o, const B2O
     }
     Ray r;
     xy_to_v(o, xi, yi, r.vx, r.vy, r.vz);
-    double inair = b2rcp(medium_n(o.media[o.medium_stop], wl));
+    const MediaN mn = media_of<PROG>(o, wl);  // the stop medium's index is one of these: computed once
+    const double inair = media_pick(mn.inv, o.medium_stop);
     r.vx *= inair;
     r.vy *= inair;
     r.vz *= inair;
@@ -737,7 +745,7 @@ __device__ __forceinline__ OpticsOut optics_photon(const DevOptics& o, const B2O
     r.t = 0.0;
     r.vignetted = false;
     r.failed = false;
-    trace_ray<PROG>(o, r, wl);
+    trace_ray<PROG>(o, mn, r);
     out.vig = r.vignetted;
     out.fail = r.failed;
     out.offz = !out.vig && !(fabs(r.z) < 1.0e-15);
