@@ -792,7 +792,7 @@ __device__ __forceinline__ void sample_time_pupil(uint64_t seed, uint64_t idx, d
     philox4(seed, idx, 2u, q);
     double ut = u01(r[0], r[1]), ur = u01(r[2], r[3]), uphi = u01(q[0], q[1]);
     time = t0 + exptime * ut;
-    double rr = sqrt(r_in * r_in + (r_out * r_out - r_in * r_in) * ur);
+    double rr = b2sqrt_fast(r_in * r_in + (r_out * r_out - r_in * r_in) * ur);
     double sn, cs;
     sincospi(2.0 * uphi, &sn, &cs);
     pu = rr * cs;

@@ -766,6 +766,8 @@ extern "C" int b2_sensor_create(b2_ctx* ctx, const B2SensorConfig* cfg, const do
     d.diff_step = cfg->diff_step;
     d.pixel_size = cfg->pixel_size;
     d.thickness = cfg->sensor_thickness;
+    d.inv_pixel_size = 1. / d.pixel_size;
+    d.diff_step_pixel_z = d.diff_step / (d.thickness * d.pixel_size);
     d.trc[0] = cfg->treering_center[0];
     d.trc[1] = cfg->treering_center[1];
     // undistorted edge points (GalSim buildEmptyPoly)

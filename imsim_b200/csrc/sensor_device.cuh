@@ -12,6 +12,7 @@ struct DevSensor {
     int xmin, ymin, nx, ny;
     int ntr, nabs, tr_spline, pad;
     double diff_step, pixel_size, thickness;
+    double inv_pixel_size, diff_step_pixel_z;  // 1 / pixel_size and diff_step / (thickness * pixel_size), from the host
     double trc[2];
     double tr_max;
     const double *tr_r, *tr_f, *tr_y2;
@@ -239,8 +240,8 @@ __device__ __forceinline__ bool sensor_fast_path(const DevSensor& s, double x0, 
                                                  double unf, double udep, SlowRec& rec, double& my_added, unsigned& nb9,
                                                  unsigned& ndrop) {
     const double T = s.thickness;
-    const double invPixelSize = 1. / s.pixel_size;
-    const double diffStep_pixel_z = s.diff_step / (T * s.pixel_size);
+    const double invPixelSize = s.inv_pixel_size;         // the same IEEE quotients the reference forms per call,
+    const double diffStep_pixel_z = s.diff_step_pixel_z;  // computed once on the host
     // calculateConversionDepth
     double dz;
     if (has_wl) {

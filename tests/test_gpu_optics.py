@@ -424,3 +424,24 @@ def test_opd_screen():
     shift = np.median(res["screen"][0][0][good] - res["plain"][0][0][good])
     # wavefront tilt 2e-7 / 4.18 rad x effective focal length 10.31 m ~ 4.9e-7 m, sign set by the three mirrors
     assert 3e-7 < abs(shift) < 7e-7
+
+
+def test_time_and_pupil_samplers():
+    """galsim.TimeSampler / PupilAnnulusSampler (config/imsim-config.yaml:281-289): times uniform over the exposure,
+    pupil positions uniform over the annulus, reproducible from (seed, photon offset)."""
+    ctx = _ctx()
+    n = 2_000_000
+    t, u, v = np.empty(n), np.empty(n), np.empty(n)
+    ctx.sample_time_pupil(t, u, v, 5.0, 30.0, 2.558, 4.18, 99, 0)
+    assert t.min() >= 5.0 and t.max() <= 35.0 and abs(t.mean() - 20.0) < 0.03 and abs(t.var() - 900.0 / 12) < 0.3
+    r2 = u * u + v * v
+    assert r2.min() >= 2.558**2 * (1 - 1e-12) and r2.max() <= 4.18**2 * (1 + 1e-12)
+    # uniform in r^2 and in azimuth
+    assert abs(r2.mean() - 0.5 * (2.558**2 + 4.18**2)) < 0.01
+    ph = np.arctan2(v, u)
+    assert abs(np.cos(ph).mean()) < 3e-3 and abs(np.sin(2 * ph).mean()) < 3e-3
+    assert abs(np.corrcoef(t, r2)[0, 1]) < 3e-3
+    # the second half regenerated with an offset equals the first call's second half
+    t2, u2, v2 = np.empty(n // 2), np.empty(n // 2), np.empty(n // 2)
+    ctx.sample_time_pupil(t2, u2, v2, 5.0, 30.0, 2.558, 4.18, 99, n // 2)
+    assert np.array_equal(t2, t[n // 2:]) and np.array_equal(u2, u[n // 2:]) and np.array_equal(v2, v[n // 2:])
