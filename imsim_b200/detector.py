@@ -52,6 +52,10 @@ class DetectorGeometry:
         return d
 
 
+#: ITL rafts of LSSTCam (the other science rafts carry e2v CCDs)
+ITL_RAFTS = {"R01", "R02", "R03", "R10", "R20", "R41", "R42", "R43"}
+
+
 def lsstcam_like(det_name: str = "R22_S11") -> DetectorGeometry:
     """Synthetic LSSTCam-like science CCD: 10 micron pixels, 42.25 mm CCD pitch,
     127 mm raft pitch.  R22_S11 reproduces the reference's golden vector
@@ -59,9 +63,11 @@ def lsstcam_like(det_name: str = "R22_S11") -> DetectorGeometry:
     rx, ry, sx, sy = int(det_name[1]), int(det_name[2]), int(det_name[5]), int(det_name[6])
     cx = (rx - 2) * 127.0 + (sx - 1) * 42.25
     cy = (ry - 2) * 127.0 + (sy - 1) * 42.25
+    # e2v CCDs have 4096 x 4004 imaging pixels (16 segments of 512 x 2002), ITL ones 4072 x 4000 (509 x 2000)
+    nx, ny = (4072, 4000) if det_name[:3] in ITL_RAFTS else (4096, 4004)
     A = np.array([[100.0, 0.0], [0.0, 100.0]])
-    b = np.array([2047.5 - 100.0 * cx, 2001.5 - 100.0 * cy])
-    return DetectorGeometry(det_name, A, b, nx=4096, ny=4004)
+    b = np.array([(nx - 1) / 2.0 - 100.0 * cx, (ny - 1) / 2.0 - 100.0 * cy])
+    return DetectorGeometry(det_name, A, b, nx=nx, ny=ny)
 
 
 def lsstcam_science_detectors():

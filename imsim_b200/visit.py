@@ -25,8 +25,7 @@ from .photon_pooling import DevicePhotons, PhotonPool, photon_batch_counts
 from .sensor import Image, SiliconSensor
 from .synthetic import gpu_tracer, make_detector_setup
 
-#: ITL rafts of LSSTCam (the rest of the science rafts carry e2v CCDs)
-ITL_RAFTS = {"R01", "R02", "R03", "R10", "R20", "R41", "R42", "R43"}
+from .detector import ITL_RAFTS  # noqa: E402  (ITL rafts of LSSTCam; the rest of the science rafts carry e2v CCDs)
 
 
 def vendor_of(det_name: str) -> str:

@@ -108,3 +108,33 @@ def test_detector_runner_from_catalogue_rows_behind_the_atmosphere():
     assert fs > 0.9 * 400000 * 0.95 and fg > 0.8 * 400000 * 0.95
     # star: atmosphere 0.75'' FWHM + optics ~ 2-3 px rms; galaxy: exponential hlr 1.5'' = 7.5 px adds ~ 10 px rms
     assert 1.0 < ws < 6.0 and wg > ws + 4.0
+
+
+def test_itl_detector_full_chain():
+    """An ITL CCD (4072 x 4000, 509 x 2000 segments, no midline bleed stop) through the whole chain: catalogue rows,
+    Gaussian PSF, optics, silicon, sky, readout."""
+    from imsim_b200.atmosphere import GaussianPSF
+    from imsim_b200.flat import wavelength_cdf
+    from imsim_b200.visit import DetectorRunner, synthetic_catalog, vendor_of
+
+    assert vendor_of("R01_S00") == "itl"
+    models = {"e2v": helpers.sensor_model("lsst_e2v_50_4"), "itl": helpers.sensor_model("lsst_itl_50_4")}
+    runner = DetectorRunner(0, models, helpers.absorption(), psf=GaussianPSF(0.7))
+    wave = np.linspace(550, 690, 15)
+    seds = [wavelength_cdf(wave, 1.0 + 0.1 * k * (wave - 550) / 140) for k in range(8)]
+    cdf = (np.array([c for c, _ in seds]), np.array([w for _, w in seds]))
+    cat = synthetic_catalog(400, 4072, 4000, seed=5, total_photons=2e6)
+    rec, image = runner.run("R01_S00", cat, nbatch=4, wavelength_cdf=cdf, readout=True, sky_level=300.0)
+    assert image.array.shape == (4000, 4072) and runner.last_raw.shape == (16, 2048, 576)
+    _, flux = cat.build()
+    assert rec["photons"] == int(flux.sum()), (rec["photons"], flux.sum())
+    # R01 sits 1.6 deg off axis, where the Rubin-like prescription vignettes about half the pupil
+    assert 0.3 * rec["photons"] < rec["electrons"] <= rec["photons"], (rec["photons"], rec["electrons"])
+    sky = image.array.astype(np.float64).sum() - rec["electrons"]
+    npix = 4000 * 4072
+    assert abs(sky / npix - (300.0 + 0.64)) < 0.05  # sky through the pixel areas + dark current
+    raw = runner.last_raw
+    # imaging area of an ITL segment: 3 prescan columns, 509 data columns, 2000 rows
+    data = raw[:, :2000, 3:512].astype(np.float64)
+    assert abs(data.mean() - (1000.0 + (300.64 + rec["electrons"] / npix) / 1.5 - 0.5)) < 0.5
+    assert abs(raw[:, 2010:, 520:].astype(np.float64).mean() - 999.5) < 0.1  # overscan corner: bias only
