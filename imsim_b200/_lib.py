@@ -193,3 +193,13 @@ def ptr(a, dtype=np.float64):
     if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags.c_contiguous:
         raise B2Error("host arrays must be C-contiguous numpy %s" % np.dtype(dtype).name)
     return C.c_void_p(a.ctypes.data)
+
+
+def h2d_async(arr, device):
+    """numpy array -> CUDA tensor without synchronising the stream: staged through torch's caching pinned-host
+    allocator (which holds the staging block until the copy has run) and copied with ``non_blocking=True``.
+    ``torch.as_tensor(arr, device=...)`` of pageable memory ends in a ``cudaStreamSynchronize``, which stops the
+    host from queueing work ahead of the GPU (visit.DetectorRunner relies on running ahead)."""
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(arr)).pin_memory().to(device, non_blocking=True)

@@ -293,7 +293,7 @@ class PhotonPool:
         if fused is None:
             fused = bool(sample) and self.sensor.pod.nrecalc == 0.0
         if fused:
-            return self._process_fused(dp, image, resume, recalc, want_stats, write_back)
+            return self._process_fused(dp, image, resume, recalc, want_stats, write_back, prebound)
         if sample:
             self.ctx.sample_time_pupil(dp.time, dp.pupil_u, dp.pupil_v, self.t0, self.exptime, self.r_inner,
                                        self.r_outer, self.seed, self.offset)
@@ -307,13 +307,13 @@ class PhotonPool:
                                        want_stats=want_stats, prebound=prebound)
         return added, stats
 
-    def _process_fused(self, dp, image, resume, recalc, want_stats, write_back):
+    def _process_fused(self, dp, image, resume, recalc, want_stats, write_back, prebound=False):
         import ctypes as C
 
         sensor = self.sensor
         if resume and image is not sensor._last_image:
             raise _lib.B2Error("image must be the same as used for the last accumulate call if resume is True")
-        if not resume:
+        if not resume and not prebound:  # prebound: SiliconSensor.bind_stamp put a zero image on the device
             sensor._bind(image)
         sensor._last_image = image
         self.opt.photon_offset = self.offset

@@ -114,10 +114,20 @@ class CcdReadout:
             pods.append(p)
         self._pods = (_abi.B2Amp * len(pods))(*pods)
         raw_nx, raw_ny = self.amps[0].raw_nx, self.amps[0].raw_ny
-        self.pband = None if pcti == 0 else cte_band(raw_ny, pcti, ntransfers)
-        self.sband = None if scti == 0 else cte_band(raw_nx, scti, ntransfers)
-        self.xtalk = None if xtalk is None else np.ascontiguousarray(xtalk, dtype=np.float64)
+        # the tables b2_readout copies to the device on every call live in pinned host memory: a cudaMemcpyAsync
+        # from pageable memory of this size waits for the stream, which would stop the caller from queueing the
+        # next detector behind this one (visit.DetectorRunner.run_many)
+        self.pband = None if pcti == 0 else self._pin(cte_band(raw_ny, pcti, ntransfers))
+        self.sband = None if scti == 0 else self._pin(cte_band(raw_nx, scti, ntransfers))
+        self.xtalk = None if xtalk is None else self._pin(np.ascontiguousarray(xtalk, dtype=np.float64))
         self.shape = (len(pods), raw_ny, raw_nx)
+
+    def _pin(self, arr: np.ndarray) -> np.ndarray:
+        import torch
+
+        t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+        self._pinned = getattr(self, "_pinned", []) + [t]  # owns the memory of the returned view
+        return t.numpy()
 
     def build_amp_images(self, eimage, seed: int = 0, want_segments: bool = False):
         import torch

@@ -244,8 +244,8 @@ class Stage1:
         dev = "cuda:%d" % ctx.device
         self.device = dev
         self.n_obj = int(objects.size)
-        raw = np.frombuffer(np.ascontiguousarray(objects).tobytes(), dtype=np.uint8)
-        self.objects = torch.as_tensor(raw.copy(), device=dev)
+        raw = np.ascontiguousarray(objects).view(np.uint8).reshape(-1)
+        self.objects = _lib.h2d_async(raw, dev)  # no stream synchronisation: callers queue work ahead of the GPU
         if sed_cdf is not None:
             sed_cdf = np.atleast_2d(np.asarray(sed_cdf, np.float64))
             sed_wave = np.atleast_2d(np.asarray(sed_wave, np.float64))
@@ -253,8 +253,8 @@ class Stage1:
                 sed_wave = np.repeat(sed_wave, sed_cdf.shape[0], axis=0)
             assert sed_cdf.shape == sed_wave.shape
             assert objects.size == 0 or int(objects["sed"].max()) < sed_cdf.shape[0]
-            self.cdf = torch.as_tensor(np.ascontiguousarray(sed_cdf), device=dev)
-            self.cdf_wave = torch.as_tensor(np.ascontiguousarray(sed_wave), device=dev)
+            self.cdf = _lib.h2d_async(sed_cdf, dev)
+            self.cdf_wave = _lib.h2d_async(sed_wave, dev)
         else:
             self.cdf = self.cdf_wave = None
         if radial_tables is not None:
@@ -268,17 +268,19 @@ class Stage1:
     def shoot(self, dp, counts: np.ndarray, seed: int, photon_offset: int = 0, select: Optional[np.ndarray] = None,
               rand=None):
         """Fill ``dp`` (DevicePhotons with x, y, flux, wavelength) with ``counts[j]`` photons of object j
-        (``select``: the object rows ``counts`` refers to; default all)."""
-        torch = self.torch
+        (``select``: the object rows ``counts`` refers to; default all).  Nothing here waits for the GPU: the
+        small index tables go up through pinned staging, so batches can be queued ahead of the device."""
         counts = np.asarray(counts, dtype=np.int64)
         n = int(counts.sum())
         assert dp.n == n
-        cum = torch.as_tensor(np.concatenate([[0], np.cumsum(counts)]).astype(np.int64), device=self.device)
+        cum_h = np.zeros(counts.size + 1, dtype=np.int64)
+        np.cumsum(counts, out=cum_h[1:])
+        cum = _lib.h2d_async(cum_h, self.device)
         if select is None:
             objs = self.objects
             nobj = self.n_obj
         else:
-            sel = torch.as_tensor(np.asarray(select, dtype=np.int64), device=self.device)
+            sel = _lib.h2d_async(np.asarray(select, dtype=np.int64), self.device)
             objs = self.objects.view(self.n_obj, -1)[sel].contiguous().view(-1)
             nobj = int(sel.shape[0])
         assert counts.size == nobj

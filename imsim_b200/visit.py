@@ -14,10 +14,12 @@ No collective on the photon path; ``sharding.gather_visit_metadata`` collects pe
 from __future__ import annotations
 
 import time
-from typing import Dict
+from dataclasses import dataclass
+from typing import Dict, Optional
 
 import numpy as np
 
+from . import _lib
 from .context import OpticsContext
 from .detector import lsstcam_like
 from .diffraction import RUBIN_LATITUDE, diffraction_config
@@ -77,8 +79,49 @@ def synthetic_catalog(n_obj: int, nx: int, ny: int, seed: int, total_photons: fl
     return tab
 
 
+@dataclass
+class PreparedDetector:
+    """Everything of one detector that the host computes before the first kernel can be queued."""
+    det_name: str
+    det_index: int
+    det: object
+    setup: object
+    catalogue: bool
+    objects: object
+    rows: Optional[np.ndarray]
+    oflux: np.ndarray
+    radial: Optional[np.ndarray]
+    wavelength_cdf: Optional[tuple]
+    counts: list
+    batches: list  # per batch: (n_photons, object indices, their counts)
+    nbatch: int
+    readout: bool
+    sky_level: float
+    setup_s: float
+
+
+@dataclass
+class LaunchedDetector:
+    """A detector whose work is queued on the stream; ``DetectorRunner.finish`` waits for it."""
+    prep: PreparedDetector
+    image: Image
+    raw: Optional[np.ndarray]
+    electrons: object
+    events: tuple
+    n_total: int
+    keep: list
+
+
 class DetectorRunner:
-    """Reusable per-GPU state: one context, one sensor object per vendor model (re-bound per detector)."""
+    """Reusable per-GPU state: one context, one sensor object per vendor model (re-bound per detector).
+
+    A detector goes through three phases so that a visit can be software-pipelined (``run_many``):
+    ``prepare`` -- host work only (telescope + WCS fit to chief rays, catalogue rows, the integer photon
+    split of imsim/photon_pooling.py:279-313, per-batch index tables); its few chief-ray traces run on a
+    second context with its own high-priority stream, so they do not queue behind another detector's kernels;
+    ``launch`` -- every upload, kernel and read-back of the detector queued on the compute stream without
+    waiting for the GPU (index tables go through pinned staging, the image is bound as zeros on the device);
+    ``finish`` -- wait, collect the record.  ``run`` is the three in sequence."""
 
     def __init__(self, device: int, sensor_models: Dict[str, tuple], absorption_table, tree_rings=None,
                  band: str = "r", rot_tel_pos: float = np.radians(60.0), altitude=np.radians(67.0),
@@ -87,8 +130,12 @@ class DetectorRunner:
 
         self.torch = torch
         self.device = device
-        self.ctx = OpticsContext(device=device, stream=torch.cuda.current_stream(torch.device("cuda", device)))
-        self.tracer = gpu_tracer(self.ctx)
+        dev = torch.device("cuda", device)
+        self.ctx = OpticsContext(device=device, stream=torch.cuda.current_stream(dev))
+        # set-up queries (chief rays, field angles of the catalogue rows) on their own stream
+        self.setup_stream = torch.cuda.Stream(dev, priority=-1)
+        self.setup_ctx = OpticsContext(device=device, stream=self.setup_stream)
+        self.tracer = gpu_tracer(self.setup_ctx)
         self.sensor_models = sensor_models
         self.absorption = absorption_table
         self.tree_rings = tree_rings or {}
@@ -97,6 +144,7 @@ class DetectorRunner:
         self._sensors: Dict[tuple, SiliconSensor] = {}
         self._readouts: Dict[str, object] = {}
         self._pin: Dict[tuple, object] = {}
+        self._slot = 0
         self.last_incident_flux = None
         self.last_raw = None
         #: stage-1 PSF (``atmosphere.AtmosphericPSF`` / ``GaussianPSF``): one realisation per visit, shared by the
@@ -125,84 +173,115 @@ class DetectorRunner:
             s.set_treerings(func, center)
         return s
 
-    def run(self, det_name: str, objects, nbatch: int = 10, wavelength_cdf=None, det_index: int = 0,
-            readout: bool = False, sky_level: float = 0.0) -> dict:
-        torch = self.torch
-        dev = torch.device("cuda", self.device)
+    # ------------------------------------------------------------------ phase 1: host
+    def prepare(self, det_name: str, objects, nbatch: int = 10, wavelength_cdf=None, det_index: int = 0,
+                readout: bool = False, sky_level: float = 0.0) -> PreparedDetector:
+        """``objects``: ``(x, y, flux, sigma)`` arrays, a ``stage1.ObjectTable``, or a callable returning one of
+        them (evaluated here, so that building the catalogue also overlaps the previous detector's kernels)."""
         t0 = time.perf_counter()
+        if callable(objects):
+            objects = objects()
         det = lsstcam_like(det_name)
         su = make_detector_setup(self.tracer, det_name, band=self.band, rot_tel_pos=self.rot_tel_pos, detector=det)
+        catalogue = not (isinstance(objects, tuple) and len(objects) == 4)
+        rows = radial = None
+        if catalogue:
+            rows, oflux = objects.build()
+            rows = rows.copy()
+            sc = self.setup_ctx  # the tracer left this detector's telescope there
+            sc.set_wcs(su.img_wcs, su.icrf_to_field)
+            sc.set_detector(su.detector)
+            vx, vy, vz = sc.xy_to_v(np.ascontiguousarray(rows["x"]), np.ascontiguousarray(rows["y"]))
+            rows["tanx"], rows["tany"] = vx / -vz, vy / -vz  # tangents of the field angle
+            radial = objects.radial_tables()
+        else:
+            oflux = objects[2]
+        gen = np.random.default_rng(self.seed + det_index)
+        counts = photon_batch_counts(oflux, np.zeros(len(oflux), bool), nbatch, gen.random)
+        batches = []
+        for k in range(nbatch):
+            cnt = np.asarray(counts[k])
+            idx = np.nonzero(cnt)[0]
+            cnt = cnt[idx].astype(np.int64)
+            batches.append((int(cnt.sum()), idx.astype(np.int64), cnt))
+        return PreparedDetector(det_name, det_index, det, su, catalogue, objects, rows, oflux, radial, wavelength_cdf,
+                                counts, batches, nbatch, readout, sky_level, time.perf_counter() - t0)
+
+    # ------------------------------------------------------------------ phase 2: queue the device work
+    def launch(self, p: PreparedDetector) -> LaunchedDetector:
+        torch = self.torch
+        dev = torch.device("cuda", self.device)
+        det, su, det_index = p.det, p.setup, p.det_index
         self.ctx.set_telescope(su.telescope)
         self.ctx.set_wcs(su.img_wcs, su.icrf_to_field)
         self.ctx.set_detector(su.detector)
         self.ctx.set_diffraction(self.dif)
-        sensor = self.sensor_for(det_name)
-        # the returned e-image (and raw segments) live in pinned buffers of the runner, reused by the next run()
-        image = Image(self._pinned("img", (det.ny, det.nx), torch.float32).numpy(), 0, 0)
-        image.array[:, :] = 0.0
+        sensor = self.sensor_for(p.det_name)
+        # the returned e-image (and raw segments) land in pinned buffers of the runner; two slots alternate, so the
+        # result of one detector stays valid while the next one is in flight
+        slot = self._slot
+        self._slot ^= 1
+        host_img = self._pinned(("img", slot), (det.ny, det.nx), torch.float32)
+        image = Image(host_img.numpy(), 0, 0)
+        sensor.bind_stamp(0, 0, det.nx, det.ny, dtype=np.float32)  # zeros, on the device: no 66 MB upload
         pool = PhotonPool(self.ctx, sensor, exptime=self.exptime, seed=self.seed + 1000 * det_index)
-        gen = np.random.default_rng(self.seed + det_index)
-        catalogue = not (isinstance(objects, tuple) and len(objects) == 4)
+        keep = []
         cdf = cdfw = None
-        if catalogue:
+        if p.catalogue:
             # stage 1 from catalogue rows (stage1.ObjectTable): profiles, per-object SEDs, PSF kicks
             from .stage1 import Stage1
 
-            rows, oflux = objects.build()
-            rows = rows.copy()
-            vx, vy, vz = self.ctx.xy_to_v(np.ascontiguousarray(rows["x"]), np.ascontiguousarray(rows["y"]))
-            rows["tanx"], rows["tany"] = vx / -vz, vy / -vz  # tangents of the field angle
-            cdf_np, cdfw_np = wavelength_cdf if wavelength_cdf is not None else (None, None)
-            stage1 = Stage1(self.ctx, rows, cdf_np, cdfw_np, objects.radial_tables())
+            cdf_np, cdfw_np = p.wavelength_cdf if p.wavelength_cdf is not None else (None, None)
+            stage1 = Stage1(self.ctx, p.rows, cdf_np, cdfw_np, p.radial)
             if self.psf is not None:
-                self.psf.upload(self.ctx, objects.arcsec_to_pix)
+                self.psf.upload(self.ctx, p.objects.arcsec_to_pix)
+            keep.append(stage1)
         else:
-            ox, oy, oflux, osig = objects
-            d_ox = torch.as_tensor(ox, device=dev)
-            d_oy = torch.as_tensor(oy, device=dev)
-            d_os = torch.as_tensor(osig, device=dev)
-            if wavelength_cdf is not None:
-                cdf, cdfw = (torch.as_tensor(a, device=dev) for a in wavelength_cdf)
-        counts = photon_batch_counts(oflux, np.zeros(len(oflux), bool), nbatch, gen.random)
-        t_setup = time.perf_counter() - t0
+            ox, oy, _, osig = p.objects
+            d_ox, d_oy, d_os = (_lib.h2d_async(np.asarray(a, np.float64), dev) for a in (ox, oy, osig))
+            if p.wavelength_cdf is not None:
+                cdf, cdfw = (_lib.h2d_async(np.asarray(a, np.float64), dev) for a in p.wavelength_cdf)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         n_total = 0
-        for k in range(nbatch):
-            cnt = counts[k]
-            idx = np.nonzero(cnt)[0]
-            cnt = cnt[idx]
-            n = int(cnt.sum())
+        first = True
+        for n, idx, cnt in p.batches:
             if n == 0:
                 continue
             dp = DevicePhotons(n, device=dev, fields=("x", "y", "flux", "wavelength"))
-            if catalogue:
+            if p.catalogue:
                 stage1.shoot(dp, cnt, seed=self.seed + 7 * det_index, photon_offset=n_total, select=idx)
             else:
-                cum = torch.as_tensor(np.concatenate([[0], np.cumsum(cnt)]), device=dev)
-                sel = torch.as_tensor(idx, device=dev)
+                cum_h = np.zeros(cnt.size + 1, dtype=np.int64)
+                np.cumsum(cnt, out=cum_h[1:])
+                cum = _lib.h2d_async(cum_h, dev)
+                sel = _lib.h2d_async(idx, dev)
                 self.ctx.object_photons(dp.x, dp.y, dp.flux, dp.wavelength, d_ox[sel].contiguous(),
                                         d_oy[sel].contiguous(), d_os[sel].contiguous(), cum, cdf, cdfw,
                                         seed=self.seed + 7 * det_index, photon_offset=n_total)
-            pool.process(dp, image, resume=(k > 0), recalc=(k > 0), fused=True)
+            pool.process(dp, image, resume=not first, recalc=not first, fused=True, prebound=True)
+            first = False
             n_total += n
         raw = None
         e = torch.empty((det.ny, det.nx), dtype=torch.float32, device=dev)
-        sensor.snapshot_image(e)
+        if first:
+            e.zero_()  # no photons at all: nothing was accumulated on the bound image
+        else:
+            sensor.snapshot_image(e)
         electrons = e.sum(dtype=torch.float64)  # collected source charge, before sky / dark current
-        if sky_level > 0.0:
+        if p.sky_level > 0.0:
             # sky background through the sensor model (imsim/lsst_image.py:128-199): level x pixel areas (tree
             # rings + the accumulated charge), exact Poisson noise, all on the device
             from .sky import add_sky, pixel_areas_device
 
             areas = pixel_areas_device(sensor, use_flux=True)
-            add_sky(self.ctx, e, sky_level, seed=self.seed + 17 * det_index, areas=areas)
-        if readout:
+            add_sky(self.ctx, e, p.sky_level, seed=self.seed + 17 * det_index, areas=areas)
+        if p.readout:
             # post-path on the device (imsim/readout.py:414-480): the e-image goes from the sensor's buffer to
             # int32 amplifier segments without visiting the host; both are then copied back
             from .readout import CcdReadout, lsstcam_like_amps
 
-            vendor = vendor_of(det_name)
+            vendor = vendor_of(p.det_name)
             ro = self._readouts.get(vendor)
             if ro is None:
                 ro = self._readouts[vendor] = CcdReadout(self.ctx, lsstcam_like_amps(vendor), exptime=self.exptime,
@@ -210,18 +289,50 @@ class DetectorRunner:
             amp = lsstcam_like_amps(vendor)[0]
             ex = e[: 2 * amp.ny, : 8 * amp.nx].contiguous() if (2 * amp.ny, 8 * amp.nx) != tuple(e.shape) else e
             draw = ro.build_amp_images(ex, seed=self.seed + 13 * det_index)
-            praw = self._pinned("raw", tuple(draw.shape), torch.int32)
+            praw = self._pinned(("raw", slot), tuple(draw.shape), torch.int32)
             praw.copy_(draw, non_blocking=True)
             raw = praw.numpy()
         # with the readout, e is the e-image after bleed trails and dark current, like CcdReadout.eimage
-        self._pinned("img", (det.ny, det.nx), torch.float32).copy_(e, non_blocking=True)
+        host_img.copy_(e, non_blocking=True)
         e1.record()
-        torch.cuda.synchronize(dev)
-        self.last_raw = raw
+        return LaunchedDetector(p, image, raw, electrons, (e0, e1), n_total, keep)
+
+    # ------------------------------------------------------------------ phase 3: wait and collect
+    def finish(self, h: LaunchedDetector):
+        e0, e1 = h.events
+        e1.synchronize()
+        p = h.prep
+        self.last_raw = h.raw
         # per-object sum of the photon fluxes shot over all batches: the ``incident_flux`` column of the
         # photon_pooling_truth output (imsim/photon_pooling.py:472-511, stamp.py:743)
-        self.last_incident_flux = np.asarray(counts, dtype=np.int64).sum(axis=0).astype(np.float64)
-        rec = {"det_name": det_name, "device": self.device, "photons": n_total, "nbatch": nbatch,
-               "electrons": float(electrons.item()), "gpu_ms": float(e0.elapsed_time(e1)),
-               "setup_ms": 1e3 * t_setup}
-        return rec, image
+        self.last_incident_flux = np.asarray(p.counts, dtype=np.int64).sum(axis=0).astype(np.float64)
+        rec = {"det_name": p.det_name, "device": self.device, "photons": h.n_total, "nbatch": p.nbatch,
+               "electrons": float(h.electrons.item()), "gpu_ms": float(e0.elapsed_time(e1)),
+               "setup_ms": 1e3 * p.setup_s}
+        h.keep.clear()
+        return rec, h.image
+
+    def run(self, det_name: str, objects, nbatch: int = 10, wavelength_cdf=None, det_index: int = 0,
+            readout: bool = False, sky_level: float = 0.0):
+        """One detector start to finish; returns ``(record, image)``."""
+        return self.finish(self.launch(self.prepare(det_name, objects, nbatch=nbatch, wavelength_cdf=wavelength_cdf,
+                                                    det_index=det_index, readout=readout, sky_level=sky_level)))
+
+    def run_many(self, jobs):
+        """Software-pipelined visit loop over ``jobs`` (an iterable of keyword dicts for ``prepare``): while
+        the GPU works through detector k, the host prepares detector k+1, and detector k+1 is queued before
+        detector k's result is handed to the caller.  Yields ``(record, image)`` in order; an image (and
+        ``last_raw``) stays valid until the caller asks for the next but one result."""
+        it = iter(jobs)
+        try:
+            handle = self.launch(self.prepare(**next(it)))
+        except StopIteration:
+            return
+        for job in it:
+            prep = self.prepare(**job)      # host work, overlapping the kernels of `handle`
+            result = self.finish(handle)
+            raw = self.last_raw
+            handle = self.launch(prep)      # the GPU is busy again before the caller sees the result
+            self.last_raw = raw
+            yield result
+        yield self.finish(handle)

@@ -138,3 +138,48 @@ def test_itl_detector_full_chain():
     data = raw[:, :2000, 3:512].astype(np.float64)
     assert abs(data.mean() - (1000.0 + (300.64 + rec["electrons"] / npix) / 1.5 - 0.5)) < 0.5
     assert abs(raw[:, 2010:, 520:].astype(np.float64).mean() - 999.5) < 0.1  # overscan corner: bias only
+
+
+def test_pipelined_visit_equals_one_detector_at_a_time():
+    """``run_many`` (host preparation of detector k+1 overlapping the kernels of detector k, results landing in
+    alternating pinned slots) gives exactly the images, raw segments and records of ``run`` called in turn --
+    across both vendors, with catalogue rows and with plain point-source tables."""
+    from imsim_b200.atmosphere import GaussianPSF
+    from imsim_b200.flat import wavelength_cdf
+    from imsim_b200.visit import DetectorRunner, synthetic_catalog, synthetic_objects
+
+    models = {"e2v": helpers.sensor_model("lsst_e2v_50_4"), "itl": helpers.sensor_model("lsst_itl_50_4")}
+    wave = np.linspace(550, 690, 15)
+    seds = [wavelength_cdf(wave, 1.0 + 0.1 * k * (wave - 550) / 140) for k in range(8)]
+    cdf = (np.array([c for c, _ in seds]), np.array([w for _, w in seds]))
+    dets = ["R22_S11", "R01_S00", "R22_S12", "R22_S11"]
+    tr = {d: helpers.tree_ring_table() for d in dets if d.startswith("R22")}
+
+    def jobs(catalogue):
+        for i, d in enumerate(dets):
+            nx, ny = (4072, 4000) if d.startswith("R01") else (4096, 4004)
+            if catalogue:
+                objects = (lambda i=i, nx=nx, ny=ny: synthetic_catalog(300, nx, ny, seed=i, total_photons=1.5e6))
+                yield dict(det_name=d, objects=objects, nbatch=3, wavelength_cdf=cdf, det_index=i, readout=True,
+                           sky_level=100.0)
+            else:
+                objects = synthetic_objects(500, nx, ny, seed=i, total_photons=1e6)
+                yield dict(det_name=d, objects=objects, nbatch=4, wavelength_cdf=(cdf[0][0], cdf[1][0]), det_index=i)
+
+    for catalogue in (False, True):
+        runner = DetectorRunner(0, models, helpers.absorption(), tree_rings=tr, psf=GaussianPSF(0.7))
+        serial = []
+        for job in jobs(catalogue):
+            rec, image = runner.run(**job)
+            serial.append((rec, image.array.copy(), None if runner.last_raw is None else runner.last_raw.copy()))
+        runner2 = DetectorRunner(0, models, helpers.absorption(), tree_rings=tr, psf=GaussianPSF(0.7))
+        n = 0
+        for (rec, image), (srec, simg, sraw) in zip(runner2.run_many(jobs(catalogue)), serial):
+            assert rec["det_name"] == srec["det_name"] and rec["photons"] == srec["photons"] > 0
+            assert rec["electrons"] == srec["electrons"]
+            assert np.array_equal(image.array, simg)
+            if catalogue:
+                assert np.array_equal(runner2.last_raw, sraw)
+            n += 1
+        assert n == len(dets)
+    assert list(runner2.run_many([])) == []
