@@ -16,7 +16,8 @@ import numpy as np
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SRC = [os.path.join(_HERE, "csrc", f) for f in ("abi.cu", "optics.cu", "sensor.cu", "pool.cu", "stage1.cu", "readout.cu")]
+_SRC = [os.path.join(_HERE, "csrc", f) for f in ("abi.cu", "optics.cu", "sensor.cu", "pool.cu", "stage1.cu", "readout.cu",
+                                                      "hostpipe.cu")]
 _HDR = [os.path.join(_HERE, "csrc", f) for f in ("b2_common.cuh", "optics_device.cuh", "sensor_device.cuh")] + \
     [os.path.join(os.path.dirname(_HERE), "include", "imsim_b200.h")]
 SO_PATH = os.path.join(_HERE, "_build", "libimsim_b200.so")

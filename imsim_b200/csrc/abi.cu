@@ -69,6 +69,7 @@ extern "C" int b2_ctx_destroy(b2_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     b2_stage1_release(ctx);
+    b2_pipe_release(ctx);
     for (void* p : ctx->extras) cudaFree(p);
     if (ctx->scratch.ptr) cudaFree(ctx->scratch.ptr);
     if (ctx->stats.ptr) cudaFree(ctx->stats.ptr);

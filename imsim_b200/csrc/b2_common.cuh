@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <utility>
 #include <vector>
@@ -128,9 +129,20 @@ struct b2_ctx {
     // live timing of the dominant kernel (bench.py roofline): event pairs around each launch
     bool record_events = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+    struct b2_hostpipe* pipe = nullptr;  // hostpipe.cu: pinned ring + streams of the pipelined B2_HOST route
 };
 
 int b2_scratch_reserve(b2_ctx* ctx, Scratch& s, size_t bytes);
+
+// hostpipe.cu -- pipelined staging of pageable host arrays.  Chunk by chunk: host threads copy `nin` caller
+// arrays into pinned slots -> H2D into din[f] + off -> kernel(off, cnt, stream) (optional) -> D2H of `nout`
+// arrays -> host threads copy them into hout[f] + off.  Everything has completed when it returns.
+bool b2_pipe_enabled(int64_t n);
+int b2_pipe_threads();
+int b2_pipe_run(b2_ctx* ctx, int64_t n, int nin, const double* const* hin, double* const* din, int nout,
+                double* const* hout, const double* const* dout,
+                const std::function<int(int64_t, int64_t, cudaStream_t)>* kernel);
+void b2_pipe_release(b2_ctx* ctx);
 void b2_stage1_release(b2_ctx* ctx);  // stage1.cu: per-context PSF / profile tables
 
 // stage helper for B2_HOST calls: carve arrays out of the context scratch

@@ -1,0 +1,214 @@
+// hostpipe.cu -- pipelined staging of pageable host photon arrays (sm_100a library, host code only).
+//
+// The reference hands every photon op and the sensor ordinary numpy arrays (GalSim PhotonArray fields,
+// imsim/photon_ops.py:81-127, imsim/photon_pooling.py:195-225).  A cudaMemcpyAsync from pageable memory is
+// staged by the driver on one host thread (~11 GB/s measured) and serialises with the kernel, so the plain
+// B2_HOST calls were bound by that copy.  Here a call is cut into chunks that move through a ring of pinned
+// slots: a small pool of host threads copies chunk k from the caller's arrays into a slot while the DMA
+// engines and the kernel work on chunks k-1 and k-2 (two internal streams), and results travel back the
+// same way.  Arithmetic is untouched: a chunk is a sub-range of the same per-photon kernel, and the Philox
+// counters are offset by the chunk start.
+#include <unistd.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstdlib>
+#include <mutex>
+#include <thread>
+
+#include "b2_common.cuh"
+
+namespace {
+
+struct Piece {
+    char* dst;
+    const char* src;
+    size_t n;
+};
+
+// Persistent memcpy workers.  Never destroyed (a joinable std::thread in a static destructor of a forked or
+// exiting interpreter is a hang waiting to happen); re-created in a forked child, where the parent's threads
+// do not exist.
+class CopyPool {
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_work_, cv_done_;
+    const std::vector<Piece>* pieces_ = nullptr;
+    std::atomic<size_t> next_{0};
+    size_t busy_ = 0;
+    uint64_t gen_ = 0;
+
+    void drain(const std::vector<Piece>& p) {
+        for (;;) {
+            size_t i = next_.fetch_add(1);
+            if (i >= p.size()) break;
+            memcpy(p[i].dst, p[i].src, p[i].n);
+        }
+    }
+    void worker() {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::vector<Piece>* p;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_work_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                p = pieces_;
+            }
+            drain(*p);
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--busy_ == 0) cv_done_.notify_one();
+            }
+        }
+    }
+
+public:
+    explicit CopyPool(int nthreads) {
+        for (int i = 1; i < nthreads; ++i) {
+            th_.emplace_back([this] { worker(); });
+            th_.back().detach();
+        }
+    }
+    int threads() const { return (int)th_.size() + 1; }
+    // copies every piece; the calling thread takes its share
+    void run(const std::vector<Piece>& p) {
+        if (th_.empty() || p.size() <= 1) {
+            for (const Piece& q : p) memcpy(q.dst, q.src, q.n);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            pieces_ = &p;
+            next_.store(0);
+            busy_ = th_.size();
+            ++gen_;
+        }
+        cv_work_.notify_all();
+        drain(p);
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [&] { return busy_ == 0; });
+    }
+};
+
+std::mutex g_pool_mu;
+CopyPool* g_pool = nullptr;
+pid_t g_pool_pid = 0;
+
+long env_long(const char* name, long dflt) {
+    const char* e = getenv(name);
+    if (!e || !*e) return dflt;
+    char* end = nullptr;
+    long v = strtol(e, &end, 10);
+    return (end && *end == 0 && v > 0) ? v : dflt;
+}
+
+CopyPool& pool() {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (!g_pool || g_pool_pid != getpid()) {
+        long hw = (long)std::thread::hardware_concurrency();
+        long n = env_long("B2_HOST_THREADS", std::max(1L, std::min(8L, hw)));
+        g_pool = new CopyPool((int)std::min(n, 64L));  // the previous pool (parent's, after a fork) is abandoned
+        g_pool_pid = getpid();
+    }
+    return *g_pool;
+}
+
+constexpr int NSLOT = 3;
+constexpr size_t PIECE = size_t(1) << 20;  // 1 MB per memcpy work item
+
+}  // namespace
+
+struct b2_hostpipe {
+    void* pin = nullptr;
+    size_t pin_bytes = 0;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t done[NSLOT] = {nullptr, nullptr, nullptr};
+    cudaEvent_t entry = nullptr;
+};
+
+void b2_pipe_release(b2_ctx* ctx) {
+    b2_hostpipe* p = ctx->pipe;
+    if (!p) return;
+    for (int i = 0; i < 2; ++i)
+        if (p->st[i]) cudaStreamDestroy(p->st[i]);
+    for (int i = 0; i < NSLOT; ++i)
+        if (p->done[i]) cudaEventDestroy(p->done[i]);
+    if (p->entry) cudaEventDestroy(p->entry);
+    if (p->pin) cudaFreeHost(p->pin);
+    delete p;
+    ctx->pipe = nullptr;
+}
+
+// B2_PIPE_MIN: smallest call [photons] that takes the pipelined route (below it the set-up costs more than the
+// single staged copy); B2_PIPE_CHUNK: photons per chunk.  Read on every call so that tests can switch them.
+bool b2_pipe_enabled(int64_t n) { return n >= env_long("B2_PIPE_MIN", 1L << 18); }
+
+int b2_pipe_threads() { return pool().threads(); }
+
+int b2_pipe_run(b2_ctx* ctx, int64_t n, int nin, const double* const* hin, double* const* din, int nout,
+                double* const* hout, const double* const* dout,
+                const std::function<int(int64_t, int64_t, cudaStream_t)>* kernel) {
+    if (n <= 0 || (nin == 0 && nout == 0)) return 0;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->pipe) ctx->pipe = new b2_hostpipe();
+    b2_hostpipe& p = *ctx->pipe;
+    if (!p.st[0]) {
+        for (int i = 0; i < 2; ++i) B2_CUDA(cudaStreamCreateWithFlags(&p.st[i], cudaStreamNonBlocking));
+        for (int i = 0; i < NSLOT; ++i) B2_CUDA(cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming));
+        B2_CUDA(cudaEventCreateWithFlags(&p.entry, cudaEventDisableTiming));
+    }
+    const int64_t chunk = std::min<int64_t>(n, env_long("B2_PIPE_CHUNK", 1L << 19));
+    const size_t slot_bytes = (size_t)(nin + nout) * (size_t)chunk * sizeof(double);
+    if (p.pin_bytes < NSLOT * slot_bytes) {
+        if (p.pin) B2_CUDA(cudaFreeHost(p.pin));
+        p.pin = nullptr;
+        p.pin_bytes = 0;
+        B2_CUDA(cudaHostAlloc(&p.pin, NSLOT * slot_bytes, cudaHostAllocDefault));
+        p.pin_bytes = NSLOT * slot_bytes;
+    }
+    auto slot = [&](int s, int f) { return (double*)((char*)p.pin + (size_t)s * slot_bytes) + (size_t)f * chunk; };
+    // the device arrays may still be in use by earlier work on the context's stream
+    B2_CUDA(cudaEventRecord(p.entry, ctx->stream));
+    for (int i = 0; i < 2; ++i) B2_CUDA(cudaStreamWaitEvent(p.st[i], p.entry, 0));
+    CopyPool& cp = pool();
+    std::vector<Piece> pieces;
+    auto host_copy = [&](int64_t k, int s, bool in) {
+        const int64_t off = k * chunk, cnt = std::min(chunk, n - off);
+        const size_t bytes = (size_t)cnt * sizeof(double);
+        pieces.clear();
+        const int nf = in ? nin : nout;
+        for (int f = 0; f < nf; ++f) {
+            char* pinned = (char*)slot(s, in ? f : nin + f);
+            char* user = in ? (char*)const_cast<double*>(hin[f] + off) : (char*)(hout[f] + off);
+            for (size_t o = 0; o < bytes; o += PIECE) {
+                size_t m = std::min(PIECE, bytes - o);
+                pieces.push_back(in ? Piece{pinned + o, user + o, m} : Piece{user + o, pinned + o, m});
+            }
+        }
+        cp.run(pieces);
+    };
+    const int64_t nch = (n + chunk - 1) / chunk;
+    for (int64_t k = 0; k < nch + NSLOT; ++k) {
+        const int s = (int)(k % NSLOT);
+        if (k >= NSLOT && k - NSLOT < nch) {
+            // chunk k - NSLOT lived in this slot: wait for it, hand its results back
+            B2_CUDA(cudaEventSynchronize(p.done[s]));
+            if (nout) host_copy(k - NSLOT, s, false);
+        }
+        if (k < nch) {
+            const int64_t off = k * chunk, cnt = std::min(chunk, n - off);
+            if (nin) host_copy(k, s, true);
+            cudaStream_t st = p.st[k & 1];
+            for (int f = 0; f < nin; ++f)
+                B2_CUDA(cudaMemcpyAsync(din[f] + off, slot(s, f), (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+            if (kernel && (*kernel)(off, cnt, st)) return 1;
+            for (int f = 0; f < nout; ++f)
+                B2_CUDA(cudaMemcpyAsync(slot(s, nin + f), dout[f] + off, (size_t)cnt * sizeof(double),
+                                        cudaMemcpyDeviceToHost, st));
+            B2_CUDA(cudaEventRecord(p.done[s], st));
+        }
+    }
+    for (int i = 0; i < 2; ++i) B2_CUDA(cudaStreamSynchronize(p.st[i]));
+    return 0;
+}

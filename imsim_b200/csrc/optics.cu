@@ -508,19 +508,20 @@ static void select_program(b2_ctx* ctx) {
     ctx->program = B2_PROG_LSST;
 }
 
-static void launch_rubin_optics(b2_ctx* ctx, const B2OpticsOptions& opt, int64_t n, double* x, double* y, double* dxdz,
-                                double* dydz, double* flux, const double* wl, const double* pu, const double* pv,
-                                const double* time, const double* gauss, double* time_out, unsigned long long* stats) {
-    B2_TIMED("k_rubin_optics", ctx->stream);
+static void launch_rubin_optics(b2_ctx* ctx, cudaStream_t st, const B2OpticsOptions& opt, int64_t n, double* x,
+                                double* y, double* dxdz, double* dydz, double* flux, const double* wl, const double* pu,
+                                const double* pv, const double* time, const double* gauss, double* time_out,
+                                unsigned long long* stats) {
+    B2_TIMED("k_rubin_optics", st);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->record_events) {
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
-        cudaEventRecord(e0, ctx->stream);
+        cudaEventRecord(e0, st);
     }
-#define B2_LAUNCH_OPTICS(MINB, PROG)                                                                              \
-    k_rubin_optics<MINB, PROG><<<nblocks(n), 256, 0, ctx->stream>>>(ctx->opt, opt, n, x, y, dxdz, dydz, flux, wl, pu, \
-                                                                    pv, time, gauss, time_out, stats)
+#define B2_LAUNCH_OPTICS(MINB, PROG)                                                                      \
+    k_rubin_optics<MINB, PROG><<<nblocks(n), 256, 0, st>>>(ctx->opt, opt, n, x, y, dxdz, dydz, flux, wl, pu, pv, \
+                                                           time, gauss, time_out, stats)
     const int occ = optics_occ(ctx->program);
     if (ctx->program == B2_PROG_LSST) {
         if (occ == 2) B2_LAUNCH_OPTICS(2, B2_PROG_LSST);
@@ -533,7 +534,7 @@ static void launch_rubin_optics(b2_ctx* ctx, const B2OpticsOptions& opt, int64_t
     }
 #undef B2_LAUNCH_OPTICS
     if (ctx->record_events) {
-        cudaEventRecord(e1, ctx->stream);
+        cudaEventRecord(e1, st);
         ctx->events.emplace_back(e0, e1);
     }
 }
@@ -562,6 +563,29 @@ extern "C" int b2_rubin_optics(b2_ctx* ctx, int64_t n, double* x, double* y, dou
         double *dx = st.take<double>(n), *dy = st.take<double>(n), *da = st.take<double>(n), *db = st.take<double>(n),
                *df = st.take<double>(n), *dw = st.take<double>(n), *du = st.take<double>(n), *dv = st.take<double>(n),
                *dt = st.take<double>(n), *dg = st.take<double>(n), *dto = st.take<double>(n);
+        if (b2_pipe_enabled(n)) {
+            // large pageable arrays: chunks through the pinned ring, copies and kernel overlapped (hostpipe.cu)
+            const double* hin[8] = {x, y, flux, wl_nm, pu, pv, time, gauss};
+            double* din[8] = {dx, dy, df, dw, du, dv, dt, dg};
+            double* hout[6] = {x, y, dxdz, dydz, flux, time_out};
+            const double* dout[6] = {dx, dy, da, db, df, dto};
+            const std::function<int(int64_t, int64_t, cudaStream_t)> chunk_kernel = [&](int64_t off, int64_t cnt,
+                                                                                       cudaStream_t cs) -> int {
+                B2OpticsOptions o = *opt;
+                o.photon_offset += (uint64_t)off;  // the kick's Philox counter is the photon's index in the call
+                launch_rubin_optics(ctx, cs, o, cnt, dx + off, dy + off, da + off, db + off, df + off, dw + off, du + off,
+                                    dv + off, dt + off, gauss ? dg + off : nullptr, time_out ? dto + off : nullptr,
+                                    dstats);
+                B2_CHECK_LAUNCH();
+                return 0;
+            };
+            if (b2_pipe_run(ctx, n, gauss ? 8 : 7, hin, din, time_out ? 6 : 5, hout, dout, &chunk_kernel)) return 1;
+            if (stats) {
+                B2_CUDA(cudaMemcpyAsync(stats, dstats, sizeof(*stats), cudaMemcpyDeviceToHost, ctx->stream));
+                B2_CUDA(cudaStreamSynchronize(ctx->stream));
+            }
+            return 0;
+        }
         H2D(dx, x, n);
         H2D(dy, y, n);
         H2D(df, flux, n);
@@ -570,7 +594,7 @@ extern "C" int b2_rubin_optics(b2_ctx* ctx, int64_t n, double* x, double* y, dou
         H2D(dv, pv, n);
         H2D(dt, time, n);
         if (gauss) H2D(dg, gauss, n);
-        launch_rubin_optics(ctx, *opt, n, dx, dy, da, db, df, dw, du, dv, dt, gauss ? dg : nullptr,
+        launch_rubin_optics(ctx, ctx->stream, *opt, n, dx, dy, da, db, df, dw, du, dv, dt, gauss ? dg : nullptr,
                             time_out ? dto : nullptr, dstats);
         B2_CHECK_LAUNCH();
         D2H(x, dx, n);
@@ -582,7 +606,8 @@ extern "C" int b2_rubin_optics(b2_ctx* ctx, int64_t n, double* x, double* y, dou
         if (stats) B2_CUDA(cudaMemcpyAsync(stats, dstats, sizeof(*stats), cudaMemcpyDeviceToHost, ctx->stream));
         B2_CUDA(cudaStreamSynchronize(ctx->stream));
     } else {
-        launch_rubin_optics(ctx, *opt, n, x, y, dxdz, dydz, flux, wl_nm, pu, pv, time, gauss, time_out, dstats);
+        launch_rubin_optics(ctx, ctx->stream, *opt, n, x, y, dxdz, dydz, flux, wl_nm, pu, pv, time, gauss, time_out,
+                            dstats);
         B2_CHECK_LAUNCH();
         if (stats) {
             B2_CUDA(cudaMemcpyAsync(stats, dstats, sizeof(*stats), cudaMemcpyDeviceToHost, ctx->stream));

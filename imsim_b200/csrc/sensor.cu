@@ -1092,21 +1092,38 @@ extern "C" int b2_sensor_accumulate(b2_sensor* s, int64_t n, const double* x, co
         Stager sg{ctx};
         size_t narr = 3 + (dxdz ? 2 : 0) + (wl ? 1 : 0) + (rand4 ? 4 : 0);
         if (sg.init(narr * pad256(n * 8))) return 1;
-        double* t;
-        t = sg.take<double>(n); H2D(t, x, n); dx = t;
-        t = sg.take<double>(n); H2D(t, y, n); dy = t;
-        t = sg.take<double>(n); H2D(t, flux, n); df = t;
+        const double* hin[10];
+        double* din[10];
+        int nin = 0;
+        auto stage = [&](const double* h, const double** d) {
+            double* t = sg.take<double>(n);
+            hin[nin] = h;
+            din[nin++] = t;
+            *d = t;
+        };
+        stage(x, &dx);
+        stage(y, &dy);
+        stage(flux, &df);
         if (dxdz) {
-            t = sg.take<double>(n); H2D(t, dxdz, n); da = t;
-            t = sg.take<double>(n); H2D(t, dydz, n); db = t;
+            stage(dxdz, &da);
+            stage(dydz, &db);
         }
-        if (wl) { t = sg.take<double>(n); H2D(t, wl, n); dw = t; }
+        if (wl) stage(wl, &dw);
         if (rand4) {
             // keep the [4][n] layout contiguous
-            t = (double*)(sg.base + sg.off);
+            double* t = (double*)(sg.base + sg.off);
             sg.off += pad256((size_t)4 * n * 8);
-            H2D(t, rand4, 4 * n);
+            for (int j = 0; j < 4; ++j) {
+                hin[nin] = rand4 + (size_t)j * n;
+                din[nin++] = t + (size_t)j * n;
+            }
             dr = t;
+        }
+        if (b2_pipe_enabled(n)) {
+            // large pageable arrays: uploaded through the pinned ring by the host copy threads (hostpipe.cu)
+            if (b2_pipe_run(ctx, n, nin, hin, din, 0, nullptr, nullptr, nullptr)) return 1;
+        } else {
+            for (int f = 0; f < nin; ++f) H2D(din[f], hin[f], n);
         }
     }
     // chunk boundaries (photon order) at the nrecalc cadence

@@ -263,9 +263,9 @@ class PhotonPool:
       TimeSampler + PupilAnnulusSampler      (config/imsim-config.yaml:281-289)
       RubinDiffractionOptics + FocusDepth + Refraction   (:297-320, one kernel)
       SiliconSensor.accumulate(resume, recalc)           (photon_pooling.py:159)
-    PhotonDCR is not part of the kernel chain yet (it needs the per-object sky
-    position; in the pooled pipeline the reference applies it with a stale one,
-    SURVEY.md Q2) -- callers that need it apply it to x, y before ``process``.
+    PhotonDCR is the optional prologue of the optics kernel: arm it on ``self.opt`` with
+    ``photon_ops.set_dcr_options`` (one Jacobian and zenith direction for the whole CCD, which is what the
+    reference's pooled pipeline does).
     """
 
     def __init__(self, ctx, sensor, exptime=30.0, t0=0.0, r_inner=2.558, r_outer=4.18, focus_depth=0.0,
