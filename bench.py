@@ -244,10 +244,6 @@ def run_visit(args):
         seds = [wavelength_cdf(wave, 1.0 + 0.8 * np.sin(wave / (15.0 + 5 * k))) for k in range(8)]
         cdf = (np.array([c for c, _ in seds]), np.array([w for _, w in seds]))
     runner = DetectorRunner(local, models, helpers.absorption(), tree_rings={d: tr for d in mine}, psf=psf)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
 
     def job(d):
         make = synthetic_catalog if args.visit_catalog else synthetic_objects
@@ -256,12 +252,23 @@ def run_visit(args):
         return dict(det_name=d, objects=lambda: make(20000, 4096, 4004, seed=i, total_photons=costs[d]), nbatch=10,
                     wavelength_cdf=cdf, det_index=i, readout=args.visit_readout, sky_level=args.visit_sky)
 
-    if args.visit_serial:  # one detector at a time, host and device in turn (the pre-pipelining behaviour)
-        recs = [runner.run(**job(d))[0] for d in mine]
-    else:
-        recs = [rec for rec, _ in runner.run_many(job(d) for d in mine)]
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
+    # The visit is simulated --visit-repeat times by the same process and the LAST one is reported: the first
+    # carries the one-time initialisation of a process (2.5 GB of boundary arrays per vendor model, the packed
+    # phase screens, pinned result buffers, the caching allocator's first cudaMallocs), which a production run
+    # pays once for all its visits, as it does the generation of the atmosphere.  first_visit_wall_s keeps it.
+    walls = []
+    for rep in range(max(1, args.visit_repeat)):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if args.visit_serial:  # one detector at a time, host and device in turn (the pre-pipelining behaviour)
+            recs = [runner.run(**job(d))[0] for d in mine]
+        else:
+            recs = [rec for rec, _ in runner.run_many(job(d) for d in mine)]
+        torch.cuda.synchronize()
+        walls.append(time.perf_counter() - t0)
+    wall = walls[-1]
     wt = torch.tensor([wall], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(wt, op=dist.ReduceOp.MAX)
@@ -277,7 +284,8 @@ def run_visit(args):
                           "visits_per_hour_gpu_time": 3600.0 / gpu_s,
                           "photons_per_s_wall": photons / float(wt.item()),
                           "setup_s_total": sum(r["setup_ms"] for r in allrec) * 1e-3,
-                          "pipelined": not args.visit_serial,
+                          "pipelined": not args.visit_serial, "visits_simulated": len(walls),
+                          "first_visit_wall_s_rank0": walls[0],
                           "note": "synthetic 20k-object field per CCD generated on device; host work per CCD = WCS "
                                   "fit + object batching (Python) + 66 MB image readback"}))
     if world > 1:
@@ -319,6 +327,9 @@ def main():
                     help="with --visit: stage 1 from catalogue rows (stars + bulge/disc/knots galaxies, per-object SEDs) "
                          "behind the atmospheric PSF (6 phase screens + second kick) instead of Gaussian point sources")
     ap.add_argument("--visit-ccds", type=int, default=189)
+    ap.add_argument("--visit-repeat", type=int, default=2,
+                    help="with --visit: simulate the visit this many times in the process and report the last "
+                         "(steady state; the first also pays the one-time allocations)")
     ap.add_argument("--visit-serial", action="store_true",
                     help="with --visit: no software pipelining (prepare, launch and finish each detector in turn)")
     ap.add_argument("--kernel-timing", action="store_true",

@@ -246,7 +246,12 @@ class AtmosphericPSF:
             pod.screen_f32 = 2
         ptrs = (C.c_void_p * len(self._dev_screens))(*[s.data_ptr() for s in self._dev_screens])
         kick = self.second_kick[0] if self.second_kick is not None else None
-        _lib.check(_lib.load().b2_psf_upload(ctx.handle, C.byref(pod), ptrs, kick.ctypes.data if kick is not None else None))
+        # same PSF, same local WCS as the context already holds (the next detector of a visit): nothing to upload
+        key = (id(self), id(kick), bytes(pod), tuple(s.data_ptr() for s in self._dev_screens))
+        if getattr(ctx, "_psf_key", None) != key:
+            _lib.check(_lib.load().b2_psf_upload(ctx.handle, C.byref(pod), ptrs,
+                                                 kick.ctypes.data if kick is not None else None))
+            ctx._psf_key = key
         return pod
 
 
@@ -266,5 +271,8 @@ class GaussianPSF:
 
     def upload(self, ctx, arcsec_to_pix=None):
         pod = self.to_pod(arcsec_to_pix)
-        _lib.check(_lib.load().b2_psf_upload(ctx.handle, C.byref(pod), None, None))
+        key = ("gaussian", bytes(pod))
+        if getattr(ctx, "_psf_key", None) != key:
+            _lib.check(_lib.load().b2_psf_upload(ctx.handle, C.byref(pod), None, None))
+            ctx._psf_key = key
         return pod

@@ -851,7 +851,9 @@ extern "C" int b2_sensor_set_treerings(b2_sensor* s, double cx, double cy, const
     B2_REQUIRE(n <= 2 || (tr_r && tr_f), "b2_sensor_set_treerings: table missing");
     b2_ctx* ctx = s->ctx;
     B2_CUDA(cudaSetDevice(ctx->device));
-    B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    // No stream synchronisation: kernels take DevSensor by value at launch, the table copies below are ordered on
+    // the stream behind whatever is already queued, and a small pageable upload is staged before cudaMemcpyAsync
+    // returns.  A visit can therefore queue the next detector behind the running one.
     DevSensor& d = s->d;
     d.trc[0] = cx;
     d.trc[1] = cy;
@@ -861,14 +863,29 @@ extern "C" int b2_sensor_set_treerings(b2_sensor* s, double cx, double cy, const
     d.tr_spline = 0;
     d.tr_r = d.tr_f = d.tr_y2 = nullptr;
     if (n > 2) {
-        if (dev_upload(ctx, s->owned, tr_r, (size_t)n, &d.tr_r)) return 1;
-        if (dev_upload(ctx, s->owned, tr_f, (size_t)n, &d.tr_f)) return 1;
+        // one set of buffers, reused from detector to detector: the copies are ordered on the stream behind the
+        // kernels that still read the previous detector's tables
+        if ((size_t)n > s->tr_cap) {
+            for (int k = 0; k < 3; ++k) {
+                void* p = nullptr;
+                B2_CUDA(cudaMalloc(&p, (size_t)n * sizeof(double)));
+                s->owned.push_back(p);
+                s->tr_buf[k] = (double*)p;
+            }
+            s->tr_cap = (size_t)n;
+        }
+        const double* src[3] = {tr_r, tr_f, tr_y2};
+        for (int k = 0; k < 3; ++k)
+            if (src[k])
+                B2_CUDA(cudaMemcpyAsync(s->tr_buf[k], src[k], (size_t)n * sizeof(double), cudaMemcpyHostToDevice,
+                                        ctx->stream));
+        d.tr_r = s->tr_buf[0];
+        d.tr_f = s->tr_buf[1];
         d.tr_max = tr_r[n - 1];
         if (tr_y2) {
-            if (dev_upload(ctx, s->owned, tr_y2, (size_t)n, &d.tr_y2)) return 1;
+            d.tr_y2 = s->tr_buf[2];
             d.tr_spline = 1;
         }
-        B2_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     s->initialized = false;
     return 0;

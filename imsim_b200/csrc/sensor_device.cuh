@@ -44,6 +44,8 @@ struct b2_sensor {
     Scratch cum;  // cumulative flux scratch
     size_t cap_H = 0, cap_V = 0, cap_pix_bytes = 0, cap_tiles = 0;  // capacities of the per-image arrays
     Scratch slow;  // compact list of photons that need the full polygon / neighbour treatment
+    double* tr_buf[3] = {nullptr, nullptr, nullptr};  // tree-ring tables of b2_sensor_set_treerings (reused)
+    size_t tr_cap = 0;
     unsigned long long* dnslow = nullptr;
 };
 

@@ -259,7 +259,13 @@ class Stage1:
             self.cdf = self.cdf_wave = None
         if radial_tables is not None:
             t = np.ascontiguousarray(radial_tables, dtype=np.float64)
-            _lib.check(_lib.load().b2_radial_luts_upload(ctx.handle, t.ctypes.data, t.shape[0], t.shape[1], RADIAL_TMAX))
+            # the upload replaces a device allocation (it waits for the stream): skip it when the context already
+            # holds these very tables, as it does from detector to detector of a visit
+            key = (t.shape, hash(t.tobytes()))
+            if getattr(ctx, "_radial_luts_key", None) != key:
+                _lib.check(_lib.load().b2_radial_luts_upload(ctx.handle, t.ctypes.data, t.shape[0], t.shape[1],
+                                                             RADIAL_TMAX))
+                ctx._radial_luts_key = key
         elif objects.size and np.any(objects["kind"] == _abi.PROF_RADIAL):
             raise ValueError("objects with radial profiles need radial_tables")
         if psf is not None:

@@ -120,7 +120,8 @@ class DetectorRunner:
     split of imsim/photon_pooling.py:279-313, per-batch index tables); its few chief-ray traces run on a
     second context with its own high-priority stream, so they do not queue behind another detector's kernels;
     ``launch`` -- every upload, kernel and read-back of the detector queued on the compute stream without
-    waiting for the GPU (index tables go through pinned staging, the image is bound as zeros on the device);
+    waiting for the GPU, possibly behind a detector that is still running (index tables go through pinned
+    staging, the image is bound as zeros on the device, per-detector tables are copied in stream order);
     ``finish`` -- wait, collect the record.  ``run`` is the three in sequence."""
 
     def __init__(self, device: int, sensor_models: Dict[str, tuple], absorption_table, tree_rings=None,
@@ -217,10 +218,10 @@ class DetectorRunner:
         self.ctx.set_detector(su.detector)
         self.ctx.set_diffraction(self.dif)
         sensor = self.sensor_for(p.det_name)
-        # the returned e-image (and raw segments) land in pinned buffers of the runner; two slots alternate, so the
-        # result of one detector stays valid while the next one is in flight
+        # the returned e-image (and raw segments) land in pinned buffers of the runner; three slots rotate, so the
+        # result handed to the caller stays valid while the next two detectors are in flight
         slot = self._slot
-        self._slot ^= 1
+        self._slot = (self._slot + 1) % 3
         host_img = self._pinned(("img", slot), (det.ny, det.nx), torch.float32)
         image = Image(host_img.numpy(), 0, 0)
         sensor.bind_stamp(0, 0, det.nx, det.ny, dtype=np.float32)  # zeros, on the device: no 66 MB upload
@@ -268,7 +269,10 @@ class DetectorRunner:
             e.zero_()  # no photons at all: nothing was accumulated on the bound image
         else:
             sensor.snapshot_image(e)
-        electrons = e.sum(dtype=torch.float64)  # collected source charge, before sky / dark current
+        # collected source charge, before sky / dark current; read back through a pinned scalar (an .item() would
+        # wait for everything queued on the stream, including the next detector)
+        electrons = self._pinned(("electrons", slot), (1,), torch.float64)
+        electrons.copy_(e.sum(dtype=torch.float64).reshape(1), non_blocking=True)
         if p.sky_level > 0.0:
             # sky background through the sensor model (imsim/lsst_image.py:128-199): level x pixel areas (tree
             # rings + the accumulated charge), exact Poisson noise, all on the device
@@ -307,7 +311,7 @@ class DetectorRunner:
         # photon_pooling_truth output (imsim/photon_pooling.py:472-511, stamp.py:743)
         self.last_incident_flux = np.asarray(p.counts, dtype=np.int64).sum(axis=0).astype(np.float64)
         rec = {"det_name": p.det_name, "device": self.device, "photons": h.n_total, "nbatch": p.nbatch,
-               "electrons": float(h.electrons.item()), "gpu_ms": float(e0.elapsed_time(e1)),
+               "electrons": float(h.electrons[0]), "gpu_ms": float(e0.elapsed_time(e1)),
                "setup_ms": 1e3 * p.setup_s}
         h.keep.clear()
         return rec, h.image
@@ -319,20 +323,22 @@ class DetectorRunner:
                                                     det_index=det_index, readout=readout, sky_level=sky_level)))
 
     def run_many(self, jobs):
-        """Software-pipelined visit loop over ``jobs`` (an iterable of keyword dicts for ``prepare``): while
-        the GPU works through detector k, the host prepares detector k+1, and detector k+1 is queued before
-        detector k's result is handed to the caller.  Yields ``(record, image)`` in order; an image (and
-        ``last_raw``) stays valid until the caller asks for the next but one result."""
+        """Software-pipelined visit loop over ``jobs`` (an iterable of keyword dicts for ``prepare``).  Two
+        detectors are kept queued on the stream: while the GPU works through detector k (with k+1 already behind
+        it), the host prepares detector k+2, so neither the host work nor the hand-over between detectors leaves
+        the GPU idle.  Yields ``(record, image)`` in order; an image (and ``last_raw``) stays valid until the
+        caller asks for the next result."""
         it = iter(jobs)
-        try:
-            handle = self.launch(self.prepare(**next(it)))
-        except StopIteration:
-            return
+        queue = []
         for job in it:
-            prep = self.prepare(**job)      # host work, overlapping the kernels of `handle`
-            result = self.finish(handle)
-            raw = self.last_raw
-            handle = self.launch(prep)      # the GPU is busy again before the caller sees the result
-            self.last_raw = raw
-            yield result
-        yield self.finish(handle)
+            prep = self.prepare(**job)          # host work, overlapping the kernels already queued
+            if len(queue) == 2:
+                result = self.finish(queue.pop(0))
+                raw = self.last_raw
+                queue.append(self.launch(prep))  # the stream holds two detectors again before the caller works
+                self.last_raw = raw
+                yield result
+            else:
+                queue.append(self.launch(prep))
+        for h in queue:
+            yield self.finish(h)
