@@ -334,9 +334,7 @@ class DetectorRunner:
             prep = self.prepare(**job)          # host work, overlapping the kernels already queued
             if len(queue) == 2:
                 result = self.finish(queue.pop(0))
-                raw = self.last_raw
                 queue.append(self.launch(prep))  # the stream holds two detectors again before the caller works
-                self.last_raw = raw
                 yield result
             else:
                 queue.append(self.launch(prep))

@@ -59,3 +59,41 @@ def test_gloo_metadata_gather_world_size_2():
     for rank, names, total in res:
         assert names == dets
         assert total == sum(int((1.0 + i) * 1000) for i in range(10))
+
+
+def test_run_many_keeps_two_detectors_queued_and_yields_in_order():
+    """Host logic of the software-pipelined visit loop (imsim_b200/visit.py, no GPU): detector k+2 is prepared
+    while k and k+1 are queued, k is finished before k+2 is launched, results come back in job order."""
+    from imsim_b200.visit import DetectorRunner
+
+    class Fake(DetectorRunner):
+        def __init__(self):
+            self.log = []
+
+        def prepare(self, name):
+            self.log.append(("prepare", name))
+            return name
+
+        def launch(self, prep):
+            self.log.append(("launch", prep))
+            return prep
+
+        def finish(self, h):
+            self.log.append(("finish", h))
+            return {"det_name": h}, None
+
+    for n in (0, 1, 2, 3, 6):
+        r = Fake()
+        out = [rec["det_name"] for rec, _ in r.run_many(dict(name=k) for k in range(n))]
+        assert out == list(range(n))
+        launched, finished = set(), set()
+        for op, k in r.log:
+            if op == "launch":
+                launched.add(k)
+                assert len(launched - finished) <= 2  # never more than two detectors on the stream
+            elif op == "finish":
+                assert k in launched
+                finished.add(k)
+            else:  # prepare(k) runs while k-1 and k-2 (if any) are still queued: the overlap
+                assert {j for j in (k - 1, k - 2) if j >= 0} <= launched - finished
+        assert finished == set(range(n))
