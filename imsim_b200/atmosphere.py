@@ -15,7 +15,8 @@ definitions (von Karman phase PSD ``0.0228 r0^-5/3 (f^2 + L0^-2)^-11/6``; second
 ``exp(-D_hk / 2)`` with ``D_hk`` the structure function of the modes above ``kcrit / r0``), PARITY
 UNPINNED against GalSim's realisations; the tests check the physics (structure function, FWHM).
 The parameter draws of ``_getAtmKwargs`` and the seeing relations are the reference's own code and are
-followed line by line (with a numpy Generator in place of galsim's deviates).
+followed line by line (with a numpy Generator in place of galsim's deviates); they are PINNED: the reference's
+source of those methods, executed on recorded deviates, gives ``tests/golden/atmosphere.npz``.
 """
 from __future__ import annotations
 
@@ -30,10 +31,14 @@ ARCSEC = 206264.80624709636
 WLEN_EFF = dict(u=365.49, g=480.03, r=622.20, i=754.06, z=868.21, y=991.66)  # atmPSF.py:125 (LSE-40 table 2)
 
 
+#: galsim/kolmogorov.py ``Kolmogorov._fwhm_factor`` (FWHM = factor x lam / r0; recalled, GalSim is not in the tree)
+KOLMOGOROV_FWHM_FACTOR = 0.9758634299
+
+
 def kolmogorov_fwhm(r0_500: float, lam_nm: float) -> float:
     """``galsim.Kolmogorov(r0_500=, lam=).fwhm`` [arcsec]: 0.9759 lam / r0(lam)."""
     r0 = r0_500 * (lam_nm / 500.0) ** 1.2
-    return 0.975865 * lam_nm * 1e-9 / r0 * ARCSEC
+    return KOLMOGOROV_FWHM_FACTOR * lam_nm * 1e-9 / r0 * ARCSEC
 
 
 def vk_seeing(r0_500: float, wavelength: float, L0: float) -> float:

@@ -51,7 +51,7 @@ def kolmogorov_radius(fwhm_arcsec: float, enclosed: float) -> float:
     """Radius [arcsec] enclosing ``enclosed`` of a Kolmogorov profile of the given FWHM (0.9759 lam / r0);
     beyond the table the analytic wing E = 1 - c theta^(-5/3) is extrapolated."""
     theta, E = _kolmogorov_ee()
-    unit = fwhm_arcsec / 0.975865  # lam / r0 in arcsec
+    unit = fwhm_arcsec / 0.9758634299  # lam / r0 in arcsec (galsim Kolmogorov._fwhm_factor)
     if enclosed <= E[-2]:
         k = int(np.searchsorted(E, enclosed))
         return float(theta[max(k, 1)] * unit)

@@ -159,3 +159,58 @@ def test_sensor_cfg_parser(tmp_path):
     assert cfg["outputfiledir"] == "data/x"
     full, _ = helpers.sensor_model("lsst_itl_50_4")
     assert calculate_diff_step(full) == pytest.approx(4.4286, abs=1e-3)
+
+
+def test_flat_control_flow_matches_the_reference_source():
+    """tests/golden/flat_control_flow.npz: ``LSST_FlatBuilder.addNoise`` (imsim/flat.py:133-281), its source
+    executed against recording stand-ins (tests/golden/make_golden_flat.py).  Same section grid, borders,
+    iteration count and level per iteration, photon counts and position ranges, ``resume`` pattern here."""
+    import os
+
+    from imsim_b200.flat import build_flat, flat_iterations, flat_sections
+    from imsim_b200.sensor import Image
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "flat_control_flow.npz"))
+    for k in range(int(g["n_cases"])):
+        sed, nrow, ncol, nx, ny, buf, counts, mx = g["c%d_in" % k]
+        nrow, ncol, nx, ny, buf = int(nrow), int(ncol), int(nx), int(ny), int(buf)
+        niter, per_iter = flat_iterations(counts, mx)
+        secs = list(flat_sections(nrow, ncol, nx, ny, buf))
+        if sed == 0:
+            # pixel-area branch: one calculate_pixel_areas + one noise call per (section, iteration), on the
+            # bordered bounds, at counts_per_iter; the charge seen by the k-th call is what k iterations left
+            calls = []
+
+            class Sensor:
+                def calculate_pixel_areas(self, sec):
+                    h, w = sec.array.shape
+                    calls.append((sec.xmin, sec.xmin + w - 1, sec.ymin, sec.ymin + h - 1, float(sec.array.sum())))
+                    return 1.0
+
+            class Identity:  # the golden run's noise builder adds nothing: a Poisson deviate equal to its mean
+                def poisson(self, lam):
+                    return lam
+
+            image = Image(np.zeros((nrow, ncol)), 1, 1)
+            build_flat(image, counts, Sensor(), rng=Identity(), max_counts_per_iter=mx, nx=nx, ny=ny, buffer_size=buf,
+                       fused=False)
+            want = g["c%d_areas" % k]
+            assert len(calls) == len(want) == len(secs) * niter
+            np.testing.assert_allclose(np.array(calls), want, rtol=1e-12)
+            np.testing.assert_allclose(g["c%d_noise" % k][:, 4], per_iter, rtol=1e-15)  # level per iteration
+            np.testing.assert_allclose(image.array, g["c%d_image" % k], rtol=1e-12)
+        else:
+            # photon-shot branch: per (section, iteration) one accumulate on the bordered section with
+            # counts_per_iter x bordered area photons, uniform over [bxmin - 0.5, bxmax + 0.5), resume = it > 0
+            want = g["c%d_accumulate" % k]
+            assert len(want) == len(secs) * niter
+            row = 0
+            for _, _, _, (bx0, bx1, by0, by1) in secs:
+                for it in range(niter):
+                    w = want[row]
+                    assert tuple(w[:4]) == (bx0, bx1, by0, by1)
+                    assert w[4] == int(per_iter * (bx1 - bx0 + 1) * (by1 - by0 + 1)) and w[5] == (it > 0)
+                    # the range build_flat hands to k_flat_photons (flat.py:250-251 of the reference)
+                    assert abs(w[6] - (bx0 - 0.5)) < 1e-9 and abs(w[7] - (bx1 + 0.5)) < 1e-9
+                    assert abs(w[8] - (by0 - 0.5)) < 1e-9 and abs(w[9] - (by1 + 0.5)) < 1e-9
+                    row += 1

@@ -163,3 +163,49 @@ def test_vectorised_batch_counts_equal_list_algebra():
             ref[b, o.index] += o.phot_flux
     np.testing.assert_array_equal(counts, ref)
     np.testing.assert_array_equal(counts.sum(axis=0), flux)
+
+
+def test_batching_algebra_matches_the_reference_source():
+    """tests/golden/pooling.npz: the reference's own ``partition_objects`` / ``make_photon_batches`` /
+    ``make_photon_subbatches`` / ``make_batches`` (their source executed by tests/golden/make_golden_pooling.py on
+    recorded uniforms) against the mirror here and against the vectorised ``photon_batch_counts`` that feeds the
+    device pipeline: same objects in every batch, in the same order, with the same integer fluxes."""
+    import os
+
+    from imsim_b200.photon_pooling import photon_batch_counts
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pooling.npz"))
+    mode_of = {0: ProcessingMode.FFT, 1: ProcessingMode.PHOT, 2: ProcessingMode.FAINT}
+
+    def flat(batches):
+        off = np.cumsum([0] + [len(b) for b in batches])
+        return (off, np.array([o.index for b in batches for o in b], dtype=np.int64),
+                np.array([o.phot_flux for b in batches for o in b], dtype=np.float64))
+
+    def check(tag, batches):
+        for nm, arr in zip(("off", "idx", "flux"), flat(batches)):
+            np.testing.assert_array_equal(arr, g["%s_%s" % (tag, nm)])
+
+    for k in range(int(g["n_cases"])):
+        nobj, nbatch = (int(v) for v in g["c%d_in" % k])
+        flux, modes, uniforms = g["c%d_flux" % k], g["c%d_modes" % k], g["c%d_uniforms" % k]
+        objs = [ObjectInfo(i, int(f), mode_of[int(m)]) for i, (f, m) in enumerate(zip(flux, modes))]
+        fft, phot, faint = Builder.partition_objects(objs, nbatch)
+        for nm, lst in (("fft", fft), ("phot", phot), ("faint", faint)):
+            np.testing.assert_array_equal(np.array([o.index for o in lst], dtype=np.int64), g["c%d_%s" % (k, nm)])
+        it = iter(uniforms)
+        batches = Builder.make_photon_batches({}, {"rng": lambda: next(it)}, None, phot, faint, nbatch)
+        check("c%d_batches" % k, batches)
+        check("c%d_fftbatches" % k, list(Builder.make_batches(fft, nbatch)))
+        if batches:
+            for nsub in (1, 4, 7):
+                check("c%d_sub%d" % (k, nsub), Builder.make_photon_subbatches(batches[0], nsub))
+        # the vectorised form: counts[b, j] photons of non-FFT object j in batch b
+        sel = np.nonzero(modes != 0)[0]
+        it = iter(uniforms)
+        counts = photon_batch_counts(flux[sel], modes[sel] == 2, nbatch, lambda: next(it))
+        want = np.zeros((nbatch, nobj), dtype=np.int64)
+        off, idx, fl = g["c%d_batches_off" % k], g["c%d_batches_idx" % k], g["c%d_batches_flux" % k]
+        for b in range(len(off) - 1):
+            np.add.at(want[b], idx[off[b]:off[b + 1]], fl[off[b]:off[b + 1]].astype(np.int64))
+        np.testing.assert_array_equal(counts, want[:, sel])

@@ -79,7 +79,7 @@ def test_seeing_relations_follow_the_reference():
     for L0, target in ((25.0, 0.7), (12.0, 1.1), (80.0, 0.5)):
         r0 = r0_500_for_seeing(622.2, L0, target)
         assert abs(vk_seeing(r0, 622.2, L0) - target) < 1e-9
-    assert abs(kolmogorov_fwhm(0.2, 500.0) - 0.975865 * 500e-9 / 0.2 * 206264.80624709636) < 1e-12
+    assert abs(kolmogorov_fwhm(0.2, 500.0) - 0.9758634299 * 500e-9 / 0.2 * 206264.80624709636) < 1e-12
     psf = AtmosphericPSF(1.2, 0.7, "r", rng=5, screen_size=25.6, screen_scale=0.1)
     assert abs(psf.targetFWHM - 0.7 * 1.2**0.6 * (622.2 / 500) ** -0.3) < 1e-15  # atmPSF.py:128
     kw = psf.kw
@@ -116,3 +116,47 @@ def test_second_kick_table():
     # with no turbulence above kcrit the table is the annular Airy pattern: 50 % inside ~ 0.5 lam / D
     airy, _, _ = second_kick_table(622.2, 1e6, 8.36, 0.61, 0.2)
     assert np.interp(np.log(2.0), t, airy) < 0.05
+
+
+def test_atmosphere_parameter_draws_match_the_reference_source():
+    """tests/golden/atmosphere.npz: imsim/atmPSF.py:211-296 executed on recorded deviates
+    (tests/golden/make_golden_atmosphere.py).  Same draws in, same atmosphere parameters out."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "atmosphere.npz"))
+    for (r0, lam, L0), want in zip(g["vk_grid"], g["vk_seeing"]):
+        assert abs(vk_seeing(r0, lam, L0) - want) <= 1e-15 * max(1.0, want)
+    for (lam, L0, target), want in zip(g["r0_grid"], g["r0_500"]):
+        assert abs(r0_500_for_seeing(lam, L0, target) - want) <= 1e-12
+    bands = {365.49: "u", 480.03: "g", 622.2: "r", 754.06: "i", 868.21: "z", 991.66: "y"}
+
+    class Replay:
+        """numpy-Generator look-alike replaying the recorded deviates (Gaussian and uniform streams apart,
+        like the reference's two deviates on one rng are in the stand-in)."""
+
+        def __init__(self, gauss, unif):
+            self.gauss, self.unif, self.ng, self.nu = gauss, unif, 0, 0
+
+        def standard_normal(self):
+            self.ng += 1
+            return self.gauss[self.ng - 1]
+
+        def random(self):
+            self.nu += 1
+            return self.unif[self.nu - 1]
+
+    for k in range(int(g["n_cases"])):
+        wl, airmass, seeing = g["case%d_in" % k]
+        psf = AtmosphericPSF.__new__(AtmosphericPSF)
+        psf.rng = Replay(g["case%d_gauss" % k], g["case%d_unif" % k])
+        psf.wlen_eff, psf.screen_size, psf.screen_scale = wl, 819.2, 0.1
+        psf.targetFWHM = seeing * airmass ** 0.6 * (wl / 500.0) ** (-0.3)
+        assert bands[float(wl)] in "ugrizy"
+        kw = psf._getAtmKwargs()
+        assert [psf.rng.ng, psf.rng.nu] == list(g["case%d_used" % k])  # same number of draws, rejections included
+        assert abs(kw["r0_500"] - float(g["case%d_r0_500" % k])) <= 1e-12
+        np.testing.assert_array_equal(np.asarray(kw["L0"]), g["case%d_L0" % k])
+        np.testing.assert_array_equal(np.asarray(kw["speed"]), g["case%d_speed" % k])
+        np.testing.assert_allclose(np.degrees(kw["direction"]), g["case%d_direction_deg" % k], rtol=1e-15, atol=0)
+        np.testing.assert_array_equal(np.asarray(kw["altitude"]), g["case%d_altitude" % k])
+        np.testing.assert_allclose(np.asarray(kw["r0_weights"]), g["case%d_weights" % k], rtol=1e-15, atol=0)
