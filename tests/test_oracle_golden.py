@@ -225,3 +225,25 @@ def test_cosmic_ray_oracle_matches_the_reference_function():
         crs[int(fid)].append((int(g["x0"][k]), int(g["y0"][k]), g["pixel_values"][edges[k]:edges[k + 1]]))
     out = R.paint_cosmic_rays(g["image_in"], list(crs.values()), g["uniforms"], int(g["num_crs"]))
     assert np.array_equal(out, g["image_out"]) and (out != g["image_in"]).sum() > 5000
+
+
+def test_tree_ring_function_matches_the_reference_class_densely():
+    """tests/golden/tree_rings_dense.npz: the reference's own ``TreeRingRadialFunction`` (source executed by
+    tests/golden/make_golden_tree_rings_dense.py) on the nodes of the 2667-point table and off the nodes, with its
+    derivative -- against the host class, the C oracle and the table the sensor is given."""
+    g = helpers.golden("tree_rings_dense.npz")
+    blocks = helpers.golden("tree_rings.npz")
+    keys = [k for k in blocks.files if "|" in k]
+    assert len(keys) == 4
+    for key in keys:
+        f = TreeRingRadialFunction(list(blocks[key]))
+        scale = np.abs(g["f_nodes|" + key]).max()
+        np.testing.assert_allclose([f(r) for r in g["r_nodes"]], g["f_nodes|" + key], rtol=0, atol=1e-13 * scale)
+        np.testing.assert_allclose([f(r) for r in g["r_off"]], g["f_off|" + key], rtol=0, atol=1e-13 * scale)
+        np.testing.assert_allclose([f.dfdr(r) for r in g["r_off"]], g["dfdr_off|" + key], rtol=0,
+                                   atol=1e-13 * np.abs(g["dfdr_off|" + key]).max())
+        val_o = orc.treering_func(f.A, f.B, f.cfreqs, f.cphases, f.sfreqs, f.sphases, g["r_off"])
+        np.testing.assert_allclose(val_o, g["f_off|" + key], rtol=0, atol=1e-12 * scale)
+        tab = RadialTable.from_func(f, 0.0, 8000.0, 2667)
+        np.testing.assert_array_equal(tab.x, g["r_nodes"])
+        np.testing.assert_allclose(tab.f, g["f_nodes|" + key], rtol=0, atol=1e-13 * scale)
