@@ -31,6 +31,7 @@ struct Piece {
 // do not exist.
 class CopyPool {
     std::vector<std::thread> th_;
+    std::mutex run_mu_;  // one copy job at a time: calls on different contexts may come from different host threads
     std::mutex m_;
     std::condition_variable cv_work_, cv_done_;
     const std::vector<Piece>* pieces_ = nullptr;
@@ -73,6 +74,7 @@ public:
     int threads() const { return (int)th_.size() + 1; }
     // copies every piece; the calling thread takes its share
     void run(const std::vector<Piece>& p) {
+        std::lock_guard<std::mutex> serial(run_mu_);
         if (th_.empty() || p.size() <= 1) {
             for (const Piece& q : p) memcpy(q.dst, q.src, q.n);
             return;
