@@ -18,6 +18,12 @@
  *   - `where` says where the array pointers of a call live:
  *       B2_HOST   : host memory (numpy).  The library stages the arrays
  *                   through device scratch; copies are part of the call.
+ *                   b2_rubin_optics and b2_sensor_accumulate move calls of
+ *                   B2_PIPE_MIN (default 2^18) photons or more through a
+ *                   ring of pinned slots in chunks of B2_PIPE_CHUNK (2^19)
+ *                   photons, copied by B2_HOST_THREADS (min(8, cores)) host
+ *                   threads while the previous chunks are transferred and
+ *                   computed; results are identical to the single copy.
  *       B2_DEVICE : device memory (e.g. torch.empty(..., device='cuda')).
  *   - all photon arrays are SoA, float64, length n (GalSim PhotonArray layout).
  *   - all calls are asynchronous on the context's stream for B2_DEVICE and
