@@ -17,6 +17,9 @@ config/imsim-config-photon-pooling.yaml:33).
            the image and the deposited flux, every step.
 `roofline`: dominant kernel (k_rubin_optics) against HBM (algorithmic 96 B/photon) and, because
            that kernel is FP64-pipe bound, against the measured FP64 FMA ceiling (`roofline_fp64`).
+`visit`  : the other half of BASELINE.json's metric, LSSTCam visits per hour on these N GPUs: the full chain
+           of a synthetic 189-CCD visit sharded by detector over the ranks (`visit_for_line`; --no-visit-line
+           skips it; `--visit ...` runs other variants of it alone).
 With N > 1 every rank simulates its own detector (weak scaling, no data-path collective).
 """
 import argparse
@@ -211,32 +214,29 @@ def run_reference(args):
     return 0
 
 
-def run_visit(args):
-    """C5: one synthetic LSSTCam visit, sharded by detector (weak scaling unit = CCD)."""
+def simulate_visit(opts, rank, world, local, barrier=None):
+    """This rank's share of one synthetic LSSTCam visit (C5): the detectors LPT assigns to it, software-pipelined
+    (visit.DetectorRunner.run_many), simulated ``opts.visit_repeat`` times.  No collective in here unless
+    ``barrier`` is given (called before each repetition).  Returns (per-repetition wall times, records of the last
+    repetition)."""
     import torch
 
     import helpers
     from imsim_b200.detector import lsstcam_science_detectors
     from imsim_b200.flat import wavelength_cdf
-    from imsim_b200.sharding import gather_visit_metadata, lpt_partition
+    from imsim_b200.sharding import lpt_partition
     from imsim_b200.visit import DetectorRunner, synthetic_catalog, synthetic_objects
 
-    rank, world, local = dist_info()
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dets = lsstcam_science_detectors()[: args.visit_ccds]
+    dets = lsstcam_science_detectors()[: opts.visit_ccds]
     rng = np.random.default_rng(5)
-    costs = {d: float(args.visit_photons * rng.lognormal(0.0, 0.3)) for d in dets}  # bright-star CCDs cost more
+    costs = {d: float(opts.visit_photons * rng.lognormal(0.0, 0.3)) for d in dets}  # bright-star CCDs cost more
     mine = lpt_partition(costs, world)[rank]
     models = {"e2v": helpers.sensor_model("lsst_e2v_50_4"), "itl": helpers.sensor_model("lsst_itl_50_4")}
     tr = helpers.tree_ring_table("R22_S11")
     psf = None
     wave = np.linspace(550.0, 690.0, 29)
     cdf = wavelength_cdf(wave, np.ones_like(wave))
-    if args.visit_catalog:
+    if opts.visit_catalog:
         # stage 1 from catalogue rows: one atmosphere realisation per visit (6 screens of 8192^2 at 0.1 m), 8 SEDs
         from imsim_b200.atmosphere import AtmosphericPSF
 
@@ -246,28 +246,46 @@ def run_visit(args):
     runner = DetectorRunner(local, models, helpers.absorption(), tree_rings={d: tr for d in mine}, psf=psf)
 
     def job(d):
-        make = synthetic_catalog if args.visit_catalog else synthetic_objects
+        make = synthetic_catalog if opts.visit_catalog else synthetic_objects
         i = dets.index(d)
         # the catalogue is built inside prepare(), i.e. while the previous detector's kernels run
         return dict(det_name=d, objects=lambda: make(20000, 4096, 4004, seed=i, total_photons=costs[d]), nbatch=10,
-                    wavelength_cdf=cdf, det_index=i, readout=args.visit_readout, sky_level=args.visit_sky)
+                    wavelength_cdf=cdf, det_index=i, readout=opts.visit_readout, sky_level=opts.visit_sky)
 
-    # The visit is simulated --visit-repeat times by the same process and the LAST one is reported: the first
+    # The visit is simulated visit_repeat times by the same process and the LAST one is reported: the first
     # carries the one-time initialisation of a process (2.5 GB of boundary arrays per vendor model, the packed
     # phase screens, pinned result buffers, the caching allocator's first cudaMallocs), which a production run
     # pays once for all its visits, as it does the generation of the atmosphere.  first_visit_wall_s keeps it.
-    walls = []
-    for rep in range(max(1, args.visit_repeat)):
-        if world > 1:
-            dist.barrier()
+    walls, recs = [], []
+    for rep in range(max(1, opts.visit_repeat)):
+        if barrier is not None:
+            barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        if args.visit_serial:  # one detector at a time, host and device in turn (the pre-pipelining behaviour)
+        if opts.visit_serial:  # one detector at a time, host and device in turn (the pre-pipelining behaviour)
             recs = [runner.run(**job(d))[0] for d in mine]
         else:
             recs = [rec for rec, _ in runner.run_many(job(d) for d in mine)]
         torch.cuda.synchronize()
         walls.append(time.perf_counter() - t0)
+    return walls, recs
+
+
+def run_visit(args):
+    """C5: one synthetic LSSTCam visit, sharded by detector (weak scaling unit = CCD)."""
+    import torch
+
+    from imsim_b200.sharding import gather_visit_metadata
+
+    rank, world, local = dist_info()
+    barrier = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        barrier = dist.barrier
+    torch.cuda.set_device(local)
+    walls, recs = simulate_visit(args, rank, world, local, barrier=barrier)
     wall = walls[-1]
     wt = torch.tensor([wall], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -291,6 +309,45 @@ def run_visit(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def visit_for_line(args, rank, world, local, dev):
+    """The second half of BASELINE.json's metric -- LSSTCam visits per hour on these GPUs -- for the bench line:
+    the full chain (catalogue objects behind the atmosphere -> optics -> silicon -> sky -> electronics readout) of a
+    synthetic 189-CCD visit, sharded by detector over the ranks, second visit of the process.  Ranks do not
+    synchronise inside the simulation, and a rank that fails still takes part in the two reductions below."""
+    import torch
+
+    opts = argparse.Namespace(visit_catalog=True, visit_readout=True, visit_sky=800.0, visit_ccds=args.visit_ccds,
+                              visit_photons=args.visit_photons, visit_repeat=2, visit_serial=False)
+    mx = [0.0, 0.0, 0.0, 0.0]  # wall of the reported visit, wall of the first, GPU time, failure flag
+    sm = [0.0, 0.0]            # photons, CCDs
+    err = ""
+    try:
+        walls, recs = simulate_visit(opts, rank, world, local)
+        mx = [walls[-1], walls[0], sum(r["gpu_ms"] for r in recs) * 1e-3, 0.0]
+        sm = [float(sum(r["photons"] for r in recs)), float(len(recs))]
+    except Exception as e:  # the headline line must survive a failure of the extra measurement
+        mx[3], err = 1.0, "%s: %s" % (type(e).__name__, e)
+    tmx = torch.tensor(mx, dtype=torch.float64, device=dev)
+    tsm = torch.tensor(sm, dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(tmx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsm, op=dist.ReduceOp.SUM)
+    mx, sm = tmx.tolist(), tsm.tolist()
+    if mx[3] != 0.0 or mx[0] <= 0.0:
+        return {"error": err or "a rank failed"}
+    if int(sm[1]) != 189:
+        err = "partial visit (%d of 189 CCDs): visits_per_hour is per this many CCDs" % int(sm[1])
+    return {"visits_per_hour": 3600.0 / mx[0], "note": err, "wall_s_max_rank": mx[0], "gpu_s_max_rank": mx[2],
+            "first_visit_wall_s_max_rank": mx[1], "ccds": int(sm[1]), "photons": int(sm[0]), "n_gpus": world,
+            "visits_simulated": 2, "reported": "second visit of the process (the first pays the one-time allocations)",
+            "chain": "catalogue objects (stars, bulge / disc / knots galaxies, 8 SEDs) -> six-screen atmosphere + second "
+                     "kick -> RubinDiffractionOptics -> SiliconSensor (brighter-fatter + tree rings, 10 batches) -> "
+                     "sky through the pixel areas -> bleed / dark / CTI / noise -> int32 segments, e-image and raw "
+                     "segments to pinned host buffers; 189 CCDs by LPT over the ranks, no collective on the path"}
 
 
 def workload_config(pool, note=""):
@@ -332,6 +389,8 @@ def main():
                          "(steady state; the first also pays the one-time allocations)")
     ap.add_argument("--visit-serial", action="store_true",
                     help="with --visit: no software pipelining (prepare, launch and finish each detector in turn)")
+    ap.add_argument("--no-visit-line", action="store_true",
+                    help="skip the synthetic full-chain visit that adds `visit` (visits per hour) to the bench line")
     ap.add_argument("--kernel-timing", action="store_true",
                     help="diagnostic: bracket every kernel with CUDA events (B2_TIMING=1) and print the breakdown "
                          "to stderr; adds event overhead, do not quote `value` from such a run")
@@ -471,6 +530,9 @@ def main():
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
     e2e_value = world * P * e2e_K / (float(et.item()) * 1e-3)
 
+    # ---- the other half of the metric: LSSTCam visits per hour on these GPUs (every rank takes part) ----
+    visit = None if args.no_visit_line else visit_for_line(args, rank, world, local, dev)
+
     # ---- roofline of the dominant kernel + CPU baseline (rank 0 only) -------------------
     if rank == 0:
         peaks = {}
@@ -508,6 +570,8 @@ def main():
                               "peak_source": "b2_fma_peak measured in this run", "fp32_peak": fp32_peak},
             "breakdown_ms": {"step": total_ms / K, dominant: tr_ms, "rest_of_step": total_ms / K - tr_ms},
         }
+        if visit is not None:
+            line["visit"] = visit
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample, 1)
         print(json.dumps(line))
