@@ -193,7 +193,13 @@ def run_reference(args):
         return 0
     from oracle import oracle as orc
 
-    threads = orc.max_threads()
+    # every host thread this process may run on: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # silently turn the "all host threads" arm into a single-thread one for N > 1
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    threads = max(threads, orc.max_threads())
     n = args.ref_sample
     vals = []
     for _ in range(args.warmup):
