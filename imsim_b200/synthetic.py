@@ -1,7 +1,7 @@
 """Synthetic per-detector set-ups (telescope + WCS pair + detector geometry) for
 benchmarks, smoke tests and parity tests: the stand-in for what
 imsim/telescope_loader.py and imsim/batoid_wcs.py hand to the photon ops at run
-time.  SYNTHETIC DATA; see ``telescope.rubin_like``.
+time.  SYNTHETIC DATA around the LSST v3.3 design of ``telescope.lsst_v33``.
 
 The image WCS is *fitted to chief-ray traces through the same telescope*, as the
 reference does (imsim/batoid_wcs.py:408-453), so photons land within a few
@@ -15,7 +15,7 @@ from typing import Callable, Optional
 import numpy as np
 
 from .detector import DetectorGeometry, lsstcam_like
-from .telescope import AIR, Telescope, rubin_like
+from .telescope import UNIT_AIR, Telescope, rubin_like
 from .wcs import TanSipWCS, field_wcs, fit_tan_sip, tan_deproject
 
 # tracer(telescope, thx, thy, wavelength_m) -> (x, y) on the detector plane [m],
@@ -34,12 +34,13 @@ class DetectorSetup:
     wavelength_nm: float
 
 
-def chief_ray_inputs(thx, thy, wavelength_m):
-    """Stop-plane rays for ``batoid.RayVector.fromFieldAngles``-like chief rays."""
+def chief_ray_inputs(thx, thy, wavelength_m, medium=None):
+    """Stop-plane rays for ``batoid.RayVector.fromFieldAngles``-like chief rays; ``medium`` is the
+    telescope's ``in_medium`` (|v| = 1/n, imsim/photon_ops.py:144-147)."""
     thx, thy = np.asarray(thx, float), np.asarray(thy, float)
     n = thx.size
     g = 1.0 / np.sqrt(1.0 + thx * thx + thy * thy)
-    nair = float(AIR.n(wavelength_m))
+    nair = float((UNIT_AIR if medium is None else medium).n(wavelength_m))
     z = np.zeros(n)
     return (z.copy(), z.copy(), z.copy(), thx * g / nair, thy * g / nair, -g / nair, z.copy(),
             np.full(n, wavelength_m))
@@ -50,7 +51,7 @@ def gpu_tracer(ctx) -> Tracer:
 
     def trace(tel, thx, thy, wl):
         ctx.set_telescope(tel)
-        x, y, z, vx, vy, vz, t, w = (np.ascontiguousarray(a) for a in chief_ray_inputs(thx, thy, wl))
+        x, y, z, vx, vy, vz, t, w = (np.ascontiguousarray(a) for a in chief_ray_inputs(thx, thy, wl, tel.in_medium))
         vig = np.zeros(x.size, np.uint8)
         fail = np.zeros(x.size, np.uint8)
         ctx.trace_rays(x, y, z, vx, vy, vz, t, w, vig, fail)

@@ -67,7 +67,7 @@ def oracle_tracer():
 
     def trace(tel, thx, thy, wl):
         bt, extras = tel.flatten()
-        x, y, z, vx, vy, vz, t, w = chief_ray_inputs(thx, thy, wl)
+        x, y, z, vx, vy, vz, t, w = chief_ray_inputs(thx, thy, wl, tel.in_medium)
         out = orc.trace_rays(bt, extras, x, y, z, vx, vy, vz, t, w)
         return out[0], out[1]
 

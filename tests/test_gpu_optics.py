@@ -445,3 +445,26 @@ def test_time_and_pupil_samplers():
     t2, u2, v2 = np.empty(n // 2), np.empty(n // 2), np.empty(n // 2)
     ctx.sample_time_pupil(t2, u2, v2, 5.0, 30.0, 2.558, 4.18, 99, n // 2)
     assert np.array_equal(t2, t[n // 2:]) and np.array_equal(u2, u[n // 2:]) and np.array_equal(v2, v[n // 2:])
+
+
+@pytest.mark.parametrize("program", ["1", "0"])
+def test_opd_zemax_on_device(program, monkeypatch):
+    """Ray trace PINNED on the device: the CUDA trace (surface program and interpreter) of the LSST v3.3
+    prescription against the Zemax wavefront of the reference's tests/test_opd.py:16-95, same tolerances."""
+    from test_oracle_golden import check_opd_against_zemax
+
+    monkeypatch.setenv("B2_PROGRAM", program)
+    ctx = _ctx()
+
+    def trace(tel, x, y, z, vx, vy, vz, t, wl):
+        ctx.set_telescope(tel)
+        assert ctx.program == (1 if program == "1" else 0)
+        a = [np.ascontiguousarray(v, dtype=np.float64).copy() for v in (x, y, z, vx, vy, vz, t)]
+        w = np.full(a[0].size, wl)
+        vig = np.zeros(a[0].size, np.uint8)
+        fail = np.zeros(a[0].size, np.uint8)
+        ctx.trace_rays(*a, w, vig, fail)
+        return (*a, vig, fail)
+
+    rms = check_opd_against_zemax(trace)
+    assert rms < 0.005  # nm

@@ -247,3 +247,51 @@ def test_tree_ring_function_matches_the_reference_class_densely():
         tab = RadialTable.from_func(f, 0.0, 8000.0, 2667)
         np.testing.assert_array_equal(tab.x, g["r_nodes"])
         np.testing.assert_allclose(tab.f, g["f_nodes|" + key], rtol=0, atol=1e-13 * scale)
+
+
+def _zemax_case():
+    from imsim_b200.telescope import lsst_v33
+
+    g = helpers.golden("zemax_opd.npz")
+    tel = lsst_v33("r").with_locally_shifted_item("M2", g["m2_shift"])
+    return g, tel, np.radians(float(g["thx_deg"])), np.radians(float(g["thy_deg"])), float(g["wavelength_nm"])
+
+
+def check_opd_against_zemax(trace):
+    """The reference's tests/test_opd.py:16-95 with its own tolerances, for any ray tracer."""
+    from imsim_b200 import opd
+
+    g, tel, thx, thy, wl_nm = _zemax_case()
+    w, grid = opd.wavefront(trace, tel, thx, thy, wl_nm * 1e-9, nx=255, projection="zemax")
+    zem = g["opd_waves"]
+    ok = (zem != 0.0) & ~np.isnan(w)  # test_opd.py:88-89: Zemax writes 0 where vignetted and models the spider
+    assert ok.sum() > 28000
+    np.testing.assert_allclose(w[ok] * wl_nm, zem[ok] * wl_nm, atol=0.01, rtol=1e-5)  # nm, test_opd.py:91-96
+    zk = opd.annular_zernikes(w, grid, jmax=28)
+    np.testing.assert_allclose(zk[1:] * wl_nm, g["annular_zernike_waves"] * wl_nm, atol=0.2, rtol=1e-3)  # :66-72
+    return float(np.sqrt(np.mean((w[ok] - zem[ok]) ** 2)) * wl_nm)
+
+
+def test_opd_zemax():
+    """Ray trace PINNED: the oracle's trace of the LSST v3.3 prescription reproduces the Zemax wavefront that
+    the reference's test_opd_zemax compares batoid with (0.01 nm)."""
+
+    def trace(tel, x, y, z, vx, vy, vz, t, wl):
+        return orc.trace_rays(*tel.flatten(), x, y, z, vx, vy, vz, t, wl)
+
+    rms = check_opd_against_zemax(trace)
+    assert rms < 0.005  # nm
+
+
+def test_annular_zernike_basis_is_orthonormal():
+    from imsim_b200 import opd
+
+    g = np.linspace(-1, 1, 801)
+    X, Y = np.meshgrid(g, g)
+    r = np.hypot(X, Y)
+    ok = (r <= 1.0) & (r >= 0.612)
+    B = opd.annular_zernike_basis(15, X[ok], Y[ok], 1.0, 0.612)[1:]
+    G = B @ B.T / ok.sum()
+    np.testing.assert_allclose(G, np.eye(15), atol=6e-3)
+    assert opd.noll_to_nm(4) == (2, 0) and opd.noll_to_nm(7) == (3, -1) and opd.noll_to_nm(8) == (3, 1)
+    assert opd.noll_to_nm(11) == (4, 0) and opd.noll_to_nm(28) == (6, 6)
