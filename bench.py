@@ -133,18 +133,18 @@ class ClockSampler:
 
 
 def sensor_inputs():
-    import helpers
+    from imsim_b200 import workload_data as wd
 
-    cfg, dat = helpers.sensor_model("lsst_e2v_50_4")
-    tr = helpers.tree_ring_table("R22_S11")
-    aw, al = helpers.absorption()
+    cfg, dat = wd.sensor_model("lsst_e2v_50_4")
+    tr = wd.tree_ring_table("R22_S11")
+    aw, al = wd.absorption()
     return cfg, dat, tr, (aw, al)
 
 
 def cpu_baseline(n_sample, threads, det_name="R22_S11", seed=0):
     """Time the CPU oracle (restatement of the reference path, kind='port') on a bounded sample
     of the same workload: optics (+diffraction, FocusDepth, Refraction) then sensor (BF + tree rings)."""
-    import helpers
+    import helpers  # tests/helpers.py: oracle set-up (this leg is the one place bench.py may run oracle/)
     from imsim_b200 import _abi
     from imsim_b200.synthetic import make_detector_setup, synthetic_photons
     from oracle import oracle as orc
@@ -227,7 +227,7 @@ def simulate_visit(opts, rank, world, local, barrier=None):
     repetition)."""
     import torch
 
-    import helpers
+    from imsim_b200 import workload_data as helpers
     from imsim_b200.detector import lsstcam_science_detectors
     from imsim_b200.flat import wavelength_cdf
     from imsim_b200.sharding import lpt_partition
@@ -410,7 +410,7 @@ def main():
 
     import torch
 
-    import helpers
+    from imsim_b200 import workload_data as helpers
     from imsim_b200 import OpticsContext, _abi, launch_count
     from imsim_b200.photon_pooling import DevicePhotons, PhotonPool, PinnedPhotons
     from imsim_b200.sensor import Image, SiliconSensor

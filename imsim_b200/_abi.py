@@ -6,7 +6,7 @@ every struct against ``b2_sizeof`` of the loaded library.
 """
 import ctypes as C
 
-B2_ABI_VERSION = 1
+B2_ABI_VERSION = 2
 B2_HOST = 0
 B2_DEVICE = 1
 

@@ -118,8 +118,9 @@ _SIGNATURES = {
     "b2_flat_step": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int32, vp, vp, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64,
                                C.c_int32, C.c_int32, C.POINTER(_abi.B2AccumStats)]),
     "b2_pool_step": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.POINTER(_abi.B2OpticsOptions), C.c_double,
-                               C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32,
-                               C.c_int32, C.c_int32, C.POINTER(_abi.B2OpticsStats), C.POINTER(_abi.B2AccumStats)]),
+                               C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                               C.c_int32, C.c_int32, C.c_int32, C.POINTER(_abi.B2OpticsStats),
+                               C.POINTER(_abi.B2AccumStats)]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

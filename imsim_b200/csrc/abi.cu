@@ -70,7 +70,13 @@ extern "C" int b2_ctx_destroy(b2_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     b2_stage1_release(ctx);
     b2_pipe_release(ctx);
-    for (void* p : ctx->extras) cudaFree(p);
+    for (auto& e : ctx->extras) {
+        if (e.dev.ptr) cudaFree(e.dev.ptr);
+        for (int k = 0; k < 2; ++k) {
+            if (e.pin[k]) cudaFreeHost(e.pin[k]);
+            if (e.ev[k]) cudaEventDestroy(e.ev[k]);
+        }
+    }
     if (ctx->scratch.ptr) cudaFree(ctx->scratch.ptr);
     if (ctx->stats.ptr) cudaFree(ctx->stats.ptr);
     delete ctx;

@@ -122,7 +122,16 @@ struct b2_ctx {
     bool have_tel = false, have_wcs = false, have_det = false;
     int program = 0;         // surface program matching the uploaded telescope (optics_device.cuh), 0 = generic
     DevOptics opt;           // host copy, passed to kernels by value (__grid_constant__)
-    std::vector<void*> extras;  // device allocations owned by the context
+    // extra sag tables (b2_telescope_set_extra): one grow-only device buffer per surface, written in stream
+    // order, fed from two alternating pinned staging slots so that re-uploading a telescope per detector
+    // neither leaks nor synchronises the stream
+    struct ExtraTable {
+        Scratch dev;
+        void* pin[2] = {nullptr, nullptr};
+        size_t pin_bytes[2] = {0, 0};
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        int next = 0;
+    } extras[B2_DEV_MAX_SURF];
     Scratch scratch;         // staging for B2_HOST calls
     Scratch stats;           // small device buffer for counters
     B2TanSip img_host, field_host;

@@ -371,12 +371,25 @@ extern "C" int b2_telescope_set_extra(b2_ctx* ctx, int is, int kind, const doubl
     if (kind == B2_EXTRA_POLY2D)
         B2_REQUIRE(n == (int64_t)d.poly_n * d.poly_n && d.poly_n <= B2_MAX_POLY_ORDER, "b2_telescope_set_extra: poly size mismatch");
     B2_CUDA(cudaSetDevice(ctx->device));
-    void* p = nullptr;
-    B2_CUDA(cudaMalloc(&p, n * sizeof(double)));
-    ctx->extras.push_back(p);
-    B2_CUDA(cudaMemcpyAsync(p, data, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    B2_CUDA(cudaStreamSynchronize(ctx->stream));
-    d.extra = (const double*)p;
+    b2_ctx::ExtraTable& e = ctx->extras[is];
+    const size_t bytes = (size_t)n * sizeof(double);
+    if (b2_scratch_reserve(ctx, e.dev, bytes)) return 1;  // grow-only, reused by every later upload
+    const int k = e.next;
+    e.next ^= 1;
+    if (e.pin_bytes[k] < bytes) {
+        if (e.ev[k]) B2_CUDA(cudaEventSynchronize(e.ev[k]));
+        if (e.pin[k]) B2_CUDA(cudaFreeHost(e.pin[k]));
+        e.pin[k] = nullptr;
+        e.pin_bytes[k] = 0;
+        B2_CUDA(cudaMallocHost(&e.pin[k], bytes));
+        e.pin_bytes[k] = bytes;
+    }
+    if (!e.ev[k]) B2_CUDA(cudaEventCreateWithFlags(&e.ev[k], cudaEventDisableTiming));
+    else B2_CUDA(cudaEventSynchronize(e.ev[k]));  // the copy that last read this slot (two uploads ago)
+    memcpy(e.pin[k], data, bytes);
+    B2_CUDA(cudaMemcpyAsync(e.dev.ptr, e.pin[k], bytes, cudaMemcpyHostToDevice, ctx->stream));
+    B2_CUDA(cudaEventRecord(e.ev[k], ctx->stream));
+    d.extra = (const double*)e.dev.ptr;
     d.extra_kind = kind;
     select_program(ctx);
     return 0;

@@ -15,7 +15,7 @@
 
 struct PoolParams {
     double t0, exptime, r_in, r_out;
-    uint64_t sampler_seed, sensor_seed, offset;
+    uint64_t sampler_seed, sensor_seed, offset, sensor_offset;
     int write_back;  // also store the traced photons (x, y, dxdz, dydz, flux) like the unfused ops
 };
 
@@ -51,7 +51,7 @@ k_pool_step(const __grid_constant__ DevOptics o, const __grid_constant__ B2Optic
             flux[i] = r.flux;
         }
         double g1, g2, unf, udep;
-        sensor_draws(pp.sensor_seed, idx, g1, g2, unf, udep);
+        sensor_draws(pp.sensor_seed, pp.sensor_offset + (uint64_t)i, g1, g2, unf, udep);
         to_slow = sensor_fast_path(s, r.x, r.y, true, r.dxdz, r.dydz, true, wl, r.flux, g1, g2, unf, udep, rec,
                                    my_added, nb9, ndrop);
     }
@@ -92,8 +92,8 @@ static int pool_occ(int program) {
 extern "C" int b2_pool_step(b2_ctx* ctx, b2_sensor* sensor, int64_t n, double* x, double* y, double* dxdz,
                             double* dydz, double* flux, const double* wl_nm, const B2OpticsOptions* opt, double t0,
                             double exptime, double r_inner, double r_outer, uint64_t sampler_seed,
-                            uint64_t sensor_seed, uint64_t photon_offset, int32_t resume, int32_t recalc,
-                            int32_t write_back, B2OpticsStats* ostats, B2AccumStats* astats) {
+                            uint64_t sensor_seed, uint64_t photon_offset, uint64_t sensor_offset, int32_t resume,
+                            int32_t recalc, int32_t write_back, B2OpticsStats* ostats, B2AccumStats* astats) {
     B2_REQUIRE(ctx && sensor && opt, "b2_pool_step: null argument");
     B2_REQUIRE(sensor->ctx == ctx, "b2_pool_step: the sensor belongs to another context");
     B2_REQUIRE(ctx->have_tel && ctx->have_wcs && ctx->have_det, "b2_pool_step: telescope / wcs / detector not uploaded");
@@ -111,7 +111,7 @@ extern "C" int b2_pool_step(b2_ctx* ctx, b2_sensor* sensor, int64_t n, double* x
     unsigned long long* dostats = (unsigned long long*)ctx->stats.ptr;
     B2_CUDA(cudaMemsetAsync(dostats, 0, 64, st));
     if (n > 0) {
-        PoolParams pp{t0, exptime, r_inner, r_outer, sampler_seed, sensor_seed, photon_offset, write_back};
+        PoolParams pp{t0, exptime, r_inner, r_outer, sampler_seed, sensor_seed, photon_offset, sensor_offset, write_back};
         unsigned blocks = (unsigned)((n + 255) / 256);
         {
             B2_TIMED("k_pool_step", st);

@@ -167,19 +167,24 @@ class LSST_PhotonPoolingImageBuilder:
                 objects_by_mode[ProcessingMode.FAINT])
 
 
-def photon_batch_counts(phot_flux, modes_faint, nbatch: int, ud):
+def photon_batch_counts(phot_flux, modes_faint, nbatch: int, ud, clamp: bool = True):
     """Vectorised ``partition_objects`` + ``make_photon_batches`` for the device pipeline: integer
     photon counts per (batch, object), identical to the list-based reference algebra
-    (imsim/photon_pooling.py:300-311,374-377).  ``phot_flux``: int64 array; ``modes_faint``: bool array
-    (True = FAINT); ``ud``: callable returning uniforms in [0, 1), called once per faint object in order."""
+    (imsim/photon_pooling.py:74,117,300-311,374-377).  ``phot_flux``: int64 array; ``modes_faint``: bool array
+    (True = FAINT); ``ud``: callable returning uniforms in [0, 1), called once per faint object in order.
+
+    As in the reference, the faint partition uses the configured ``nbatch`` (``phot_flux < nbatch``), and the
+    number of batches is then clamped to ``max(min(nbatch, n_bright), 1)`` before the flux split (Q9): the
+    result has that many rows (``clamp=False``: ``make_photon_batches`` alone, ``nbatch`` rows)."""
     f = np.asarray(phot_flux, dtype=np.int64)
     faint = np.asarray(modes_faint, dtype=bool) | (f < nbatch)
-    counts = np.zeros((nbatch, f.size), dtype=np.int64)
-    i = np.arange(nbatch, dtype=np.int64)[:, None]
     bright = ~faint
-    counts[:, bright] = (f[None, bright] * (i + 1)) // nbatch - (f[None, bright] * i) // nbatch
+    nb = max(min(int(nbatch), int(bright.sum())), 1) if clamp else int(nbatch)
+    counts = np.zeros((nb, f.size), dtype=np.int64)
+    i = np.arange(nb, dtype=np.int64)[:, None]
+    counts[:, bright] = (f[None, bright] * (i + 1)) // nb - (f[None, bright] * i) // nb
     for k in np.nonzero(faint)[0]:
-        counts[int(ud() * nbatch), k] = f[k]
+        counts[int(ud() * nb), k] = f[k]
     return counts
 
 
@@ -322,7 +327,8 @@ class PhotonPool:
         _lib.check(_lib.load().b2_pool_step(
             self.ctx.handle, sensor._h, dp.n, _lib.ptr(dp.x), _lib.ptr(dp.y), _lib.ptr(dp.dxdz), _lib.ptr(dp.dydz),
             _lib.ptr(dp.flux), _lib.ptr(dp.wavelength), C.byref(self.opt), self.t0, self.exptime, self.r_inner,
-            self.r_outer, self.seed, sensor._seed & 0xFFFFFFFFFFFFFFFF, self.offset, int(bool(resume)),
+            self.r_outer, self.seed, sensor._seed & 0xFFFFFFFFFFFFFFFF, self.offset, sensor._photon_offset,
+            int(bool(resume)),
             int(bool(recalc)), int(bool(write_back)), C.byref(ostats) if want_stats else None,
             C.byref(astats) if want_stats else None))
         self.offset += dp.n

@@ -340,14 +340,23 @@ class SiliconSensor:
         injected draws ``[g1, g2, u_notfound, u_depth]``, shape (4, N)."""
         if resume and image is not self._last_image:
             raise _lib.B2Error("image must be the same as used for the last accumulate call if resume is True")
-        self._last_image = image
         ocx, ocy = (0, 0) if orig_center is None else (int(orig_center.x), int(orig_center.y)) \
             if hasattr(orig_center, 'x') else (int(orig_center[0]), int(orig_center[1]))
         n = photons.size() if hasattr(photons, 'size') and callable(photons.size) else len(photons)
-        if n == 0:
-            return 0.0
         if not resume and not prebound:
             self._bind(image)
+        # only a successful bind makes this the image a later resume=True may continue on; an empty first
+        # batch still initialises the boundaries from the image (GalSim has no early-out either)
+        self._last_image = image
+        if n == 0:
+            if resume and not recalc:
+                return 0.0
+            _lib.check(self._lib.b2_sensor_accumulate(
+                self._h, 0, None, None, None, None, None, None, None, self._seed & 0xFFFFFFFFFFFFFFFF,
+                self._photon_offset, ocx, ocy, int(bool(resume)), int(bool(recalc)), _abi.B2_HOST, None))
+            if sync_image:
+                self.read_image(image)
+            return 0.0
         x, y, flux = photons.x, photons.y, photons.flux
         where = _lib.where_of(x)
         dxdz = photons.dxdz if photons.hasAllocatedAngles() else None

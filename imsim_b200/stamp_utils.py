@@ -18,6 +18,8 @@ from functools import lru_cache
 import numpy as np
 
 from . import _abi
+
+_trapz = getattr(np, "trapezoid", None) or np.trapz  # NumPy >= 2 renamed trapz
 from .atmosphere import WLEN_EFF
 
 FT_DEFAULT = 5.0e-3          # galsim.GSParams().folding_threshold
@@ -42,7 +44,7 @@ def _kolmogorov_ee():
     rho = np.linspace(0.0, 6.0, 6001)
     tau = np.exp(-3.442 * rho ** (5.0 / 3.0))
     theta = np.concatenate([[0.0], np.logspace(-2, 2.5, 1200)])
-    E = 2 * np.pi * theta * np.trapezoid(tau[None, :] * j1(2 * np.pi * rho[None, :] * theta[:, None]), rho, axis=1)
+    E = 2 * np.pi * theta * _trapz(tau[None, :] * j1(2 * np.pi * rho[None, :] * theta[:, None]), rho, axis=1)
     E = np.maximum.accumulate(np.clip(E, 0.0, 1.0))
     return theta, E
 

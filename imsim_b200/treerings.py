@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import os
 import warnings
+from dataclasses import dataclass
 
 import numpy as np
 
@@ -133,95 +134,160 @@ def _position(x, y):
         return _Position(x, y)
 
 
+@dataclass
+class TreeRingRecord:
+    """One detector's entry of a tree-ring parameter file, parsed: 23 text lines in the file (a comment line,
+    the parameter line ``Rx Ry Sx Sy Cx Cy A B``, a column header and ``numfreqs`` rows
+    ``CosFreq CosPhase SinFreq SinPhase``; imsim/treerings.py:120-136)."""
+
+    det_name: str
+    comment: str
+    columns: str
+    raft_slot: tuple          # the four index tokens as written in the file
+    cx: str                   # centre offset and amplitudes stay text until asked for: rewriting a file
+    cy: str                   # must reproduce untouched entries character by character
+    a: str
+    b: str
+    rows: list                # the numfreqs coefficient lines, verbatim
+    original: str = ""        # the parameter line as read (returned while none of its fields was edited)
+
+    @classmethod
+    def parse(cls, lines):
+        tok = lines[1].split()
+        return cls("R%s%s_S%s%s" % tuple(tok[:4]), lines[0], lines[2], tuple(tok[:4]), tok[4], tok[5], tok[6],
+                   tok[7], list(lines[3:]), lines[1])
+
+    def parameter_line(self) -> str:
+        if self.original and self.original.split()[4:8] == [self.cx, self.cy, self.a, self.b]:
+            return self.original
+        return "\t".join(self.raft_slot + (self.cx, self.cy, self.a, self.b)) + "\n"
+
+    def lines(self) -> list:
+        """The block as text, in the layout ``TreeRingRadialFunction`` reads."""
+        return [self.comment, self.parameter_line(), self.columns] + self.rows
+
+    def center(self, x0=2048.5, y0=2048.5):
+        return float(self.cx) + x0, float(self.cy) + y0
+
+
+def read_tree_ring_file(path) -> "dict[str, TreeRingRecord]":
+    """All detector records of a parameter file, keyed by ``Rxx_Syy``, in file order."""
+    per = numfreqs + 3
+    with open(path, "r") as f:
+        text = f.readlines()
+    recs = (TreeRingRecord.parse(text[k:k + per]) for k in range(0, len(text) - per + 1, per))
+    return {r.det_name: r for r in recs}
+
+
+class _InfoBlocks(dict):
+    """``TreeRings.info_blocks`` as the reference exposes it (det_name -> list of text lines), backed by the
+    parsed records."""
+
+    def __init__(self, records):
+        super().__init__()
+        self._records = records
+
+    def __getitem__(self, det_name):
+        return self._records[det_name].lines()
+
+    def __contains__(self, det_name):
+        return det_name in self._records
+
+    def __iter__(self):
+        return iter(self._records)
+
+    def __len__(self):
+        return len(self._records)
+
+    def keys(self):
+        return self._records.keys()
+
+    def values(self):
+        return [r.lines() for r in self._records.values()]
+
+    def items(self):
+        return [(k, r.lines()) for k, r in self._records.items()]
+
+
 class TreeRings:
-    """Per-detector tree-ring models read from a parameter file (treerings.py:71-218)."""
+    """Per-detector tree-ring models from a parameter file: the ``tree_rings`` input object of
+    imsim/treerings.py:71-218 (same constructor, ``info`` / ``info_blocks``, ``get_center`` / ``get_func`` /
+    ``get_dfdr``, ``update_info_block``, ``write``), over parsed records."""
 
     _req_params = {'file_name': str}
     _opt_params = {'only_dets': list, 'defer_load': bool}
 
+    R_MAX = 8000.0   # extent of the tabulated function [px]
+    DR = 3.0         # node spacing [px]
+    PIXEL_CENTER = (2048.5, 2048.5)
+
     def __init__(self, file_name, only_dets=None, logger=None, defer_load=True, data_dir=None):
-        self.file_name = file_name
-        if not os.path.isfile(self.file_name):
-            for d in filter(None, [data_dir, os.environ.get("IMSIM_DATA_DIR")]):
-                cand = os.path.join(d, 'tree_ring_data', file_name)
-                if os.path.isfile(cand):
-                    self.file_name = cand
-                    break
-        if not os.path.isfile(self.file_name):
-            raise OSError("TreeRing file %s not found" % file_name)
+        self.file_name = self._locate(file_name, data_dir)
         self.only_dets = only_dets
         self.numfreqs = numfreqs
-        self.r_max = 8000.0  # maximum extent of the tree-ring function in pixels
-        dr = 3.0  # step size in pixels
-        self.npoints = int(self.r_max / dr) + 1
+        self.r_max = self.R_MAX
+        self.npoints = int(self.R_MAX / self.DR) + 1
         if logger is not None:
             logger.warning("TreeRing file %s will be used.", self.file_name)
-        self._read_info_blocks()
-        if only_dets and logger is not None:
-            missing_dets = set(only_dets).difference(self.info_blocks)
-            if missing_dets:
-                logger.info("Requested det_names that are not in the tree ring info file: %s", missing_dets)
+        self.records = read_tree_ring_file(self.file_name)
+        self.info_blocks = _InfoBlocks(self.records)
         self.info = {}
+        unknown = set(only_dets or ()) - set(self.records)
+        if unknown and logger is not None:
+            logger.info("Requested det_names that are not in the tree ring info file: %s", unknown)
         if not defer_load:
             self.fill_dict(only_dets=only_dets)
 
-    def _read_info_blocks(self):
-        with open(self.file_name, 'r') as fobj:
-            lines = fobj.readlines()
-        block_size = self.numfreqs + 3
-        self.info_blocks = {}
-        for iblock in range(len(lines) // block_size):
-            block = lines[iblock * block_size:(iblock + 1) * block_size]
-            items = block[1].split()
-            self.info_blocks["R%s%s_S%s%s" % tuple(items[:4])] = block
+    @staticmethod
+    def _locate(file_name, data_dir):
+        search = [file_name] + [os.path.join(d, 'tree_ring_data', file_name)
+                                for d in (data_dir, os.environ.get("IMSIM_DATA_DIR")) if d]
+        for cand in search:
+            if os.path.isfile(cand):
+                return cand
+        raise OSError("TreeRing file %s not found" % file_name)
 
     def write(self, outfile, overwrite=False):
         if os.path.isfile(outfile) and not overwrite:
             raise FileExistsError(f"{outfile} already exists.")
-        with open(outfile, 'w') as fobj:
-            for block in self.info_blocks.values():
-                fobj.writelines(block)
+        with open(outfile, 'w') as f:
+            for rec in self.records.values():
+                f.writelines(rec.lines())
 
     def update_info_block(self, det_name, Cx=None, Cy=None, A=None, B=None):
-        keys = ["Rx", "Ry", "Sx", "Sy", "Cx", "Cy", "A", "B"]
-        pars = dict(zip(keys, self.info_blocks[det_name][1].split()))
-        pars['Cx'] = f"{Cx:.1f}" if Cx is not None else pars['Cx']
-        pars['Cy'] = f"{Cy:.1f}" if Cy is not None else pars['Cy']
-        pars['A'] = f"{A:.2e}" if A is not None else pars['A']
-        pars['B'] = f"{B:.2e}" if B is not None else pars['B']
-        self.info_blocks[det_name][1] = "\t".join([pars[k] for k in keys]) + "\n"
-        self.info.pop(det_name, None)
+        """New centre offsets / amplitudes for one detector, in the file's number formats."""
+        rec = self.records[det_name]
+        for attr, value, fmt in (("cx", Cx, "%.1f"), ("cy", Cy, "%.1f"), ("a", A, "%.2e"), ("b", B, "%.2e")):
+            if value is not None:
+                setattr(rec, attr, fmt % value)
+        self.info.pop(det_name, None)  # tabulated again on the next request
+
+    def _tabulate(self, rec: TreeRingRecord):
+        table = RadialTable.from_func(TreeRingRadialFunction(rec.lines()), x_min=0.0, x_max=self.r_max,
+                                      npoints=self.npoints)
+        return _position(*rec.center(*self.PIXEL_CENTER)), table
 
     def fill_dict(self, only_dets=None):
-        xCenterPix = 2048.5
-        yCenterPix = 2048.5
-        if only_dets is None:
-            only_dets = self.info_blocks.keys()
-        for det_name in only_dets:
-            if det_name not in self.info_blocks:
-                continue
-            info_block = self.info_blocks[det_name]
-            items = info_block[1].split()
-            center = _position(float(items[4]) + xCenterPix, float(items[5]) + yCenterPix)
-            func = RadialTable.from_func(TreeRingRadialFunction(info_block), x_min=0.0, x_max=self.r_max,
-                                         npoints=self.npoints)
-            self.info[det_name] = (center, func)
+        for det_name in (self.records if only_dets is None else only_dets):
+            rec = self.records.get(det_name)
+            if rec is not None:
+                self.info[det_name] = self._tabulate(rec)
+
+    def _entry(self, det_name, what, default):
+        if det_name not in self.info:
+            self.fill_dict((det_name,))
+        if det_name not in self.info:
+            warnings.warn("No treering information available for %s.  Setting %s." % (det_name, what))
+            return default
+        return self.info[det_name]
 
     def get_dfdr(self, det_name):
-        return TreeRingRadialFunction(self.info_blocks[det_name]).dfdr
+        return TreeRingRadialFunction(self.records[det_name].lines()).dfdr
 
     def get_center(self, det_name):
-        if det_name not in self.info:
-            self.fill_dict((det_name,))
-        if det_name in self.info:
-            return self.info[det_name][0]
-        warnings.warn("No treering information available for %s.  Setting treering_center to PositionD(0, 0)." % det_name)
-        return _position(0, 0)
+        e = self._entry(det_name, "treering_center to PositionD(0, 0)", None)
+        return _position(0, 0) if e is None else e[0]
 
     def get_func(self, det_name):
-        if det_name not in self.info:
-            self.fill_dict((det_name,))
-        if det_name in self.info:
-            return self.info[det_name][1]
-        warnings.warn("No treering information available for %s.  Setting treering_func to None." % det_name)
-        return None
+        e = self._entry(det_name, "treering_func to None", None)
+        return None if e is None else e[1]

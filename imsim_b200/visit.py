@@ -200,6 +200,7 @@ class DetectorRunner:
         gen = np.random.default_rng(self.seed + det_index)
         counts = photon_batch_counts(oflux, np.zeros(len(oflux), bool), nbatch, gen.random)
         batches = []
+        nbatch = counts.shape[0]  # clamped to the number of bright objects, like the reference
         for k in range(nbatch):
             cnt = np.asarray(counts[k])
             idx = np.nonzero(cnt)[0]
@@ -218,6 +219,9 @@ class DetectorRunner:
         self.ctx.set_detector(su.detector)
         self.ctx.set_diffraction(self.dif)
         sensor = self.sensor_for(p.det_name)
+        # an independent sensor stream per detector image (the reference: sensor.updateRNG(rng) per image,
+        # imsim/photon_pooling.py:71, with the per-file seed of imsim/ccd.py:30)
+        sensor.updateRNG((self.seed * 0x9E3779B97F4A7C15 + 1000003 * (det_index + 1)) & 0x7FFFFFFFFFFFFFFF)
         # the returned e-image (and raw segments) land in pinned buffers of the runner; three slots rotate, so the
         # result handed to the caller stays valid while the next two detectors are in flight
         slot = self._slot

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 1
+#define B2_ABI_VERSION 2
 
 #define B2_HOST 0
 #define B2_DEVICE 1
@@ -468,13 +468,14 @@ int b2_plain_accumulate(b2_sensor* s, int64_t n, const double* x, const double* 
    SiliconSensor.accumulate(photons, image, resume, recalc).  Needs nrecalc == 0 (pooled cadence).
    x, y, flux in (pixel positions of the pooled photons), wl_nm in; if write_back != 0 the traced
    photons (x, y, dxdz, dydz, flux) are stored like the separate ops would leave them.
-   Draws: sampler Philox(sampler_seed), kick Philox(opt->seed), sensor Philox(sensor_seed), all
-   counted from photon_offset (opt->photon_offset for the kick) -- identical to the unfused calls. */
+   Draws: sampler Philox(sampler_seed) counted from photon_offset, kick Philox(opt->seed) from
+   opt->photon_offset, sensor Philox(sensor_seed) from sensor_offset (the sensor's own photon counter,
+   what b2_sensor_accumulate is given) -- identical to the unfused calls. */
 int b2_pool_step(b2_ctx* ctx, b2_sensor* sensor, int64_t n, double* x, double* y, double* dxdz, double* dydz,
                  double* flux, const double* wl_nm, const B2OpticsOptions* opt, double t0, double exptime,
                  double r_inner, double r_outer, uint64_t sampler_seed, uint64_t sensor_seed,
-                 uint64_t photon_offset, int32_t resume, int32_t recalc, int32_t write_back,
-                 B2OpticsStats* ostats, B2AccumStats* astats);
+                 uint64_t photon_offset, uint64_t sensor_offset, int32_t resume, int32_t recalc,
+                 int32_t write_back, B2OpticsStats* ostats, B2AccumStats* astats);
 /* One iteration of the photon-shot flat (imsim/flat.py:239-264) on the sensor's bound image, fused:
    photons are generated tile by tile (tile x tile pixels) straight into the charge deposit.
    tile_cum: HOST int64[tiles+1], tile_cum[0] = 0, cumulative per-tile photon counts of this iteration (Poisson

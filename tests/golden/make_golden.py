@@ -83,7 +83,7 @@ def make_sensor_models():
         out[name + "_cfg"] = np.array([float(cfg[k]) for k in keys])
         out[name + "_dat"] = np.loadtxt(base + ".dat", skiprows=1).astype(np.float64)
     out["cfg_keys"] = np.array(keys)
-    np.savez_compressed(os.path.join(HERE, "sensor_models.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, "..", "..", "imsim_b200", "data", "sensor_models.npz"), **out)
     print("sensor_models.npz written")
 
 
@@ -103,7 +103,7 @@ def make_tree_rings():
     out["known_r"] = np.array(5280.0)
     out["known_values"] = np.array([.0030205, -.0034135])
     out["known_centers"] = np.array([(-3026.3, -3001.0), (3095.5, -2971.3)])
-    np.savez_compressed(os.path.join(HERE, "tree_rings.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, "..", "..", "imsim_b200", "data", "tree_rings.npz"), **out)
     print("tree_rings.npz written")
 
 

@@ -23,7 +23,7 @@ def main():
     ns = {"np": np}
     exec(ast.get_source_segment(src, node), ns)
     cls = ns["TreeRingRadialFunction"]
-    blocks = np.load(os.path.join(HERE, "tree_rings.npz"))
+    blocks = np.load(os.path.join(HERE, "..", "..", "imsim_b200", "data", "tree_rings.npz"))
     rng = np.random.default_rng(20261019)
     r_nodes = np.linspace(0.0, 8000.0, 2667)
     r_off = np.sort(rng.uniform(0.0, 8000.0, 500))

@@ -15,32 +15,17 @@ RUBIN_LAT = np.radians(-30.24463)
 
 
 def golden(name):
+    """Golden vectors of tests/golden/; the two copies of reference data files that the synthetic workloads also
+    use live in the package (imsim_b200/data/)."""
+    if name in ("sensor_models.npz", "tree_rings.npz"):
+        from imsim_b200 import workload_data
+
+        return workload_data.load(name)
     return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
 
 
-def sensor_model(name="lsst_itl_50_4"):
-    """(config dict, vertex_data) from the golden copy of data/sensor_models."""
-    g = golden("sensor_models.npz")
-    keys = [str(k) for k in g["cfg_keys"]]
-    vals = g[name + "_cfg"]
-    cfg = {}
-    for k, v in zip(keys, vals):
-        cfg[k] = int(v) if k in ("NumVertices", "PixelBoundaryNx", "PixelBoundaryNy", "NumPhases",
-                                 "CollectingPhases") else float(v)
-    return cfg, np.ascontiguousarray(g[name + "_dat"])
-
-
-def tree_ring_block(det="R22_S11", fn="tree_ring_parameters_2026-04-02.txt"):
-    g = golden("tree_rings.npz")
-    return [str(s) for s in g["%s|%s" % (fn, det)]]
-
-
-def tree_ring_table(det="R22_S11", fn="tree_ring_parameters_2026-04-02.txt"):
-    block = tree_ring_block(det, fn)
-    items = block[1].split()
-    center = (float(items[4]) + 2048.5, float(items[5]) + 2048.5)
-    func = RadialTable.from_func(TreeRingRadialFunction(block), 0.0, 8000.0, int(8000.0 / 3.0) + 1)
-    return center, func
+from imsim_b200.workload_data import (absorption, default_diffraction, sensor_model, tree_ring_block,  # noqa: E402,F401
+                                      tree_ring_table)
 
 
 def sensor_pod(cfg, strength=1.0, nrecalc=10000, qdist=3, diffusion_factor=1.0, treering=None, n_abs=0):
@@ -100,10 +85,3 @@ def test_photon_arrays(n=10000, t=0.0, seed=42, wavelength=577.6, center=(0.0, 0
                 time=np.full(n, t))
 
 
-def default_diffraction(enabled=True, field_rotation=True):
-    return diffraction_config(latitude=RUBIN_LAT, altitude=np.radians(67.0), azimuth=np.radians(213.0),
-                              disable_field_rotation=not field_rotation, enabled=enabled)
-
-
-def absorption():
-    return synthetic_absorption_table()

@@ -213,3 +213,28 @@ def test_restart_from_a_checkpointed_image_rebuilds_the_boundaries():
     # identical up to the few photons within a float32 ulp of a moved boundary
     assert diff.sum() <= 20 and diff.max() <= 2, (diff.sum(), diff.max())
     assert not np.array_equal(full, checkpoint)
+
+
+def test_empty_first_batch_then_resume_on_a_reused_sensor():
+    """A first pooled sub-batch may be empty (all stamps None).  The empty non-resume call must still bind and
+    initialise the new image, so that the following resume=True call neither fails nor lands on the buffers of
+    the previous CCD (and read-back must not overwrite what the new image already held)."""
+    s = _sensor()
+    rng = np.random.default_rng(5)
+    n = 20000
+    first = Image(np.zeros((32, 32), np.float32))
+    s.accumulate(PhotonArray(n, x=rng.uniform(5, 27, n), y=rng.uniform(5, 27, n), flux=np.ones(n)), first)
+    assert first.array.sum() > 0
+    # same-sized new image that already holds something (an FFT object drawn earlier)
+    second = Image(np.zeros((32, 32), np.float32))
+    second.array[3, 4] = 123.0
+    assert s.accumulate(PhotonArray(0), second, resume=False) == 0.0
+    m = 5000
+    pa = PhotonArray(m, x=rng.uniform(10, 20, m), y=rng.uniform(10, 20, m), flux=np.ones(m))
+    added = s.accumulate(pa, second, resume=True)
+    assert added == m
+    assert second.array[3, 4] == 123.0
+    assert second.array.sum() == pytest.approx(123.0 + m)
+    assert second.array[:8].sum() == 123.0  # nothing of the first image's 5..27 field leaked in
+    with pytest.raises(B2Error):
+        s.accumulate(pa, Image(np.zeros((32, 32), np.float32)), resume=True)

@@ -43,6 +43,19 @@ def test_tree_rings_reader(tmp_path):
     # update_info_block drops the cached table
     tr2.update_info_block("R22_S11", A=0.0, B=0.0)
     assert float(tr2.get_func("R22_S11")(5280.0)) == 0.0
+    # write: untouched files come back character by character; edits land in the parameter line
+    tr3 = TreeRings(fn)
+    out = tmp_path / "copy.txt"
+    tr3.write(str(out))
+    assert out.read_text() == open(fn).read()
+    with pytest.raises(FileExistsError):
+        tr3.write(str(out))
+    tr3.update_info_block("R34_S22", Cx=12.25, A=1.5e-3)
+    tr3.write(str(out), overwrite=True)
+    tr4 = TreeRings(str(out))
+    assert tr4.get_center("R34_S22").x == pytest.approx(2048.5 + 12.2, abs=0.06)
+    assert tr4.info_blocks["R34_S22"][1].split()[6] == "1.50e-03"
+    assert tr4.info_blocks["R22_S11"] == tr3.info_blocks["R22_S11"] and len(tr4.info_blocks) == 2
 
 
 def test_detector_geometry_golden():

@@ -70,4 +70,4 @@ def test_fixture_carries_the_sampler_tables(live):
     # the fixture exists; here only their presence and sanity
     assert live["kick2_xvalue"][0] > live["kick2_xvalue"][-1] > 0
     assert live["size_star"].shape[1] == 4 and np.all(np.diff(live["size_star"][:, 1]) >= 0)
-    assert _abi.B2_ABI_VERSION == 1
+    assert _abi.B2_ABI_VERSION == 2

@@ -156,7 +156,7 @@ def test_vectorised_batch_counts_equal_list_algebra():
     it = iter(draws)
     batches = Builder.make_photon_batches({}, {"rng": lambda: next(it)}, None, phot, fnt, nbatch)
     it2 = iter(draws)
-    counts = photon_batch_counts(flux, faint, nbatch, lambda: next(it2))
+    counts = photon_batch_counts(flux, faint, nbatch, lambda: next(it2), clamp=False)
     ref = np.zeros_like(counts)
     for b, batch in enumerate(batches):
         for o in batch:
@@ -203,9 +203,36 @@ def test_batching_algebra_matches_the_reference_source():
         # the vectorised form: counts[b, j] photons of non-FFT object j in batch b
         sel = np.nonzero(modes != 0)[0]
         it = iter(uniforms)
-        counts = photon_batch_counts(flux[sel], modes[sel] == 2, nbatch, lambda: next(it))
+        counts = photon_batch_counts(flux[sel], modes[sel] == 2, nbatch, lambda: next(it), clamp=False)
         want = np.zeros((nbatch, nobj), dtype=np.int64)
         off, idx, fl = g["c%d_batches_off" % k], g["c%d_batches_idx" % k], g["c%d_batches_flux" % k]
         for b in range(len(off) - 1):
             np.add.at(want[b], idx[off[b]:off[b + 1]], fl[off[b]:off[b + 1]].astype(np.int64))
         np.testing.assert_array_equal(counts, want[:, sel])
+
+
+def test_batch_counts_clamp_like_buildImage_when_bright_objects_are_fewer_than_nbatch():
+    """imsim/photon_pooling.py:74,117: the faint partition uses the configured nbatch, the flux split the
+    clamped one -- a sparse CCD gets fewer batches (and so fewer boundary recalculations)."""
+    from imsim_b200.photon_pooling import photon_batch_counts
+
+    flux = np.array([5, 120000, 7, 33333, 2, 9, 0, 650], dtype=np.int64)  # 3 bright objects for nbatch = 10
+    nbatch = 10
+    infos = [ObjectInfo(i, int(f), ProcessingMode.PHOT) for i, f in enumerate(flux)]
+    _, phot, fnt = Builder.partition_objects(infos, nbatch)
+    assert [o.index for o in phot] == [1, 3, 7]
+    nb = max(min(nbatch, len(phot)), 1)
+    draws = list(np.random.default_rng(2).random(len(fnt)))
+    it = iter(draws)
+    batches = Builder.make_photon_batches({}, {"rng": lambda: next(it)}, None, phot, fnt, nb)
+    it2 = iter(draws)
+    counts = photon_batch_counts(flux, np.zeros(len(flux), bool), nbatch, lambda: next(it2))
+    assert counts.shape == (3, len(flux))
+    ref = np.zeros_like(counts)
+    for b, batch in enumerate(batches):
+        for o in batch:
+            ref[b, o.index] += o.phot_flux
+    np.testing.assert_array_equal(counts, ref)
+    # no bright object at all: one batch
+    c1 = photon_batch_counts(np.array([3, 4]), np.zeros(2, bool), 10, lambda: 0.99)
+    assert c1.shape == (1, 2) and c1.sum() == 7
