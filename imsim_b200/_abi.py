@@ -157,6 +157,11 @@ class B2AccumStats(C.Structure):
         return {name: getattr(self, name) for name, _ in self._fields_}
 
 
+class B2StampJob(C.Structure):
+    _fields_ = [("p0", C.c_int64), ("n", C.c_int64), ("xmin", C.c_int32), ("ymin", C.c_int32), ("nx", C.c_int32),
+                ("ny", C.c_int32), ("plain", C.c_int32), ("pad", C.c_int32)]
+
+
 PROF_DELTA, PROF_GAUSSIAN, PROF_RADIAL, PROF_KNOTS, PROF_BOX = range(5)
 B2_MAX_SCREENS = 8
 B2_STAGE1_NRAND = 12
@@ -208,5 +213,5 @@ assert OBJECT_DTYPE.itemsize == C.sizeof(B2Object)
 # order of b2_sizeof(which)
 SIZEOF_ORDER = [
     B2Telescope, B2Surface, B2TanSip, B2Detector, B2Diffraction, B2OpticsOptions,
-    B2OpticsStats, B2SensorConfig, B2AccumStats, B2Obsc, B2Medium, B2Object, B2Psf, B2Amp,
+    B2OpticsStats, B2SensorConfig, B2AccumStats, B2Obsc, B2Medium, B2Object, B2Psf, B2Amp, B2StampJob,
 ]

@@ -16,7 +16,7 @@ import numpy as np
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SRC = [os.path.join(_HERE, "csrc", f) for f in ("abi.cu", "optics.cu", "sensor.cu", "pool.cu", "stage1.cu", "readout.cu",
+_SRC = [os.path.join(_HERE, "csrc", f) for f in ("abi.cu", "optics.cu", "sensor.cu", "pool.cu", "stamps.cu", "stage1.cu", "readout.cu",
                                                       "hostpipe.cu")]
 _HDR = [os.path.join(_HERE, "csrc", f) for f in ("b2_common.cuh", "optics_device.cuh", "sensor_device.cuh")] + \
     [os.path.join(os.path.dirname(_HERE), "include", "imsim_b200.h")]
@@ -117,6 +117,10 @@ _SIGNATURES = {
     "b2_sensor_get_pixel": (C.c_int, [vp, C.c_int32, C.c_int32, vp, vp]),
     "b2_flat_step": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int32, vp, vp, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64,
                                C.c_int32, C.c_int32, C.POINTER(_abi.B2AccumStats)]),
+    "b2_sensor_accumulate_stamps": (C.c_int, [vp, C.c_int32, vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, C.c_uint64,
+                                              C.c_uint64, C.c_int32, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32,
+                                              C.c_int32, C.c_int32, C.POINTER(_abi.B2AccumStats), vp]),
+    "b2_xytov_compile": (C.c_int, [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, dp]),
     "b2_pool_step": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.POINTER(_abi.B2OpticsOptions), C.c_double,
                                C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                C.c_int32, C.c_int32, C.c_int32, C.POINTER(_abi.B2OpticsStats),

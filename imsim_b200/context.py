@@ -55,14 +55,40 @@ class OpticsContext:
         """Surface program of the uploaded telescope (0 interpreter, 1 Rubin layout; -1 none)."""
         return int(self._lib.b2_telescope_program(self._h))
 
+    #: pixels around the detector over which XyToV is compiled (stamps of objects just off the chip, the
+    #: reach of all but the longest diffraction kicks); positions further out take the exact chain
+    XYTOV_MARGIN = 512.0
+    XYTOV_TOL_PX = 2e-9
+
     def set_wcs(self, img_wcs, icrf_to_field):
         a = img_wcs.to_pod() if isinstance(img_wcs, TanSipWCS) else img_wcs
         b = icrf_to_field.to_pod() if isinstance(icrf_to_field, TanSipWCS) else icrf_to_field
         _lib.check(self._lib.b2_wcs_upload(self._h, C.byref(a), C.byref(b)))
+        self._have_wcs = True
+        self.xytov_residual_px = None
+        self._compile_xytov()
 
     def set_detector(self, det):
         d = det.to_pod() if isinstance(det, DetectorGeometry) else det
         _lib.check(self._lib.b2_detector_upload(self._h, C.byref(d)))
+        self._det_box = None
+        if isinstance(det, DetectorGeometry):
+            m = self.XYTOV_MARGIN
+            self._det_box = (det.xmin - m, det.xmin + det.nx + m, det.ymin - m, det.ymin + det.ny + m)
+        self._compile_xytov()
+
+    def _compile_xytov(self):
+        """XyToV as one polynomial over this detector (``b2_xytov_compile``), once both the WCS pair and the
+        detector's pixel box are known; ``B2_XYTOV_EXACT=1`` keeps the exact chain.  ``xytov_residual_px``: the
+        largest deviation from the exact chain on the check grid (None: not compiled)."""
+        import os
+
+        box = getattr(self, "_det_box", None)
+        if not getattr(self, "_have_wcs", False) or box is None or os.environ.get("B2_XYTOV_EXACT") == "1":
+            return
+        r = C.c_double(0.0)
+        _lib.check(self._lib.b2_xytov_compile(self._h, box[0], box[1], box[2], box[3], self.XYTOV_TOL_PX, C.byref(r)))
+        self.xytov_residual_px = r.value
 
     def set_diffraction(self, cfg: Optional[_abi.B2Diffraction]):
         if cfg is None:

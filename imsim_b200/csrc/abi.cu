@@ -28,6 +28,7 @@ extern "C" int64_t b2_sizeof(int32_t which) {
         case 11: return sizeof(B2Object);
         case 12: return sizeof(B2Psf);
         case 13: return sizeof(B2Amp);
+        case 14: return sizeof(B2StampJob);
     }
     return -1;
 }

@@ -101,12 +101,22 @@ struct DevSurf {
 #define B2_DEV_MAX_SURF 16
 #define B2_DEV_MAX_MEDIA 4
 
+// pixel -> field-angle tangents compiled into one polynomial per detector (b2_xytov_compile)
+#define B2_XYPOLY_N 6
+struct DevXyPoly {
+    int enabled, pad;
+    double box[4];   // xlo, xhi, ylo, yhi [pixels]: where the fit was made and checked
+    double c0[2], sc[2];
+    double cx[B2_XYPOLY_N][B2_XYPOLY_N], cy[B2_XYPOLY_N][B2_XYPOLY_N];  // c[i][j] X^i Y^j
+};
+
 struct DevOptics {
     int n_surf, n_media, medium_stop, pad;
     DevSurf surf[B2_DEV_MAX_SURF];
     B2Medium media[B2_DEV_MAX_MEDIA];
     DevWcs img, field;
     double M_if[9];  // img tangent frame -> field tangent frame (row-major)
+    DevXyPoly xyv;
     B2Detector det;
     B2Diffraction dif;
 };

@@ -273,6 +273,93 @@ extern "C" int b2_wcs_upload(b2_ctx* ctx, const B2TanSip* img, const B2TanSip* f
     ctx->img_host = *img;
     ctx->field_host = *field;
     ctx->have_wcs = true;
+    ctx->opt.xyv.enabled = 0;  // a compiled XyToV belongs to the previous WCS pair
+    return 0;
+}
+
+// XyToV compiled for one detector.  The field tangents (thx, thy) as functions of the pixel position are
+// interpolated at the 12 x 12 Chebyshev points of the box [xlo, xhi] x [ylo, yhi] by a tensor Chebyshev series
+// (discrete orthogonality: a projection, no linear solve), truncated to degree 5 x 5, converted to monomials of
+// the scaled coordinates, and checked against the exact chain on a 33 x 33 grid of other points.  The
+// polynomial is adopted only if it reproduces the exact chain to tol_px pixels; max_resid_px reports it either way.
+extern "C" int b2_xytov_compile(b2_ctx* ctx, double xlo, double xhi, double ylo, double yhi, double tol_px,
+                                double* max_resid_px) {
+    B2_REQUIRE(ctx && ctx->have_wcs, "b2_xytov_compile: upload the WCS pair first");
+    B2_REQUIRE(xhi > xlo && yhi > ylo, "b2_xytov_compile: empty box");
+    DevOptics& o = ctx->opt;
+    o.xyv.enabled = 0;
+    constexpr int NC = 12, ND = B2_XYPOLY_N;
+    const double cx0 = 0.5 * (xlo + xhi), cy0 = 0.5 * (ylo + yhi), hx = 0.5 * (xhi - xlo), hy = 0.5 * (yhi - ylo);
+    double node[NC], T[NC][ND];
+    for (int k = 0; k < NC; ++k) {
+        node[k] = cos(M_PI * (k + 0.5) / NC);
+        for (int d = 0; d < ND; ++d) T[k][d] = cos(d * M_PI * (k + 0.5) / NC);
+    }
+    double fx[NC][NC], fy[NC][NC];
+    for (int a = 0; a < NC; ++a)
+        for (int b = 0; b < NC; ++b) xy_to_field_exact(o, cx0 + hx * node[a], cy0 + hy * node[b], fx[a][b], fy[a][b]);
+    // Chebyshev coefficients c[i][j] of T_i(X) T_j(Y)
+    double chx[ND][ND], chy[ND][ND];
+    for (int i = 0; i < ND; ++i)
+        for (int j = 0; j < ND; ++j) {
+            double sx = 0.0, sy = 0.0;
+            for (int a = 0; a < NC; ++a)
+                for (int b = 0; b < NC; ++b) {
+                    sx += fx[a][b] * T[a][i] * T[b][j];
+                    sy += fy[a][b] * T[a][i] * T[b][j];
+                }
+            const double w = (i ? 2.0 : 1.0) * (j ? 2.0 : 1.0) / (NC * NC);
+            chx[i][j] = w * sx;
+            chy[i][j] = w * sy;
+        }
+    // T_d(x) = sum_m tm[d][m] x^m
+    double tm[ND][ND] = {};
+    tm[0][0] = 1.0;
+    if (ND > 1) tm[1][1] = 1.0;
+    for (int d = 2; d < ND; ++d)
+        for (int m = 0; m < ND; ++m) tm[d][m] = (m ? 2.0 * tm[d - 1][m - 1] : 0.0) - tm[d - 2][m];
+    DevXyPoly p;
+    memset(&p, 0, sizeof(p));
+    for (int i = 0; i < ND; ++i)
+        for (int j = 0; j < ND; ++j)
+            for (int a = 0; a < ND; ++a)
+                for (int b = 0; b < ND; ++b) {
+                    p.cx[a][b] += chx[i][j] * tm[i][a] * tm[j][b];
+                    p.cy[a][b] += chy[i][j] * tm[i][a] * tm[j][b];
+                }
+    p.box[0] = xlo; p.box[1] = xhi; p.box[2] = ylo; p.box[3] = yhi;
+    p.c0[0] = cx0; p.c0[1] = cy0;
+    p.sc[0] = 1.0 / hx; p.sc[1] = 1.0 / hy;
+    // validation against the exact chain, in pixels: radians of field angle per pixel from the box diagonal
+    double t00x, t00y, t11x, t11y;
+    xy_to_field_exact(o, xlo, ylo, t00x, t00y);
+    xy_to_field_exact(o, xhi, yhi, t11x, t11y);
+    const double rad_per_px = hypot(t11x - t00x, t11y - t00y) / hypot(xhi - xlo, yhi - ylo);
+    B2_REQUIRE(rad_per_px > 0.0 && std::isfinite(rad_per_px), "b2_xytov_compile: degenerate WCS over the box");
+    double worst = 0.0;
+    constexpr int NV = 33;
+    for (int a = 0; a < NV; ++a)
+        for (int b = 0; b < NV; ++b) {
+            const double X = -1.0 + 2.0 * a / (NV - 1), Y = -1.0 + 2.0 * b / (NV - 1);
+            double ex, ey;
+            xy_to_field_exact(o, cx0 + hx * X, cy0 + hy * Y, ex, ey);
+            double gx = 0.0, gy = 0.0;
+            for (int i = ND - 1; i >= 0; --i) {
+                double rx = p.cx[i][ND - 1], ry = p.cy[i][ND - 1];
+                for (int j = ND - 2; j >= 0; --j) {
+                    rx = fma(rx, Y, p.cx[i][j]);
+                    ry = fma(ry, Y, p.cy[i][j]);
+                }
+                gx = fma(gx, X, rx);
+                gy = fma(gy, X, ry);
+            }
+            worst = std::max(worst, std::max(fabs(gx - ex), fabs(gy - ey)) / rad_per_px);
+        }
+    if (max_resid_px) *max_resid_px = worst;
+    if (worst <= tol_px) {
+        p.enabled = 1;
+        o.xyv = p;
+    }
     return 0;
 }
 

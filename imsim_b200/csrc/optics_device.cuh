@@ -10,14 +10,21 @@
 // within 2.8e-16, b2sqrt equal to sqrt().  The library division / sqrt cost ~27 issue slots each
 // (special-case branches); these cost 4-8.  Only the optics path uses them (1e-10 tolerance); the
 // sensor path keeps IEEE operations.
-__device__ __forceinline__ double b2rcp(double x) {
+__host__ __device__ __forceinline__ double b2rcp(double x) {
+#ifndef __CUDA_ARCH__
+    return 1.0 / x;  // host copy: set-up code only (the per-detector XyToV fit)
+#else
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     double e = fma(-x, r, 1.0);  // r (1 + e + e^2) = 1/x (1 - e^3)
     double t = fma(e, e, e);
     return fma(r, t, r);
+#endif
 }
-__device__ __forceinline__ double b2rsqrt(double x) {
+__host__ __device__ __forceinline__ double b2rsqrt(double x) {
+#ifndef __CUDA_ARCH__
+    return 1.0 / sqrt(x);
+#else
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double t = x * y;
@@ -25,6 +32,7 @@ __device__ __forceinline__ double b2rsqrt(double x) {
     double p = fma(0.375, e, 0.5);
     p *= e;
     return fma(y, p, y);
+#endif
 }
 // sqrt(x) for x >= 0 (x == 0 -> 0); negative x gives NaN like sqrt
 __device__ __forceinline__ double b2sqrt(double x) {
@@ -87,7 +95,7 @@ __device__ __forceinline__ double dcr_refraction(double wave_nm, const double pt
 // ------------------------------------------------------------------ TAN-SIP
 // packed triangle index for (i,j), i+j<=3, order: 00 01 02 03 10 11 12 20 21 30
 //   f(u,v) = sum ab[i][j] u^i v^j
-__device__ __forceinline__ void sip_fwd(const DevWcs& w, double u, double v, double& f, double& g) {
+__host__ __device__ __forceinline__ void sip_fwd(const DevWcs& w, double u, double v, double& f, double& g) {
     if (w.order <= 0) {
         f = u;
         g = v;
@@ -100,7 +108,7 @@ __device__ __forceinline__ void sip_fwd(const DevWcs& w, double u, double v, dou
     g = ((b[9] * u + (b[7] + b[8] * v)) * u + (b[4] + v * (b[5] + v * b[6]))) * u + (b[0] + v * (b[1] + v * (b[2] + v * b[3])));
 }
 
-__device__ __forceinline__ void sip_jac(const double* a, double u, double v, double& f, double& fu, double& fv) {
+__host__ __device__ __forceinline__ void sip_jac(const double* a, double u, double v, double& f, double& fu, double& fv) {
     double r0 = a[0] + v * (a[1] + v * (a[2] + v * a[3]));
     double r1 = a[4] + v * (a[5] + v * a[6]);
     double r2 = a[7] + a[8] * v;
@@ -114,7 +122,7 @@ __device__ __forceinline__ void sip_jac(const double* a, double u, double v, dou
 }
 
 // Newton inversion of the SIP polynomial (GalSim src/WCS.cpp InvertAB)
-__device__ __forceinline__ void sip_inv(const DevWcs& w, double u1, double v1, double& u, double& v) {
+__host__ __device__ __forceinline__ void sip_inv(const DevWcs& w, double u1, double v1, double& u, double& v) {
     u = u1;
     v = v1;
     if (w.order <= 0) return;
@@ -135,7 +143,7 @@ __device__ __forceinline__ void sip_inv(const DevWcs& w, double u1, double v1, d
 }
 
 // pixel -> tangent-plane (xi, eta) in radians, east/north positive
-__device__ __forceinline__ void wcs_pix_to_tan(const DevWcs& w, double x, double y, double& xi, double& eta) {
+__host__ __device__ __forceinline__ void wcs_pix_to_tan(const DevWcs& w, double x, double y, double& xi, double& eta) {
     double u = x - w.crpix[0], v = y - w.crpix[1];
     double f, g;
     sip_fwd(w, u, v, f, g);
@@ -144,7 +152,7 @@ __device__ __forceinline__ void wcs_pix_to_tan(const DevWcs& w, double x, double
     eta = (w.cd[2] * f + w.cd[3] * g) * d2r;
 }
 
-__device__ __forceinline__ void wcs_tan_to_pix(const DevWcs& w, double xi, double eta, double& x, double& y) {
+__host__ __device__ __forceinline__ void wcs_tan_to_pix(const DevWcs& w, double xi, double eta, double& x, double& y) {
     const double r2d = 180.0 / PI_D;
     double xd = xi * r2d, ed = eta * r2d;
     double u1 = w.cdinv[0] * xd + w.cdinv[1] * ed;
@@ -158,7 +166,8 @@ __device__ __forceinline__ void wcs_tan_to_pix(const DevWcs& w, double xi, doubl
 // XyToV.__call__: the deproject(img centre) o project(field centre) pair of
 // galsim/coord is a rotation of the unit sphere, i.e. a homography between the
 // two tangent planes: (a,b,c) = M (xi, eta, 1), (xi', eta') = (a/c, b/c).
-__device__ __forceinline__ void xy_to_v(const DevOptics& o, double x, double y, double& vx, double& vy, double& vz) {
+__host__ __device__ __forceinline__ void xy_to_field_exact(const DevOptics& o, double x, double y, double& thx,
+                                                           double& thy) {
     double xi, eta;
     wcs_pix_to_tan(o.img, x, y, xi, eta);
     const double* M = o.M_if;
@@ -166,8 +175,40 @@ __device__ __forceinline__ void xy_to_v(const DevOptics& o, double x, double y, 
     double b = M[3] * xi + M[4] * eta + M[5];
     double c = M[6] * xi + M[7] * eta + M[8];
     double ic = b2rcp(c);
-    double thx, thy;
     wcs_tan_to_pix(o.field, a * ic, b * ic, thx, thy);
+}
+
+// The same map compiled per detector (b2_xytov_compile): over one CCD the field tangents are a smooth,
+// almost affine function of the pixel position, and a tensor polynomial of degree 5 x 5 in the scaled
+// coordinates reproduces the exact chain (SIP forward, homography, Newton inversion of the field SIP) to
+// a few 1e-10 px -- 1e-13 of the coordinate, three orders inside the 1e-10 parity bar -- for 70 fused
+// multiply-adds.  Positions outside the fitted box take the exact chain.
+__device__ __forceinline__ void xy_to_field(const DevOptics& o, double x, double y, double& thx, double& thy) {
+    const DevXyPoly& p = o.xyv;
+    if (p.enabled && x >= p.box[0] && x <= p.box[1] && y >= p.box[2] && y <= p.box[3]) {
+        const double X = (x - p.c0[0]) * p.sc[0], Y = (y - p.c0[1]) * p.sc[1];
+        double fx = 0.0, fy = 0.0;
+#pragma unroll
+        for (int i = B2_XYPOLY_N - 1; i >= 0; --i) {
+            double rx = p.cx[i][B2_XYPOLY_N - 1], ry = p.cy[i][B2_XYPOLY_N - 1];
+#pragma unroll
+            for (int j = B2_XYPOLY_N - 2; j >= 0; --j) {
+                rx = fma(rx, Y, p.cx[i][j]);
+                ry = fma(ry, Y, p.cy[i][j]);
+            }
+            fx = fma(fx, X, rx);
+            fy = fma(fy, X, ry);
+        }
+        thx = fx;
+        thy = fy;
+    } else {
+        xy_to_field_exact(o, x, y, thx, thy);
+    }
+}
+
+__device__ __forceinline__ void xy_to_v(const DevOptics& o, double x, double y, double& vx, double& vy, double& vz) {
+    double thx, thy;
+    xy_to_field(o, x, y, thx, thy);
     // batoid.utils.gnomonicToDirCos
     double gamma = b2rsqrt(1.0 + thx * thx + thy * thy);
     vx = thx * gamma;

@@ -84,46 +84,8 @@ k_accumulate_slow(const __grid_constant__ DevSensor s, const SlowRec* __restrict
     for (unsigned long long base = first - (threadIdx.x & 31); base < total; base += stride) {
         unsigned long long j = base + (threadIdx.x & 31);
         if (j < total) {
-            SlowRec r = slow[j];
-            int ix = r.ix, iy = r.iy;
-            const double x = r.x, y = r.y, zconv = r.zconv;
-            bool off_edge = false;
-            bool found = inside_pixel<NVT>(s, ix, iy, x, y, zconv, &off_edge, npoly);
-            bool drop = (!found && off_edge);
-            if (!drop) {
-                int step = 0;
-                if (!found) {
-                    nneigh++;
-                    if ((x > y) && (x > 1.0 - y)) step = 1;
-                    else if ((x > y) && (x < 1.0 - y)) step = 7;
-                    else if ((x < y) && (x > 1.0 - y)) step = 3;
-                    else step = 5;
-                    int nn = step;
-#pragma unroll 1
-                    for (int m = 1; m < 9; ++m) {
-                        int ix_off = ix + c_xoff[nn], iy_off = iy + c_yoff[nn];
-                        double x_off = x - c_xoff[nn], y_off = y - c_yoff[nn];
-                        if (inside_pixel<NVT>(s, ix_off, iy_off, x_off, y_off, zconv, nullptr, npoly)) {
-                            ix = ix_off;
-                            iy = iy_off;
-                            found = true;
-                            break;
-                        }
-                        nn = ((nn - 1) + step) % 8 + 1;
-                    }
-                }
-                if (!found) {
-                    nnf++;
-                    int nn = r.coin ? 0 : step;
-                    ix += c_xoff[nn];
-                    iy += c_yoff[nn];
-                }
-                int ax = ix - s.xmin, ay = iy - s.ymin;
-                if (ax >= 0 && ax < s.nx && ay >= 0 && ay < s.ny) {
-                    atomicAdd(&s.delta[(size_t)ay * s.nx + ax], r.flux);
-                    my_added += r.flux;
-                }
-            }
+            int dax, day;
+            my_added += slow_photon<NVT>(s, slow[j], npoly, nneigh, nnf, dax, day);
         }
     }
     unsigned long long w0 = warp_sum(npoly), w1 = warp_sum(nneigh), w2 = warp_sum(nnf);
@@ -160,19 +122,6 @@ k_plain_accumulate(const __grid_constant__ DevSensor s, int64_t n, const double*
 }
 
 // ------------------------------------------------------------------ boundaries
-__device__ __forceinline__ void treering_point(const DevSensor& s, float2& pt, int i, int j, int ocx, int ocy) {
-    double tx = (double)i + (double)pt.x - s.trc[0] + (double)ocx;
-    double ty = (double)j + (double)pt.y - s.trc[1] + (double)ocy;
-    double r = sqrt(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)));
-    if (r > 0 && r < s.tr_max) {
-        double shift = s.tr_spline ? table_spline(s.ntr, s.tr_r, s.tr_f, s.tr_y2, r) : table_linear(s.ntr, s.tr_r, s.tr_f, r);
-        double dx = __ddiv_rn(__dmul_rn(shift, tx), r);
-        double dy = __ddiv_rn(__dmul_rn(shift, ty), r);
-        pt.x = (float)((double)pt.x + dx);
-        pt.y = (float)((double)pt.y + dy);
-    }
-}
-
 // undistorted boundaries + tree rings: one thread per (x, y) slot, x in [0,nx], y in [0,ny]
 __global__ void __launch_bounds__(256)
 k_init_boundaries(const __grid_constant__ DevSensor s, int ocx, int ocy) {
@@ -904,6 +853,8 @@ extern "C" int b2_sensor_destroy(b2_sensor* s) {
     free_list(s->owned);
     if (s->cum.ptr) cudaFree(s->cum.ptr);
     if (s->slow.ptr) cudaFree(s->slow.ptr);
+    if (s->stamp_meta.ptr) cudaFree(s->stamp_meta.ptr);
+    if (s->stamp_arena.ptr) cudaFree(s->stamp_arena.ptr);
     delete s;
     return 0;
 }

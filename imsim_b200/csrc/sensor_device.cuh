@@ -47,6 +47,7 @@ struct b2_sensor {
     double* tr_buf[3] = {nullptr, nullptr, nullptr};  // tree-ring tables of b2_sensor_set_treerings (reused)
     size_t tr_cap = 0;
     unsigned long long* dnslow = nullptr;
+    Scratch stamp_meta, stamp_arena;  // stamps.cu: job tables + per-block lists; boundary state of the stamps in flight
 };
 
 enum { ST_POLY = 0, ST_NEIGH = 1, ST_NOTFOUND = 2, ST_B9 = 3, ST_DROP = 4, ST_N = 8 };
@@ -237,10 +238,12 @@ struct SlowRec {
 // The first (converged) phase of Silicon::accumulate for one photon: conversion depth, drift to the
 // conversion point, diffusion, nominal pixel, inner-box test.  Deposits decided photons into `delta`
 // and returns true (filling `rec`) for the ones that need the polygon / neighbour treatment.
-__device__ __forceinline__ bool sensor_fast_path(const DevSensor& s, double x0, double y0, bool has_angles, double a,
-                                                 double b, bool has_wl, double wl_nm, double flux, double g1, double g2,
-                                                 double unf, double udep, SlowRec& rec, double& my_added, unsigned& nb9,
-                                                 unsigned& ndrop) {
+// (dax, day): array coordinates of the pixel a decided photon was deposited in, (-1, -1) if none
+__device__ __forceinline__ bool sensor_fast_path_ex(const DevSensor& s, double x0, double y0, bool has_angles, double a,
+                                                    double b, bool has_wl, double wl_nm, double flux, double g1,
+                                                    double g2, double unf, double udep, SlowRec& rec, double& my_added,
+                                                    unsigned& nb9, unsigned& ndrop, int& dax, int& day) {
+    dax = day = -1;
     const double T = s.thickness;
     const double invPixelSize = s.inv_pixel_size;         // the same IEEE quotients the reference forms per call,
     const double diffStep_pixel_z = s.diff_step_pixel_z;  // computed once on the host
@@ -286,6 +289,8 @@ __device__ __forceinline__ bool sensor_fast_path(const DevSensor& s, double x0, 
     if (x >= in.x && x <= in.y && y >= in.z && y <= in.w) {
         atomicAdd(&s.delta[k], flux);
         my_added = flux;
+        dax = ax;
+        day = ay;
         return false;
     }
     rec.ix = ix; rec.iy = iy;
@@ -295,6 +300,78 @@ __device__ __forceinline__ bool sensor_fast_path(const DevSensor& s, double x0, 
     rec.pad = 0;
     return true;
 }
+
+__device__ __forceinline__ bool sensor_fast_path(const DevSensor& s, double x0, double y0, bool has_angles, double a,
+                                                 double b, bool has_wl, double wl_nm, double flux, double g1, double g2,
+                                                 double unf, double udep, SlowRec& rec, double& my_added, unsigned& nb9,
+                                                 unsigned& ndrop) {
+    int dax, day;
+    return sensor_fast_path_ex(s, x0, y0, has_angles, a, b, has_wl, wl_nm, flux, g1, g2, unf, udep, rec, my_added, nb9,
+                               ndrop, dax, day);
+}
+
+// The second phase for one listed photon: outer box, polygon test, neighbour search, coin flip -- the
+// reference's sequence (Silicon::accumulate / searchNeighbors).  Returns the flux deposited (0 if lost).
+template <int NVT>
+__device__ __forceinline__ double slow_photon(const DevSensor& s, const SlowRec& r, unsigned& npoly, unsigned& nneigh,
+                                              unsigned& nnf, int& dax, int& day) {
+    dax = day = -1;
+    int ix = r.ix, iy = r.iy;
+    const double x = r.x, y = r.y, zconv = r.zconv;
+    bool off_edge = false;
+    bool found = inside_pixel<NVT>(s, ix, iy, x, y, zconv, &off_edge, npoly);
+    if (!found && off_edge) return 0.0;
+    int step = 0;
+    if (!found) {
+        nneigh++;
+        if ((x > y) && (x > 1.0 - y)) step = 1;
+        else if ((x > y) && (x < 1.0 - y)) step = 7;
+        else if ((x < y) && (x > 1.0 - y)) step = 3;
+        else step = 5;
+        int nn = step;
+#pragma unroll 1
+        for (int m = 1; m < 9; ++m) {
+            int ix_off = ix + c_xoff[nn], iy_off = iy + c_yoff[nn];
+            double x_off = x - c_xoff[nn], y_off = y - c_yoff[nn];
+            if (inside_pixel<NVT>(s, ix_off, iy_off, x_off, y_off, zconv, nullptr, npoly)) {
+                ix = ix_off;
+                iy = iy_off;
+                found = true;
+                break;
+            }
+            nn = ((nn - 1) + step) % 8 + 1;
+        }
+    }
+    if (!found) {
+        nnf++;
+        int nn = r.coin ? 0 : step;
+        ix += c_xoff[nn];
+        iy += c_yoff[nn];
+    }
+    int ax = ix - s.xmin, ay = iy - s.ymin;
+    if (ax >= 0 && ax < s.nx && ay >= 0 && ay < s.ny) {
+        atomicAdd(&s.delta[(size_t)ay * s.nx + ax], r.flux);
+        dax = ax;
+        day = ay;
+        return r.flux;
+    }
+    return 0.0;
+}
+
+// Silicon::calculateTreeRingDistortion on one stored boundary point of the slot (i, j) (image coordinates)
+__device__ __forceinline__ void treering_point(const DevSensor& s, float2& pt, int i, int j, int ocx, int ocy) {
+    double tx = (double)i + (double)pt.x - s.trc[0] + (double)ocx;
+    double ty = (double)j + (double)pt.y - s.trc[1] + (double)ocy;
+    double r = sqrt(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)));
+    if (r > 0 && r < s.tr_max) {
+        double shift = s.tr_spline ? table_spline(s.ntr, s.tr_r, s.tr_f, s.tr_y2, r) : table_linear(s.ntr, s.tr_r, s.tr_f, r);
+        double dx = __ddiv_rn(__dmul_rn(shift, tx), r);
+        double dy = __ddiv_rn(__dmul_rn(shift, ty), r);
+        pt.x = (float)((double)pt.x + dx);
+        pt.y = (float)((double)pt.y + dy);
+    }
+}
+
 
 // the four sensor draws of photon `idx` (Philox stream 3): one Philox block per photon; two 24-bit
 // uniforms -> Box-Muller in FP32 (a diffusion step with 1e-7 relative granularity is statistically

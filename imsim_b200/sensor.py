@@ -331,6 +331,40 @@ class SiliconSensor:
                                                  _lib.ptr(photons.flux), _lib.where_of(photons.x), C.byref(added)))
         return added.value
 
+    def accumulate_stamps(self, jobs, photons, full, full_xmin=0, full_ymin=0, orig_center=(0, 0), rand4=None,
+                          want_stats=True, want_added=False):
+        """The object loop of the classic pipeline in one call (``b2_sensor_accumulate_stamps``): every job
+        ``(p0, n, xmin, ymin, nx, ny, plain)`` gets its own zero stamp with fresh boundaries, its photons
+        ``photons[p0:p0+n]`` are accumulated there at this sensor's ``nrecalc`` cadence -- the loop runs on the
+        device, one thread block per stamp -- and the stamp is added to ``full`` (a 2-d CUDA tensor, float32 or
+        float64, whose pixel (0, 0) is image pixel (full_xmin, full_ymin)).  ``photons``: ``DevicePhotons``.
+        Returns the stats (``added_flux`` summed over the stamps) and, if asked, the flux per job."""
+        import torch
+
+        jobs = list(jobs)
+        arr = (_abi.B2StampJob * max(len(jobs), 1))()
+        for k, j in enumerate(jobs):
+            arr[k].p0, arr[k].n, arr[k].xmin, arr[k].ymin, arr[k].nx, arr[k].ny = (int(v) for v in j[:6])
+            arr[k].plain = int(bool(j[6])) if len(j) > 6 else 0
+        if not (full.is_cuda and full.dim() == 2 and full.is_contiguous() and full.dtype in (torch.float32, torch.float64)):
+            raise _lib.B2Error("accumulate_stamps needs a contiguous 2-d float32 / float64 CUDA tensor as full image")
+        n = len(photons)
+        has_ang = photons.hasAllocatedAngles()
+        has_wl = photons.hasAllocatedWavelengths()
+        stats = _abi.B2AccumStats() if want_stats else None
+        added = np.zeros(max(len(jobs), 1)) if want_added else None
+        _lib.check(self._lib.b2_sensor_accumulate_stamps(
+            self._h, len(jobs), C.cast(arr, C.c_void_p), n, _lib.ptr(photons.x), _lib.ptr(photons.y),
+            _lib.ptr(photons.dxdz) if has_ang else None, _lib.ptr(photons.dydz) if has_ang else None,
+            _lib.ptr(photons.wavelength) if has_wl else None, _lib.ptr(photons.flux), _lib.ptr(rand4),
+            self._seed & 0xFFFFFFFFFFFFFFFF, self._photon_offset, int(orig_center[0]), int(orig_center[1]),
+            C.c_void_p(full.data_ptr()), int(full_xmin), int(full_ymin), int(full.shape[1]), int(full.shape[0]),
+            full.element_size(), C.byref(stats) if want_stats else None,
+            added.ctypes.data if want_added else None))
+        self._photon_offset += n
+        self.last_stats = stats
+        return (stats, added[:len(jobs)]) if want_added else stats
+
     def accumulate(self, photons, image, orig_center=None, resume=False, recalc=False, rand4=None,
                    sync_image=True, want_stats=True, prebound=False):
         """Accumulate photons on the image; returns the flux that landed on it.

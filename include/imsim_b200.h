@@ -219,6 +219,15 @@ typedef struct {
     uint64_t n_dropped_bottom;  /* zconv < 0 */
 } B2AccumStats;
 
+/* One object of the classic per-object pipeline for b2_sensor_accumulate_stamps: photons [p0, p0 + n) of the
+   arrays handed to the call are accumulated on the object's own zero stamp image (imsim/stamp.py:562-572) */
+typedef struct {
+    int64_t p0, n;
+    int32_t xmin, ymin, nx, ny; /* stamp bounds in image coordinates */
+    int32_t plain;              /* != 0: galsim.Sensor semantics (objects below max_flux_simple, stamp.py:534-537) */
+    int32_t pad;
+} B2StampJob;
+
 /* ------------------------------------------------------------------ */
 /* Stage 1: photons of catalogue objects generated in HBM              */
 /* ------------------------------------------------------------------ */
@@ -297,7 +306,8 @@ int b2_abi_version(void);
 uint64_t b2_launch_count(void);
 /* sizeof() of the POD structs, for binding self-checks:
    0 B2Telescope, 1 B2Surface, 2 B2TanSip, 3 B2Detector, 4 B2Diffraction,
-   5 B2OpticsOptions, 6 B2OpticsStats, 7 B2SensorConfig, 8 B2AccumStats, 9 B2Obsc, 10 B2Medium */
+   5 B2OpticsOptions, 6 B2OpticsStats, 7 B2SensorConfig, 8 B2AccumStats, 9 B2Obsc, 10 B2Medium,
+   11 B2Object, 12 B2Psf, 13 B2Amp, 14 B2StampJob */
 int64_t b2_sizeof(int32_t which);
 
 /* ---- context: one per (process, detector) --------------------------- */
@@ -336,6 +346,13 @@ int b2_telescope_set_extra(b2_ctx* ctx, int surface_index, int extra_kind, const
 int b2_telescope_program(b2_ctx* ctx);
 /* replaces: base['current_image'].wcs, base['_icrf_to_field'] (imsim/photon_ops.py:407-408) */
 int b2_wcs_upload(b2_ctx* ctx, const B2TanSip* img_wcs, const B2TanSip* icrf_to_field);
+/* XyToV (imsim/photon_ops.py:454-475) compiled for one detector: over the pixel box the chain img_wcs.xyToradec
+   -> icrf_to_field.radecToxy is replaced by one degree 5 x 5 polynomial of the field-angle tangents, fitted to the
+   exact chain at Chebyshev points and adopted only if it reproduces the exact chain on a check grid to tol_px
+   pixels (1e-9 is typical: ~3e-10 px is reached, 1e-13 of the coordinate); max_resid_px reports the check.
+   Positions outside the box always take the exact chain; b2_wcs_upload discards the compiled form. */
+int b2_xytov_compile(b2_ctx* ctx, double xlo, double xhi, double ylo, double yhi, double tol_px,
+                     double* max_resid_px);
 /* replaces: camera[det_name] as used by imsim/photon_ops.py:495-500 */
 int b2_detector_upload(b2_ctx* ctx, const B2Detector* det);
 /* replaces: RubinDiffraction.__init__ (imsim/photon_ops.py:233-262) */
@@ -454,6 +471,21 @@ int b2_sensor_accumulate(b2_sensor* s, int64_t n, const double* x, const double*
                          const double* flux, const double* rand4, uint64_t seed, uint64_t photon_offset,
                          int32_t orig_center_x, int32_t orig_center_y, int32_t resume, int32_t recalc,
                          int where, B2AccumStats* stats);
+/* The object loop of the classic pipeline (imsim/lsst_image.py:342-389 around imsim/stamp.py:562-572) in one
+   call: for every job a zero stamp is bound (fresh tree-ring boundaries), its photons are accumulated with the
+   sensor's nrecalc cadence inside the stamp -- the whole loop runs on the device, one thread block per stamp --
+   and the stamp is added to the full image (full_image[bounds] += stamp[bounds]).
+   jobs: HOST; photon arrays, rand4 ([4][n], optional) and full_pixels (full_ny x full_nx, float32 / float64): DEVICE.
+   Draws: Philox(seed) at photon_offset + index in the arrays.  Stamp states live in an arena
+   (B2_STAMP_ARENA_MB, default 6144; larger job lists run as several launches).  The sensor's own bound image is
+   not touched.  added_per_job (HOST, optional): flux that landed on each stamp.  Bit-identical, stamp by stamp,
+   to b2_sensor_bind_image(zeros) + b2_sensor_accumulate on the same photons. */
+int b2_sensor_accumulate_stamps(b2_sensor* s, int32_t njobs, const B2StampJob* jobs, int64_t n, const double* x,
+                                const double* y, const double* dxdz, const double* dydz, const double* wavelength_nm,
+                                const double* flux, const double* rand4, uint64_t seed, uint64_t photon_offset,
+                                int32_t orig_center_x, int32_t orig_center_y, void* full_pixels, int32_t full_xmin,
+                                int32_t full_ymin, int32_t full_nx, int32_t full_ny, int32_t dtype_bytes,
+                                B2AccumStats* stats, double* added_per_job);
 /* galsim.SiliconSensor.calculate_pixel_areas(image, orig_center, use_flux)
    (imsim/flat.py:223).  Uses the bound image as the charge; areas: ny*nx float64. */
 int b2_sensor_pixel_areas(b2_sensor* s, int32_t orig_center_x, int32_t orig_center_y, int32_t use_flux,

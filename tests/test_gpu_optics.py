@@ -405,6 +405,7 @@ def test_opd_screen():
     assert [it.name for it in tels.items][:2] == ["Screen", "M1"]
     rr = np.sqrt(rng.uniform(2.6**2, 4.1**2, n))
     ph = rng.uniform(0, 2 * np.pi, n)
+    nair = tel.in_medium.n(wl)  # the telescope's own entrance medium (|v| = 1 / n)
     base = [rr * np.cos(ph), rr * np.sin(ph), np.zeros(n), np.full(n, 1e-3) / nair, np.zeros(n), -np.sqrt(1 - 1e-6) / nair,
             np.zeros(n), wl]
     res = {}
@@ -468,3 +469,33 @@ def test_opd_zemax_on_device(program, monkeypatch):
 
     rms = check_opd_against_zemax(trace)
     assert rms < 0.005  # nm
+
+
+def test_compiled_xy_to_v_reproduces_the_exact_chain(monkeypatch):
+    """XyToV compiled per detector (b2_xytov_compile): the polynomial is adopted only below 2e-9 px on its check
+    grid; here it is compared with the exact chain (B2_XYTOV_EXACT=1, and the oracle) on random positions inside
+    the box, and positions outside the box must take the exact chain."""
+    from imsim_b200 import OpticsContext
+    from oracle import oracle as orc
+
+    for det in ("R22_S11", "R41_S20"):
+        su = helpers.oracle_setup(det)
+        ctx = _ctx(su)
+        assert ctx.xytov_residual_px is not None and ctx.xytov_residual_px < 2e-9, ctx.xytov_residual_px
+        monkeypatch.setenv("B2_XYTOV_EXACT", "1")
+        exact = _ctx(su)
+        monkeypatch.delenv("B2_XYTOV_EXACT")
+        assert exact.xytov_residual_px is None
+        rng = np.random.default_rng(11)
+        m = OpticsContext.XYTOV_MARGIN
+        x = rng.uniform(-m, su.detector.nx + m, 50000)
+        y = rng.uniform(-m, su.detector.ny + m, 50000)
+        x[:100] = rng.uniform(-5000, -m - 1, 100)  # outside the box: exact chain
+        v = ctx.xy_to_v(x, y)
+        ve = exact.xy_to_v(x, y)
+        vo = orc.xy_to_v(su.img_wcs.to_pod(), su.icrf_to_field.to_pod(), x, y)
+        rad_per_px = 0.2 / 206264.8
+        for k in range(2):
+            assert np.abs(v[k] - ve[k]).max() < 2e-9 * rad_per_px
+            assert np.abs(v[k] - vo[k]).max() < 2e-9 * rad_per_px
+            np.testing.assert_array_equal(v[k][:100], ve[k][:100])
