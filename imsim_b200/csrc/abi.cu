@@ -69,6 +69,8 @@ extern "C" int b2_ctx_destroy(b2_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (b2_sensor* s : ctx->sensors) b2_sensor_orphan(s);
+    ctx->sensors.clear();
     b2_stage1_release(ctx);
     b2_pipe_release(ctx);
     for (auto& e : ctx->extras) {

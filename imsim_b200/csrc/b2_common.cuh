@@ -148,6 +148,7 @@ struct b2_ctx {
     // live timing of the dominant kernel (bench.py roofline): event pairs around each launch
     bool record_events = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+    std::vector<struct b2_sensor*> sensors;  // sensors created on this context and not yet destroyed
     struct b2_hostpipe* pipe = nullptr;  // hostpipe.cu: pinned ring + streams of the pipelined B2_HOST route
 };
 
@@ -162,7 +163,8 @@ int b2_pipe_run(b2_ctx* ctx, int64_t n, int nin, const double* const* hin, doubl
                 double* const* hout, const double* const* dout,
                 const std::function<int(int64_t, int64_t, cudaStream_t)>* kernel);
 void b2_pipe_release(b2_ctx* ctx);
-void b2_stage1_release(b2_ctx* ctx);  // stage1.cu: per-context PSF / profile tables
+void b2_stage1_release(b2_ctx* ctx);
+void b2_sensor_orphan(struct b2_sensor* s);  // sensor.cu  // stage1.cu: per-context PSF / profile tables
 
 // stage helper for B2_HOST calls: carve arrays out of the context scratch
 struct Stager {

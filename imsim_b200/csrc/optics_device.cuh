@@ -832,8 +832,12 @@ __device__ __forceinline__ void sample_time_pupil(uint64_t seed, uint64_t idx, d
     philox4(seed, idx, 1u, r);
     philox4(seed, idx, 2u, q);
     double ut = u01(r[0], r[1]), ur = u01(r[2], r[3]), uphi = u01(q[0], q[1]);
-    time = t0 + exptime * ut;
-    double rr = b2sqrt_fast(r_in * r_in + (r_out * r_out - r_in * r_in) * ur);
+    // explicit fused operations: the same bits whether this is inlined in the fused pool step or runs as the
+    // sampler kernel (a contraction left to the compiler may differ between the two, and a one-ulp change of the
+    // pupil position is amplified by the spider kick of a photon grazing a vane)
+    time = fma(exptime, ut, t0);
+    const double rin2 = r_in * r_in;
+    double rr = b2sqrt_fast(fma(__dsub_rn(r_out * r_out, rin2), ur, rin2));
     double sn, cs;
     sincospi(2.0 * uphi, &sn, &cs);
     pu = rr * cs;

@@ -788,6 +788,7 @@ extern "C" int b2_sensor_create(b2_ctx* ctx, const B2SensorConfig* cfg, const do
     s->dadded = (double*)((char*)p + ST_N * sizeof(unsigned long long));
     s->dnslow = (unsigned long long*)((char*)p + ST_N * sizeof(unsigned long long) + 8);
     B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->sensors.push_back(s);
     *out = s;
     return 0;
 }
@@ -796,6 +797,7 @@ extern "C" int b2_sensor_create(b2_ctx* ctx, const B2SensorConfig* cfg, const do
 // per-image boundary arrays, the big allocation, are kept
 extern "C" int b2_sensor_set_treerings(b2_sensor* s, double cx, double cy, const double* tr_r, const double* tr_f,
                                        const double* tr_y2, int32_t n) {
+    B2_REQUIRE(s && s->ctx, "b2_sensor_set_treerings: null sensor, or its context has been destroyed");
     B2_REQUIRE(s, "b2_sensor_set_treerings: null sensor");
     B2_REQUIRE(n <= 2 || (tr_r && tr_f), "b2_sensor_set_treerings: table missing");
     b2_ctx* ctx = s->ctx;
@@ -845,8 +847,9 @@ static void free_list(std::vector<void*>& v) {
     v.clear();
 }
 
-extern "C" int b2_sensor_destroy(b2_sensor* s) {
-    if (!s) return 0;
+// device resources of a sensor; the struct itself stays until b2_sensor_destroy
+static void sensor_release_device(b2_sensor* s) {
+    if (!s->ctx) return;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     free_list(s->image_owned);
@@ -855,6 +858,24 @@ extern "C" int b2_sensor_destroy(b2_sensor* s) {
     if (s->slow.ptr) cudaFree(s->slow.ptr);
     if (s->stamp_meta.ptr) cudaFree(s->stamp_meta.ptr);
     if (s->stamp_arena.ptr) cudaFree(s->stamp_arena.ptr);
+    s->cum = s->slow = s->stamp_meta = s->stamp_arena = Scratch{};
+    s->bound = s->initialized = false;
+}
+
+// called by b2_ctx_destroy for the sensors still alive on it: host languages with garbage collection may
+// finalise the context before its sensors; their handles stay valid to destroy, every other call fails loudly
+void b2_sensor_orphan(b2_sensor* s) {
+    sensor_release_device(s);
+    s->ctx = nullptr;
+}
+
+extern "C" int b2_sensor_destroy(b2_sensor* s) {
+    if (!s) return 0;
+    if (s->ctx) {
+        auto& v = s->ctx->sensors;
+        v.erase(std::remove(v.begin(), v.end(), s), v.end());
+        sensor_release_device(s);
+    }
     delete s;
     return 0;
 }
@@ -862,6 +883,7 @@ extern "C" int b2_sensor_destroy(b2_sensor* s) {
 extern "C" int b2_sensor_bind_image(b2_sensor* s, int32_t xmin, int32_t ymin, int32_t nx, int32_t ny,
                                     int32_t dtype_bytes, const void* pixels, int where) {
     B2_REQUIRE(s, "b2_sensor_bind_image: null sensor");
+    B2_REQUIRE(s->ctx, "b2_sensor_bind_image: the context this sensor was created on has been destroyed");
     B2_REQUIRE(nx > 0 && ny > 0, "b2_sensor_bind_image: empty image");
     B2_REQUIRE(dtype_bytes == 4 || dtype_bytes == 8, "b2_sensor_bind_image: image must be float32 or float64");
     b2_ctx* ctx = s->ctx;

@@ -27,9 +27,11 @@
 #define ST_THREADS 512
 #define ST_PER 4
 #define ST_TILE (ST_THREADS * ST_PER)  // photons per pass
+#define ST_QCAP 4096                  // owned slots / pixels queued per round of the boundary update
+#define ST_PIXCAP 32768                // charged pixels listed per boundary update (beyond: box scan)
 
 struct StampSlot {  // byte offsets of one stamp's state inside the arena
-    size_t H, V, inner, outer, delta, target, changed;
+    size_t H, V, inner, outer, delta, target, changed, cbits;
 };
 
 struct StampPhotons {
@@ -87,7 +89,7 @@ __device__ __forceinline__ void stamp_update_slot(const DevSensor& s, const floa
         bool change = false;
         for (int j = j1; j <= j2; ++j)
             for (int i = i1; i <= i2; ++i) {
-                double c = charge[(size_t)j * nx + i];
+                double c = __ldcg(charge + (size_t)j * nx + i);
                 if (c == 0.0) continue;
                 change = true;
                 const float2* kh = KH + ((y - j + cyk) * s.nx9 + (x - i + cxk)) * (NV + 2);
@@ -112,7 +114,7 @@ __device__ __forceinline__ void stamp_update_slot(const DevSensor& s, const floa
         bool change = false;
         for (int j = j1; j <= j2; ++j)
             for (int i = i1; i <= i2; ++i) {
-                double c = charge[(size_t)j * nx + i];
+                double c = __ldcg(charge + (size_t)j * nx + i);
                 if (c == 0.0) continue;
                 change = true;
                 const float2* kv = KV + ((y - j + cyk) * s.nx9 + (x - i + cxk)) * NV;
@@ -132,10 +134,135 @@ __device__ __forceinline__ void stamp_update_slot(const DevSensor& s, const floa
     }
 }
 
+// ---- the update driven by the list of charged pixels ----------------------------------------------------------
+// Every listed pixel proposes the boundary slots (and, in a second pass, the pixels) within its reach.  A proposal
+// is taken up by exactly one proposer without any atomics: all charged pixels that reach a slot see the same
+// (2q+2) x (2q+2) window of the stamp's occupancy bitmap around it, and the first set bit of that window, in
+// (row, column) order, is the owner.  The owner then gathers the window's charges in that same order -- the order
+// of k_update_distortions, so the sums are bit-identical -- reading only the bitmap rows it already holds and the
+// delta of pixels that do carry charge.  Bitmap and delta are written by atomics: they are read with __ldcg.
+struct StampBits {  // occupancy bitmap of the stamp in flight: in shared memory when it fits, else in the arena
+    unsigned* w;
+    int wpr;      // words per pixel row
+    bool global;  // arena copy: written by atomics, so read with __ldcg (L2), never through L1
+    __device__ __forceinline__ unsigned word(int k) const { return global ? __ldcg(w + k) : w[k]; }
+};
+
+__device__ __forceinline__ unsigned row_bits(const StampBits& cb, int j, int i1, int i2) {
+    // bits of row j for columns i1 .. i2 (i2 - i1 < 32), bit 0 = column i1
+    const int w1 = i1 >> 5, w2 = i2 >> 5;
+    unsigned long long v = cb.word(j * cb.wpr + w1);
+    if (w2 != w1) v |= (unsigned long long)cb.word(j * cb.wpr + w2) << 32;
+    v >>= (i1 & 31);
+    const int n = i2 - i1 + 1;
+    return (unsigned)v & (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
+}
+
+#define ST_QMAX 3  // the list path is written for qdist = 3 (GalSim's default, what imSim's models use): 8 x 8 windows
+
+// q == 3: the window of slot (x, y) is 8 rows x 8 columns, one 64-bit word, bit 8 r + c = pixel (x - 4 + c, y - 4 + r)
+__device__ __forceinline__ unsigned long long stamp_slot_window(const DevSensor& s, const StampBits& cb, int x, int y) {
+    const int c0 = x - 4, r0 = y - 4;
+    const int cl = max(c0, 0), ch = min(x + 3, s.nx - 1);
+    unsigned long long W = 0ull;
+    if (cl > ch) return W;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int j = r0 + r;
+        if (j >= 0 && j < s.ny) W |= (unsigned long long)(row_bits(cb, j, cl, ch) << (cl - c0)) << (8 * r);
+    }
+    return W;
+}
+
+// is (pi, pj) the first charged pixel of the window (row, column order)?
+__device__ __forceinline__ bool stamp_slot_owner(unsigned long long W, int x, int y, int pi, int pj) {
+    if (!W) return false;
+    const int ob = __ffsll((long long)W) - 1;
+    return (y - 4 + (ob >> 3)) == pj && (x - 4 + (ob & 7)) == pi;
+}
+
+// the gather of slot (x, y): boundary points in registers, one delta load per charged pixel, one store at the end
+template <int NV>
+__device__ __forceinline__ void stamp_slot_apply(const DevSensor& s, const float2* __restrict__ KH,
+                                                 const float2* __restrict__ KV, unsigned long long W, int x, int y) {
+    const int nx = s.nx, ny = s.ny;
+    const int c0 = x - 4, r0 = y - 4;
+    const int cxk = (s.nx9 - 1) / 2, cyk = (s.ny9 - 1) / 2;
+    const double* __restrict__ charge = s.delta;
+    if (x < nx) {
+        // horizontal boundary: all rows of the window, columns x-3 .. x+3 (not column c0)
+        unsigned long long Wh = W & 0xfefefefefefefefeull;
+        float2* h = s.H + Hidx(s, x, y);
+        float2 hp[NV + 2];
+#pragma unroll
+        for (int k = 0; k <= NV + 1; ++k) hp[k] = h[k];
+        bool any = false;
+        while (Wh) {
+            const int b = __ffsll((long long)Wh) - 1;
+            Wh &= Wh - 1;
+            const int j = r0 + (b >> 3), i = c0 + (b & 7);
+            const double c = __ldcg(charge + (size_t)j * nx + i);
+            if (c == 0.0) continue;
+            any = true;
+            const float2* kh = KH + ((y - j + cyk) * s.nx9 + (x - i + cxk)) * (NV + 2);
+#pragma unroll
+            for (int k = 0; k <= NV + 1; ++k) {
+                const float2 d = kh[k];
+                hp[k].x = (float)__dadd_rn((double)hp[k].x, __dmul_rn((double)d.x, c));
+                hp[k].y = (float)__dadd_rn((double)hp[k].y, __dmul_rn((double)d.y, c));
+            }
+        }
+        if (any) {
+#pragma unroll
+            for (int k = 0; k <= NV + 1; ++k) h[k] = hp[k];
+        }
+    }
+    if (y < ny) {
+        // vertical boundary: rows y-3 .. y+3 (not row r0), all columns of the window
+        unsigned long long Wv = W & ~0xffull;
+        float2* v = s.V + Vidx(s, x, y);
+        float2 vp[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) vp[k] = v[k];
+        bool any = false;
+        while (Wv) {
+            const int b = __ffsll((long long)Wv) - 1;
+            Wv &= Wv - 1;
+            const int j = r0 + (b >> 3), i = c0 + (b & 7);
+            const double c = __ldcg(charge + (size_t)j * nx + i);
+            if (c == 0.0) continue;
+            any = true;
+            const float2* kv = KV + ((y - j + cyk) * s.nx9 + (x - i + cxk)) * NV;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                const float2 d = kv[k];
+                vp[k].x = (float)__dadd_rn((double)vp[k].x, __dmul_rn((double)d.x, c));
+                vp[k].y = (float)__dadd_rn((double)vp[k].y, __dmul_rn((double)d.y, c));
+            }
+        }
+        if (any) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) v[k] = vp[k];
+        }
+    }
+}
+
+// second pass: is (pi, pj) the first charged pixel within q+1 of pixel (x, y)?  (then it refreshes that pixel's boxes)
+__device__ __forceinline__ bool stamp_owns_pixel(const DevSensor& s, const StampBits& cb, int x, int y, int pi, int pj) {
+    const int q = s.qdist;
+    const int cl = max(x - q - 1, 0), ch = min(x + q + 1, s.nx - 1);
+    const int jl = max(y - q - 1, 0), jh = min(y + q + 1, s.ny - 1);
+    for (int j = jl; j <= jh; ++j) {
+        const unsigned mm = row_bits(cb, j, cl, ch);
+        if (mm) return j == pj && cl + __ffs(mm) - 1 == pi;
+    }
+    return false;
+}
+
 template <typename T>
 __device__ __forceinline__ void stamp_fold_delta(const DevSensor& s, int x, int y) {
     size_t i = (size_t)y * s.nx + x;
-    double d = s.delta[i];
+    double d = __ldcg(s.delta + i);  // written by atomics: read where they live (L2), not through L1
     if (d != 0.0) {
         T* t = reinterpret_cast<T*>(s.target);
         t[i] = (T)__dadd_rn((double)t[i], d);
@@ -149,11 +276,13 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
              const int* __restrict__ order, int njobs, int* __restrict__ next, unsigned char* __restrict__ arena,
              const __grid_constant__ StampPhotons ph, double nrecalc, int ocx, int ocy, const __grid_constant__ FullImage full,
              unsigned long long* __restrict__ stats, double* __restrict__ added_total, double* __restrict__ added_job,
-             SlowRec* __restrict__ slow_scratch) {
+             SlowRec* __restrict__ slow_scratch, int* __restrict__ pix_scratch, int smem_bit_words,
+             unsigned long long* __restrict__ prof) {
     extern __shared__ float2 sK[];  // KH then KV
     __shared__ DevSensor s;
     __shared__ int sh_job, sh_cut, pend[4];  // pend: box of the pixels holding charge since the last update
-    __shared__ unsigned sh_nslow, sh_nupd;
+    __shared__ unsigned sh_nslow, sh_nupd, sh_npix, sh_nq;
+    __shared__ unsigned queue[ST_QCAP];  // sh_npix: length of the charged-pixel list (may exceed its capacity)
     __shared__ double sh_warp[ST_THREADS / 32], sh_tile_sum;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nKH = base.nx9 * base.ny9 * (NV + 2), nKV = base.nx9 * base.ny9 * NV;
@@ -162,9 +291,19 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
     const float2* KH = sK;
     const float2* KV = sK + nKH;
     SlowRec* slow = slow_scratch + (size_t)blockIdx.x * ST_TILE;
+    int* pixlist = pix_scratch + (size_t)blockIdx.x * ST_PIXCAP;
     unsigned npoly = 0, nneigh = 0, nnf = 0, nb9 = 0, ndrop = 0;
     const bool f32 = full.dtype_bytes == 4;
     if (tid == 0) sh_nupd = 0;
+    // B2_STAMP_PROFILE: cycles of thread 0 per phase, summed over the blocks (0 set-up, 1 cut search, 2 deposit, 3 slow
+    // list, 4 boundary slots, 5 boxes, 6 fold, 7 final add)
+    long long tlast = prof ? clock64() : 0;
+#define ST_PROF(k)                                                   \
+    if (prof && tid == 0) {                                          \
+        const long long tnow = clock64();                            \
+        atomicAdd(&prof[k], (unsigned long long)(tnow - tlast));     \
+        tlast = tnow;                                                \
+    }
 
     for (;;) {
         __syncthreads();
@@ -201,9 +340,17 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
                 s.dtype_bytes = full.dtype_bytes;
                 pend[0] = pend[2] = 1 << 30;
                 pend[1] = pend[3] = -1;
+                sh_npix = 0;
             }
             __syncthreads();
             uint8_t* changed = arena + slots[jid].changed;
+            StampBits cb;
+            cb.wpr = (s.nx + 31) / 32;
+            cb.global = cb.wpr * s.ny > smem_bit_words;
+            cb.w = cb.global ? reinterpret_cast<unsigned*>(arena + slots[jid].cbits)
+                             : reinterpret_cast<unsigned*>(sK + nKH + nKV);
+            unsigned* const cbits = cb.w;
+            const int wpr = cb.wpr;
             const int nx = s.nx, ny = s.ny;
             const bool tr = s.ntr > 2;
             for (int idx = tid; idx < (nx + 1) * (ny + 1); idx += ST_THREADS) {
@@ -232,12 +379,15 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
                     size_t i = (size_t)y * nx + x;
                     s.delta[i] = 0.0;
                     changed[i] = 0;
+                    if ((x & 31) == 0) cbits[y * wpr + (x >> 5)] = 0u;
                     if (f32) reinterpret_cast<float*>(s.target)[i] = 0.f;
                     else reinterpret_cast<double*>(s.target)[i] = 0.0;
                 }
             }
             __syncthreads();
             for (int idx = tid; idx < nx * ny; idx += ST_THREADS) stamp_bounds_pixel<NV>(s, idx % nx, idx / nx);
+            __syncthreads();
+            ST_PROF(0)
 
             // ---- Silicon::accumulate with the boundary update every nrecalc electrons
             double accum = 0.0;  // flux since the last update (block-uniform)
@@ -284,6 +434,7 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
                 }
                 __syncthreads();
                 const bool hit = sh_cut <= ST_TILE;
+                ST_PROF(1)
                 const int64_t cut = hit ? i0 + sh_cut + 1 : tend;
                 // ---- deposit photons [i0, cut): fast path, the rest to the block's list
                 int bx0 = 1 << 30, bx1 = -1, by0 = 1 << 30, by1 = -1;
@@ -319,6 +470,14 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
                         if (dax >= 0) {
                             bx0 = min(bx0, dax); bx1 = max(bx1, dax);
                             by0 = min(by0, day); by1 = max(by1, day);
+                            const int pix = day * nx + dax;
+                            if (nrecalc > 0.0) {
+                                const unsigned bit = 1u << (dax & 31);
+                                if (!(atomicOr(&cbits[day * wpr + (dax >> 5)], bit) & bit)) {  // first charge since the update
+                                    unsigned at = atomicAdd(&sh_npix, 1u);
+                                    if (at < ST_PIXCAP) pixlist[at] = pix;
+                                }
+                            }
                         }
                     }
                     unsigned m = __ballot_sync(0xffffffffu, to_slow);
@@ -330,12 +489,21 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
                     }
                 }
                 __syncthreads();
+                ST_PROF(2)
                 for (unsigned j = tid; j < sh_nslow; j += ST_THREADS) {
                     int dax, day;
                     my_added += slow_photon<NV>(s, slow[j], npoly, nneigh, nnf, dax, day);
                     if (dax >= 0) {
                         bx0 = min(bx0, dax); bx1 = max(bx1, dax);
                         by0 = min(by0, day); by1 = max(by1, day);
+                        const int pix = day * nx + dax;
+                        if (nrecalc > 0.0) {
+                            const unsigned bit = 1u << (dax & 31);
+                            if (!(atomicOr(&cbits[day * wpr + (dax >> 5)], bit) & bit)) {
+                                unsigned at = atomicAdd(&sh_npix, 1u);
+                                if (at < ST_PIXCAP) pixlist[at] = pix;
+                            }
+                        }
                     }
                 }
                 if (bx1 >= 0) {
@@ -343,10 +511,83 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
                     atomicMin(&pend[2], by0); atomicMax(&pend[3], by1);
                 }
                 __syncthreads();
+                ST_PROF(3)
                 if (hit) {
                     // ---- Silicon::update, restricted to the reach of the charge deposited since the last one
                     const int q = s.qdist;
-                    if (pend[1] >= 0) {
+                    const unsigned npix = sh_npix;
+                    if (npix > 0 && npix <= ST_PIXCAP && q == ST_QMAX && nx < 65536 && ny < 65536) {
+                        // the usual case: work proportional to the number of charged pixels (see
+                        // stamp_update_slot_owned): boundary slots within reach first, then the boxes of the pixels
+                        // Owners are few and scattered among the proposals (one in ~50 in a star's core), so the
+                        // proposals of a round are only judged; the owned slots / pixels go to a queue in shared memory
+                        // and are then worked off with every lane busy.
+                        // A charged pixel with no other charge within 8 pixels (most of a star's wings) owns every
+                        // slot and pixel it proposes: marked once here (top bit of its list entry), it skips the windows.
+                        for (unsigned k = tid; k < npix; k += ST_THREADS) {
+                            const int pix = pixlist[k];
+                            const int pi = pix % nx, pj = pix / nx;
+                            const int cl = max(pi - 8, 0), ch = min(pi + 8, nx - 1);
+                            bool alone = true;
+                            for (int j = max(pj - 8, 0); j <= min(pj + 8, ny - 1) && alone; ++j) {
+                                unsigned mrow = row_bits(cb, j, cl, ch);
+                                if (j == pj) mrow &= ~(1u << (pi - cl));
+                                alone = (mrow == 0u);
+                            }
+                            if (alone) pixlist[k] = pix | (int)0x80000000;
+                        }
+                        __syncthreads();
+                        for (int pass = 0; pass < 2; ++pass) {
+                            const int B = pass == 0 ? 8 : 9, BB = B * B;     // slots within reach; pixels next to those
+                            const unsigned total = npix * (unsigned)BB;
+                            unsigned idx0 = 0;
+                            while (idx0 < total) {
+                                if (tid == 0) sh_nq = 0;
+                                __syncthreads();
+                                // fill: judge one proposal per thread and round until the queue could overflow
+                                unsigned nq = 0;
+                                while (idx0 < total && nq <= ST_QCAP - ST_THREADS) {
+                                    const unsigned idx = idx0 + tid;
+                                    if (idx < total) {
+                                        const int raw = pixlist[idx / BB], c = (int)(idx % BB);
+                                        const int pix = raw & 0x7fffffff;
+                                        const bool alone = raw < 0;
+                                        const int pi = pix % nx, pj = pix / nx;
+                                        const int x = pi - (pass == 0 ? 3 : 4) + c % B, y = pj - (pass == 0 ? 3 : 4) + c / B;
+                                        bool own = false;
+                                        if (pass == 0) {
+                                            if (x >= 0 && y >= 0 && x <= nx && y <= ny)
+                                                own = alone || stamp_slot_owner(stamp_slot_window(s, cb, x, y), x, y, pi, pj);
+                                        } else if (x >= 0 && y >= 0 && x < nx && y < ny) {
+                                            own = alone || stamp_owns_pixel(s, cb, x, y, pi, pj);
+                                        }
+                                        if (own) queue[atomicAdd(&sh_nq, 1u)] = ((unsigned)y << 16) | (unsigned)x;
+                                    }
+                                    idx0 += ST_THREADS;
+                                    __syncthreads();
+                                    nq = sh_nq;
+                                }
+                                // drain: every lane takes owned slots / pixels
+                                for (unsigned k = tid; k < nq; k += ST_THREADS) {
+                                    const int x = (int)(queue[k] & 0xffffu), y = (int)(queue[k] >> 16);
+                                    if (pass == 0) stamp_slot_apply<NV>(s, KH, KV, stamp_slot_window(s, cb, x, y), x, y);
+                                    else stamp_bounds_pixel<NV>(s, x, y);
+                                }
+                                __syncthreads();
+                            }
+                            ST_PROF(4 + pass)
+                        }
+                        for (unsigned k = tid; k < npix; k += ST_THREADS) {
+                            const int pix = pixlist[k] & 0x7fffffff;
+                            const int x = pix % nx, y = pix / nx;
+                            if (f32) stamp_fold_delta<float>(s, x, y);
+                            else stamp_fold_delta<double>(s, x, y);
+                            atomicAnd(&cbits[y * wpr + (x >> 5)], ~(1u << (x & 31)));
+                        }
+                        __syncthreads();
+                        ST_PROF(6)
+                    } else if (pend[1] >= 0) {
+                        // more charged pixels than the list holds: scan the box of the pending charge
                         const int sx0 = max(pend[0] - q, 0), sx1 = min(pend[1] + q + 1, nx);      // boundary slots
                         const int sy0 = max(pend[2] - q, 0), sy1 = min(pend[3] + q + 1, ny);
                         const int sw = sx1 - sx0 + 1, shh = sy1 - sy0 + 1;
@@ -367,11 +608,13 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
                                 else stamp_fold_delta<double>(s, x, y);
                             }
                         }
+                        for (int idx = tid; idx < ny * wpr; idx += ST_THREADS) cbits[idx] = 0u;
                         __syncthreads();
                     }
                     if (tid == 0) {
                         pend[0] = pend[2] = 1 << 30;
                         pend[1] = pend[3] = -1;
+                        sh_npix = 0;
                         sh_nupd++;
                     }
                     accum = 0.0;
@@ -396,6 +639,8 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
                 }
             }
         }
+        __syncthreads();
+        ST_PROF(7)
         // flux that landed on this stamp
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) my_added += __shfl_xor_sync(0xffffffffu, my_added, o);
@@ -440,6 +685,7 @@ static size_t stamp_state_bytes(int nx, int ny, int nv, int dtype_bytes, StampSl
     t.delta = take(npix * sizeof(double));
     t.target = take(npix * dtype_bytes);
     t.changed = take(npix);
+    t.cbits = take((size_t)ny * ((nx + 31) / 32) * sizeof(unsigned));  // one bit per pixel: charge since the last update
     if (sl) *sl = t;
     return off;
 }
@@ -454,6 +700,7 @@ extern "C" int b2_sensor_accumulate_stamps(b2_sensor* s, int32_t njobs, const B2
                                            int32_t full_xmin, int32_t full_ymin, int32_t full_nx, int32_t full_ny,
                                            int32_t dtype_bytes, B2AccumStats* stats, double* added_per_job) {
     B2_REQUIRE(s && jobs && njobs >= 0, "b2_sensor_accumulate_stamps: null argument");
+    B2_REQUIRE(s->ctx, "b2_sensor_accumulate_stamps: the context this sensor was created on has been destroyed");
     B2_REQUIRE(n == 0 || (x && y && flux), "b2_sensor_accumulate_stamps: null photon array (device pointers expected)");
     B2_REQUIRE((dxdz == nullptr) == (dydz == nullptr), "b2_sensor_accumulate_stamps: dxdz and dydz go together");
     B2_REQUIRE(!wl || s->d.nabs > 0, "b2_sensor_accumulate_stamps: wavelengths given but the sensor has no absorption table");
@@ -489,20 +736,30 @@ extern "C" int b2_sensor_accumulate_stamps(b2_sensor* s, int32_t njobs, const B2
     const size_t jobs_b = up256((size_t)njobs * sizeof(B2StampJob)), slots_b = up256((size_t)njobs * sizeof(StampSlot));
     const size_t order_b = up256((size_t)njobs * sizeof(int)), added_b = up256((size_t)njobs * sizeof(double));
     const size_t slow_b = up256((size_t)grid_max * ST_TILE * sizeof(SlowRec));
-    if (b2_scratch_reserve(ctx, s->stamp_meta, jobs_b + slots_b + order_b + added_b + slow_b + 512)) return 1;
+    const size_t pix_b = up256((size_t)grid_max * ST_PIXCAP * sizeof(int));
+    if (b2_scratch_reserve(ctx, s->stamp_meta, jobs_b + slots_b + order_b + added_b + slow_b + pix_b + 512)) return 1;
     unsigned char* m = (unsigned char*)s->stamp_meta.ptr;
     B2StampJob* djobs = (B2StampJob*)m;
     StampSlot* dslots = (StampSlot*)(m + jobs_b);
     int* dorder = (int*)(m + jobs_b + slots_b);
     double* dadded_job = (double*)(m + jobs_b + slots_b + order_b);
     SlowRec* dslow = (SlowRec*)(m + jobs_b + slots_b + order_b + added_b);
-    int* dnext = (int*)(m + jobs_b + slots_b + order_b + added_b + slow_b);
+    int* dpix = (int*)(m + jobs_b + slots_b + order_b + added_b + slow_b);
+    int* dnext = (int*)(m + jobs_b + slots_b + order_b + added_b + slow_b + pix_b);
+    unsigned long long* dprof = getenv("B2_STAMP_PROFILE") ? (unsigned long long*)(dnext + 16) : nullptr;
+    if (dprof) B2_CUDA(cudaMemsetAsync(dprof, 0, 8 * sizeof(unsigned long long), st));
     B2_CUDA(cudaMemsetAsync(s->dstats, 0, ST_N * sizeof(unsigned long long) + 64, st));
     B2_CUDA(cudaMemcpyAsync(djobs, jobs, (size_t)njobs * sizeof(B2StampJob), cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaMemcpyAsync(dorder, order.data(), (size_t)njobs * sizeof(int), cudaMemcpyHostToDevice, st));
     const StampPhotons ph{x, y, dxdz, dydz, wl, flux, rand4, n, seed, offset};
     const FullImage full{full_pixels, full_xmin, full_ymin, full_nx, full_ny, dtype_bytes};
-    const size_t smem = (size_t)s->d.nx9 * s->d.ny9 * (2 * nv + 2) * sizeof(float2);
+    const size_t smem_k = (size_t)s->d.nx9 * s->d.ny9 * (2 * nv + 2) * sizeof(float2);
+    // occupancy bitmap of the stamp in flight in shared memory: two blocks per SM share ~220 KB
+    size_t bit_words = 0;
+    for (int j = 0; j < njobs; ++j)
+        if (!jobs[j].plain) bit_words = std::max(bit_words, (size_t)((jobs[j].nx + 31) / 32) * jobs[j].ny);
+    bit_words = std::min(bit_words, (size_t)(80 * 1024) / sizeof(unsigned));
+    const size_t smem = smem_k + bit_words * sizeof(unsigned);
     // waves: consecutive jobs of the sorted list whose stamp states fit the arena together
     int w0 = 0;
     bool slots_sent = false;
@@ -513,7 +770,7 @@ extern "C" int b2_sensor_accumulate_stamps(b2_sensor* s, int32_t njobs, const B2
         while (w1 < njobs && (w1 == w0 || used + need[order[w1]] <= budget)) {
             const int j = order[w1];
             StampSlot t = slots[j];
-            t.H += used; t.V += used; t.inner += used; t.outer += used; t.delta += used; t.target += used; t.changed += used;
+            t.H += used; t.V += used; t.inner += used; t.outer += used; t.delta += used; t.target += used; t.changed += used; t.cbits += used;
             abs_slots[j] = t;
             used += need[j];
             ++w1;
@@ -529,21 +786,28 @@ extern "C" int b2_sensor_accumulate_stamps(b2_sensor* s, int32_t njobs, const B2
         {
             B2_TIMED("k_stamp_jobs", st);
             if (nv == 4) {
-                if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(k_stamp_jobs<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                B2_CUDA(cudaFuncSetAttribute(k_stamp_jobs<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 k_stamp_jobs<4><<<grid, ST_THREADS, smem, st>>>(s->d, djobs, dslots, dorder + w0, nw, dnext,
                                                                (unsigned char*)s->stamp_arena.ptr, ph, s->cfg.nrecalc, ocx, ocy,
-                                                               full, s->dstats, s->dadded, dadded_job, dslow);
+                                                               full, s->dstats, s->dadded, dadded_job, dslow, dpix, (int)bit_words, dprof);
             } else {
-                if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(k_stamp_jobs<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                B2_CUDA(cudaFuncSetAttribute(k_stamp_jobs<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 k_stamp_jobs<8><<<grid, ST_THREADS, smem, st>>>(s->d, djobs, dslots, dorder + w0, nw, dnext,
                                                                (unsigned char*)s->stamp_arena.ptr, ph, s->cfg.nrecalc, ocx, ocy,
-                                                               full, s->dstats, s->dadded, dadded_job, dslow);
+                                                               full, s->dstats, s->dadded, dadded_job, dslow, dpix, (int)bit_words, dprof);
             }
             B2_CHECK_LAUNCH();
         }
         w0 = w1;
     }
     (void)slots_sent;
+    if (dprof) {
+        unsigned long long hp[8];
+        B2_CUDA(cudaMemcpyAsync(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaStreamSynchronize(st));
+        fprintf(stderr, "k_stamp_jobs cycles of thread 0 summed over blocks: setup %llu cut %llu deposit %llu slow %llu slots %llu boxes %llu fold %llu final %llu\n",
+                hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6], hp[7]);
+    }
     // the sensor's own bound image (if any) is untouched; a later accumulate(resume=True) on it stays valid
     if (stats || added_per_job) {
         unsigned long long h[ST_N];

@@ -10,11 +10,14 @@ boundaries are recomputed every ``nrecalc`` electrons; objects below ``max_flux_
 optics nor silicon (stamp.py:534-537,555-556); finally ``full_image[bounds] += stamp[bounds]``
 (lsst_image.py:359-368).
 
-Here the same sequence runs on HBM-resident data: stage 1 generates the object's photons
-(``b2_stage1_photons``), the samplers + fused optics kernel run on them, the sensor is re-bound to a
-device-only stamp (``bind_stamp``: the per-image arrays are reused, no allocation per object) and the stamp
-is added to the device-resident full image.  Photons stay in full-image coordinates throughout, which is
-what the reference's shift / unshift pair amounts to.  FFT-rendered objects (stamp.py:467-513) are out of
+Here the same sequence runs on HBM-resident data, for all objects at once (``build``): stage 1 generates the
+photons of every object in one launch (``b2_stage1_photons``), the samplers + fused optics kernel run on the
+photons of all non-faint objects, and ``b2_sensor_accumulate_stamps`` gives every object its own zero stamp
+with fresh boundaries, accumulates its photons at the ``nrecalc`` cadence inside the stamp -- the chunk loop
+runs inside the kernel, one thread block per stamp -- and adds the stamp to the device-resident full image.
+``build_per_object`` is the host-driven loop (one bind / optics / accumulate per object) the batched form
+replaced; both draw identical stamps from identical photons (tests/test_gpu_stamps.py).  Photons stay in
+full-image coordinates throughout, which is what the reference's shift / unshift pair amounts to.  FFT-rendered objects (stamp.py:467-513) are out of
 scope: objects brighter than ``fft_flux_limit`` are still photon shot.
 """
 from __future__ import annotations
@@ -63,9 +66,79 @@ class ClassicImageBuilder:
         icx, icy = int(np.floor(r["x"] + 0.5)), int(np.floor(r["y"] + 0.5))
         return icx - size // 2, icy - size // 2, size
 
+    #: photons per group of objects handed to the device at once (9 float64 arrays each)
+    GROUP_PHOTONS = 1 << 27
+
     def build(self, image: Image, nominal_flux, phot_flux=None, rng=None):
-        """Draw every object onto ``image`` (added in place).  ``phot_flux``: Poisson realisation of the
-        fluxes (stamp.py:194-196), drawn here from ``rng`` if not given.  Returns a record of counts."""
+        """Draw every object onto ``image`` (added in place), all objects of a group in three launches.
+        ``phot_flux``: Poisson realisation of the fluxes (stamp.py:194-196), drawn here from ``rng`` if not
+        given.  Returns a record of counts."""
+        import torch
+
+        ctx, sensor = self.ctx, self.sensor
+        dev = "cuda:%d" % ctx.device
+        gen = rng if isinstance(rng, np.random.Generator) else np.random.default_rng(rng)
+        nominal_flux = np.asarray(nominal_flux, dtype=np.float64)
+        if phot_flux is None:
+            phot_flux = gen.poisson(nominal_flux)
+        phot_flux = np.asarray(phot_flux, dtype=np.int64)
+        arr = image.array
+        X0, Y0 = image.xmin, image.ymin
+        ny, nx = arr.shape
+        t0 = time.perf_counter()
+        # host: which objects are drawn, on which stamps (SkipThisObject / off-image stamps, lsst_image.py:361-366)
+        bright, faint = [], []
+        n_skipped = 0
+        for j in range(self.rows.size):
+            n = int(phot_flux[j])
+            if n == 0:
+                n_skipped += 1
+                continue
+            xmin, ymin, size = self.stamp_bounds(j, float(nominal_flux[j]))
+            if max(xmin, X0) >= min(xmin + size, X0 + nx) or max(ymin, Y0) >= min(ymin + size, Y0 + ny):
+                n_skipped += 1
+                continue
+            (faint if nominal_flux[j] < self.max_flux_simple else bright).append((j, n, xmin, ymin, size))
+        t_host = time.perf_counter() - t0
+        full = torch.as_tensor(arr, device=dev).clone()
+        n_photons = 0
+        # groups: bright objects first inside a group, so that the optics run on one contiguous range
+        todo = [(o, False) for o in bright] + [(o, True) for o in faint]
+        todo.sort(key=lambda t: t[0][0])
+        k = 0
+        while k < len(todo):
+            grp, tot = [], 0
+            while k < len(todo) and (not grp or tot + todo[k][0][1] <= self.GROUP_PHOTONS):
+                grp.append(todo[k])
+                tot += todo[k][0][1]
+                k += 1
+            grp.sort(key=lambda t: t[1])  # stable: non-faint first
+            sel = np.array([o[0] for o, _ in grp], dtype=np.int64)
+            counts = np.array([o[1] for o, _ in grp], dtype=np.int64)
+            n_opt = int(sum(o[1] for o, f in grp if not f))
+            dp = DevicePhotons(tot, device=dev)
+            self.stage1.shoot(dp, counts, seed=self.seed, photon_offset=n_photons, select=sel)
+            if self.stage1.cdf is None:
+                dp.wavelength.fill_(self.wlen_eff)  # monochromatic at the band's effective wavelength
+            if n_opt:
+                self.pool.trace(dp, n_opt)
+            dp._has.update(dxdz=True, dydz=True)
+            jobs, p0 = [], 0
+            for (j, n, xmin, ymin, size), is_faint in grp:
+                jobs.append((p0, n, xmin, ymin, size, size, int(is_faint)))
+                p0 += n
+            if n_opt < tot:  # faint objects carry no slopes: the plain jobs do not read them
+                dp.dxdz[n_opt:].zero_()
+                dp.dydz[n_opt:].zero_()
+            sensor.accumulate_stamps(jobs, dp, full, X0, Y0, want_stats=False)
+            n_photons += tot
+        arr[:, :] = full.cpu().numpy()
+        self.stats = {"phot": len(bright), "faint": len(faint), "skipped": n_skipped, "photons": n_photons,
+                      "seconds": time.perf_counter() - t0, "host_setup_seconds": t_host}
+        return self.stats
+
+    def build_per_object(self, image: Image, nominal_flux, phot_flux=None, rng=None):
+        """The same drawing, driven object by object from the host (one bind / optics / accumulate per object)."""
         import torch
 
         ctx, sensor = self.ctx, self.sensor

@@ -288,6 +288,22 @@ class PhotonPool:
         self.opt.index_ratio = float(index_ratio)
         self.opt.seed = self.seed
 
+    def trace(self, dp: DevicePhotons, n: Optional[int] = None, want_stats=False):
+        """Samplers + optics only, on the first ``n`` photons of the pool (all by default): the photons are
+        left as the op list leaves them for the sensor (x, y, dxdz, dydz, flux)."""
+        n = dp.n if n is None else int(n)
+        f = (lambda a: a[:n]) if n != dp.n else (lambda a: a)
+        self.ctx.sample_time_pupil(f(dp.time), f(dp.pupil_u), f(dp.pupil_v), self.t0, self.exptime, self.r_inner,
+                                   self.r_outer, self.seed, self.offset)
+        dp._has.update(pupil_u=True, pupil_v=True, time=True)
+        self.opt.photon_offset = self.offset
+        stats = self.ctx.rubin_optics(f(dp.x), f(dp.y), f(dp.dxdz), f(dp.dydz), f(dp.flux), f(dp.wavelength),
+                                      f(dp.pupil_u), f(dp.pupil_v), f(dp.time), options=self.opt,
+                                      want_stats=want_stats)
+        dp._has.update(dxdz=True, dydz=True)
+        self.offset += n
+        return stats
+
     def process(self, dp: DevicePhotons, image, resume: bool, recalc: bool, sample=True, want_stats=False,
                 fused=None, write_back=False, prebound=False):
         """Run the chain on a device pool and accumulate onto the sensor's bound image.

@@ -112,3 +112,42 @@ def test_classic_brighter_fatter_acts_within_the_stamp():
     print({k: v[0] for k, v in widths.items()})
     assert widths["bf"][0] > widths["off"][0] * 1.01
     assert abs(widths["bf_chunks"][0] / widths["bf"][0] - 1.0) < 0.005
+
+
+def test_batched_build_matches_the_per_object_loop():
+    """``build`` (all objects in three launches, chunk loop on the device) against ``build_per_object`` (host-driven
+    bind / optics / accumulate per object).  The two seed their photons differently, so the comparison is
+    statistical here (per-object electron counts and centroids); that a stamp is bit-identical for identical
+    photons is tests/test_gpu_stamps.py."""
+    from imsim_b200.flat import wavelength_cdf
+    from imsim_b200.lsst_image import ClassicImageBuilder
+    from imsim_b200.sensor import Image
+    from imsim_b200.stage1 import ObjectTable
+
+    ctx, det, sensor, psf = _runner()
+    tab = ObjectTable()
+    xs = [800.0, 1500.0, 2300.0, 3100.0, 3900.0, 4090.0]
+    ys = [700.0, 1600.0, 2400.0, 3300.0, 500.0, 3990.0]
+    tab.add_points(xs, ys, [1] * 6)
+    rows, _ = tab.build()
+    flux = np.array([200000, 90, 150000, 40000, 30, 120000], dtype=np.float64)
+    wave = np.linspace(550, 690, 15)
+    cdf, cw = wavelength_cdf(wave, np.ones_like(wave))
+    out = {}
+    for name in ("build", "build_per_object"):
+        b = ClassicImageBuilder(ctx, sensor, rows, None, None, cdf[None], cw[None], psf=psf, maxN=100000, seed=3)
+        image = Image(np.zeros((det.ny, det.nx), np.float32), 0, 0)
+        st = getattr(b, name)(image, flux, phot_flux=flux.astype(np.int64))
+        assert (st["phot"], st["faint"], st["photons"]) == (4, 2, int(flux.sum()))
+        a = image.array.astype(np.float64)
+        per = []
+        for j in range(rows.size):
+            x0, y0, s = b.stamp_bounds(j, flux[j])
+            sub = a[max(y0, 0):y0 + s, max(x0, 0):x0 + s]
+            gy, gx = np.mgrid[max(y0, 0):max(y0, 0) + sub.shape[0], max(x0, 0):max(x0, 0) + sub.shape[1]]
+            per.append((sub.sum(), (sub * gx).sum() / sub.sum(), (sub * gy).sum() / sub.sum()))
+        out[name] = np.array(per)
+    for j in range(rows.size):
+        e0, e1 = out["build"][j, 0], out["build_per_object"][j, 0]
+        assert abs(e0 - e1) <= 5.0 * np.sqrt(max(flux[j] - min(e0, e1), 1.0)) + 1.0, (j, e0, e1)  # lost-photon noise
+        assert np.all(np.abs(out["build"][j, 1:] - out["build_per_object"][j, 1:]) < 0.05 + 12.0 / np.sqrt(flux[j]))

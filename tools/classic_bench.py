@@ -41,13 +41,21 @@ seds = [wavelength_cdf(wave, 1.0 + 0.8 * np.sin(wave / (15.0 + 5 * k))) for k in
 psf = AtmosphericPSF(1.2, 0.7, "r", rng=1, device="cuda:0")
 b = ClassicImageBuilder(ctx, sensor, rows, cat.radial_tables(), cat.sersic_n, np.array([c for c, _ in seds]),
                         np.array([w for _, w in seds]), psf=psf, seed=2)
-for rep in range(2):
+import json  # noqa: E402
+
+res = {}
+for which, reps in (("build", 3), ("build_per_object", 1)):
+  for rep in range(reps):
     image = Image(np.zeros((det.ny, det.nx), np.float32), 0, 0)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    st = b.build(image, flux, phot_flux=flux.astype(np.int64))
+    st = getattr(b, which)(image, flux, phot_flux=flux.astype(np.int64))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    print("classic pipeline: %d catalogue rows (%d phot, %d faint), %d photons: %.2f s = %.3e photons/s, %.2f ms / object; "
+    res[which] = {"seconds": dt, "photons_per_s": st["photons"] / dt, "host_setup_s": st.get("host_setup_seconds"),
+                  "electrons": float(image.array.sum(dtype=np.float64)), "objects": int(rows.size),
+                  "photons": int(st["photons"])}
+    print(which, "classic pipeline: %d catalogue rows (%d phot, %d faint), %d photons: %.2f s = %.3e photons/s, %.2f ms / object; "
           "electrons %.4e" % (rows.size, st["phot"], st["faint"], st["photons"], dt, st["photons"] / dt,
-                              1e3 * dt / rows.size, image.array.sum(dtype=np.float64)))
+                              1e3 * dt / rows.size, image.array.sum(dtype=np.float64)), "host set-up %s s" % st.get("host_setup_seconds"))
+print(json.dumps({"classic_bench": res}))
