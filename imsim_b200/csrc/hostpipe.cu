@@ -214,3 +214,74 @@ int b2_pipe_run(b2_ctx* ctx, int64_t n, int nin, const double* const* hin, doubl
     for (int i = 0; i < 2; ++i) B2_CUDA(cudaStreamSynchronize(p.st[i]));
     return 0;
 }
+
+
+// Pooled upload: the photon arrays of many stamps (imsim/photon_pooling.py:177-192 merges them on the host with one
+// memcpy per stamp and field) go straight from the stamps' own pageable arrays into one device array per field --
+// the merge happens inside the pinned ring: the copy threads gather the segments that fall into a chunk while the
+// copy engine moves the previous chunk.  seg: nfields * nseg host pointers, field-major; seg_len: photons per segment;
+// dst: one device array per field, each holding sum(seg_len) doubles.  Complete when it returns.
+extern "C" int b2_photons_upload(b2_ctx* ctx, int32_t nfields, int64_t nseg, const double* const* seg,
+                                 const int64_t* seg_len, double* const* dst) {
+    B2_REQUIRE(ctx && seg && seg_len && dst && nfields > 0 && nfields <= 16 && nseg >= 0, "b2_photons_upload: bad argument");
+    std::vector<int64_t> start((size_t)nseg + 1, 0);
+    for (int64_t k = 0; k < nseg; ++k) {
+        B2_REQUIRE(seg_len[k] >= 0, "b2_photons_upload: negative segment length");
+        start[k + 1] = start[k] + seg_len[k];
+    }
+    const int64_t n = start[nseg];
+    if (n == 0) return 0;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->pipe) ctx->pipe = new b2_hostpipe();
+    b2_hostpipe& p = *ctx->pipe;
+    if (!p.st[0]) {
+        for (int i = 0; i < 2; ++i) B2_CUDA(cudaStreamCreateWithFlags(&p.st[i], cudaStreamNonBlocking));
+        for (int i = 0; i < NSLOT; ++i) B2_CUDA(cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming));
+        B2_CUDA(cudaEventCreateWithFlags(&p.entry, cudaEventDisableTiming));
+    }
+    const int64_t chunk = std::min<int64_t>(n, env_long("B2_PIPE_CHUNK", 1L << 19));
+    const size_t slot_bytes = (size_t)nfields * (size_t)chunk * sizeof(double);
+    for (int i = 0; i < 2; ++i) B2_CUDA(cudaStreamSynchronize(p.st[i]));  // copies of an earlier call still read the ring
+    if (p.pin_bytes < NSLOT * slot_bytes) {
+        if (p.pin) B2_CUDA(cudaFreeHost(p.pin));
+        p.pin = nullptr;
+        p.pin_bytes = 0;
+        B2_CUDA(cudaHostAlloc(&p.pin, NSLOT * slot_bytes, cudaHostAllocDefault));
+        p.pin_bytes = NSLOT * slot_bytes;
+    }
+    auto slot = [&](int s, int f) { return (char*)p.pin + (size_t)s * slot_bytes + (size_t)f * chunk * sizeof(double); };
+    B2_CUDA(cudaEventRecord(p.entry, ctx->stream));
+    for (int i = 0; i < 2; ++i) B2_CUDA(cudaStreamWaitEvent(p.st[i], p.entry, 0));
+    CopyPool& cp = pool();
+    std::vector<Piece> pieces;
+    const int64_t nch = (n + chunk - 1) / chunk;
+    int64_t sfirst = 0;  // first segment that reaches into the current chunk
+    for (int64_t k = 0; k < nch; ++k) {
+        const int s = (int)(k % NSLOT);
+        const int64_t off = k * chunk, cnt = std::min(chunk, n - off);
+        if (k >= NSLOT) B2_CUDA(cudaEventSynchronize(p.done[s]));  // the copy that last read this slot
+        while (sfirst < nseg && start[sfirst + 1] <= off) ++sfirst;
+        pieces.clear();
+        for (int64_t g = sfirst; g < nseg && start[g] < off + cnt; ++g) {
+            const int64_t a = std::max(start[g], off), b = std::min(start[g + 1], off + cnt);
+            if (b <= a) continue;
+            for (int f = 0; f < nfields; ++f) {
+                const char* src = (const char*)(seg[(size_t)f * nseg + g] + (a - start[g]));
+                char* dstp = slot(s, f) + (size_t)(a - off) * sizeof(double);
+                const size_t bytes = (size_t)(b - a) * sizeof(double);
+                for (size_t o = 0; o < bytes; o += PIECE) pieces.push_back(Piece{dstp + o, src + o, std::min(PIECE, bytes - o)});
+            }
+        }
+        cp.run(pieces);
+        cudaStream_t st = p.st[k & 1];
+        for (int f = 0; f < nfields; ++f)
+            B2_CUDA(cudaMemcpyAsync(dst[f] + off, slot(s, f), (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+        B2_CUDA(cudaEventRecord(p.done[s], st));
+    }
+    // later work on the context's stream sees the uploaded arrays; the host does not wait for the copies
+    for (int i = 0; i < 2; ++i) {
+        B2_CUDA(cudaEventRecord(p.entry, p.st[i]));
+        B2_CUDA(cudaStreamWaitEvent(ctx->stream, p.entry, 0));
+    }
+    return 0;
+}

@@ -14,10 +14,16 @@ It re-registers, under the reference's own names,
 * input ``tree_rings`` and value types ``TreeRingCenter`` / ``TreeRingFunc``
   (imsim/treerings.py:220-243).
 
-``LSST_PhotonPoolingImage`` and ``LSST_Photons`` stay imSim's own builders: with the
-ops and the sensor swapped, their hot loop (imsim/photon_pooling.py:141-160) already
-runs on the device; ``B200SiliconSensor`` subclasses ``galsim.SiliconSensor`` so the
-``isinstance`` test at photon_pooling.py:209 keeps passing ``recalc``.
+* image type ``LSST_PhotonPoolingImage`` (imsim/photon_pooling.py:469): imSim's builder with ``buildImage``
+  re-stated so that the pooled hot loop (photon_pooling.py:141-160) keeps ``full_image``, the sensor state and
+  the photon pool in HBM -- the stamps' photon arrays go straight from GalSim's shooters into the device pool,
+  one fused launch per sub-batch, the image comes back at checkpoints and at the end.  Object loading,
+  partitioning, FFT objects, checkpoint files and the faint-object rule stay imSim's own code (inherited),
+* stamp type ``LSST_Photons`` (imsim/stamp.py:747) and image type ``LSST_Flat`` (imsim/flat.py:300): imSim's
+  builders, re-registered so that a config naming them gets the device sensor behind them.
+
+``B200SiliconSensor`` subclasses ``galsim.SiliconSensor`` so the ``isinstance`` test at
+photon_pooling.py:209 keeps passing ``recalc`` on the host route as well.
 
 GalSim, batoid and the LSST stack are not available in the build container: this
 module is import-guarded and UNTESTED there.
@@ -25,12 +31,14 @@ module is import-guarded and UNTESTED there.
 from __future__ import annotations
 
 import galsim
+import numpy as np
 from galsim.config import (GetAllParams, GetInputObj, InputLoader, PhotonOpBuilder, RegisterInputType,
                            RegisterPhotonOpType, RegisterValueType)
 from galsim.config.util import get_cls_params
 
 from . import photon_ops as _ops
 from .diffraction import RUBIN_LATITUDE
+from .photon_pooling import PooledDevicePath
 from .sensor import SiliconSensor as _B200Sensor
 from .treerings import TreeRings
 
@@ -38,7 +46,8 @@ _TYPES = {"CelestialCoord": galsim.CelestialCoord, "Angle": galsim.Angle, "Posit
 
 
 def _resolve(params):
-    return {k: _TYPES.get(v, v) if isinstance(v, str) else v for k, v in params.items()}
+    """type names -> the types of the GalSim that is imported now (also on a re-import of this module)"""
+    return {k: _TYPES.get(v if isinstance(v, str) else getattr(v, "__name__", None), v) for k, v in params.items()}
 
 
 for _cls in (_ops.RubinOptics, _ops.RubinDiffractionOptics, _ops.RubinDiffraction):
@@ -154,3 +163,143 @@ _tree_rings_with_data_dir._opt_params = TreeRings._opt_params
 RegisterInputType("tree_rings", InputLoader(_tree_rings_with_data_dir, takes_logger=True))
 RegisterValueType("TreeRingCenter", TreeRingCenter, [galsim.PositionD], input_type="tree_rings")
 RegisterValueType("TreeRingFunc", TreeRingFunc, [object], input_type="tree_rings")
+
+
+# ---------------------------------------------------------------------------
+# LSST_PhotonPoolingImage with the pooled loop on the device
+# ---------------------------------------------------------------------------
+from imsim.photon_pooling import LSST_PhotonPoolingImageBuilder as _ImsimPoolingBuilder  # noqa: E402
+
+
+class B200PhotonPoolingImageBuilder(_ImsimPoolingBuilder):
+    """``LSST_PhotonPoolingImage``.  ``setup``, ``addNoise``, object loading / partitioning / batching, stamp
+    building and checkpoint I/O are imSim's (inherited); ``buildImage`` follows imsim/photon_pooling.py:29-174 step
+    by step but hands the per-sub-batch work -- merge, photon ops, ``accumulate_photons`` -- to
+    ``PooledDevicePath`` whenever the configured op list and sensor are the ones it knows, and to the inherited
+    host code otherwise."""
+
+    #: set by buildImage: "device" or "host" (which route the last image took), photons pooled, bytes uploaded
+    last_route = None
+
+    def _draw_fft_batches(self, base, logger, fft_objects, full_image, book, chk_name, image_num):
+        """FFT-rendered objects, batch by batch on the host (photon_pooling.py:76-114)."""
+        nbatch = max(min(self.nbatch_fft, len(fft_objects)), 1)
+        for batch_num, batch in enumerate(self.make_batches(fft_objects, nbatch), start=1):
+            if nbatch > 1:
+                logger.warning("Start FFT batch %d/%d with %d objects", batch_num, nbatch, len(batch))
+            stamps, current_vars = self.build_stamps(base, logger, batch)
+            base['index_key'] = 'image_num'
+            for obj, stamp in zip(batch, stamps):
+                overlap = self.stamp_bounds(stamp, full_image.bounds)
+                if overlap is None:
+                    continue
+                full_image[overlap] += stamp[overlap]
+                book["obj_nums"].append(obj.index)
+            noisy = [k for k, v in enumerate(current_vars) if v != 0]
+            book["stamps"].extend(stamps[k] for k in noisy)
+            book["vars"].extend(current_vars[k] for k in noisy)
+            if self.checkpoint is not None:
+                self.save_checkpoint(self.checkpoint, chk_name, base, full_image, book["stamps"], book["vars"],
+                                     book["obj_nums"], book["photon_batch"])
+                logger.warning('File %d: Completed batch %d, and wrote checkpoint data to %s',
+                               base.get('file_num', 0), batch_num, self.checkpoint.file_name)
+
+    def buildImage(self, config, base, image_num, _obj_num, logger):
+        self._set_config_image_pos(config, base)
+        book = {"stamps": [], "vars": [], "obj_nums": [], "photon_batch": 0}
+        full_image = None
+        chk_name = "buildImage_photonpooling_" + self.det_name
+        if self.checkpoint is not None:
+            (full_image, book["vars"], book["stamps"], book["obj_nums"],
+             book["photon_batch"]) = self.load_checkpoint(self.checkpoint, chk_name, base, logger)
+        todo = sorted(frozenset(range(self.nobjects)) - frozenset(book["obj_nums"]))
+        if full_image is None:
+            full_image = self._create_full_image(config, base)
+
+        sensor = base.get('sensor', None)
+        rng = galsim.config.GetRNG(config, base, logger, "LSST_Silicon")
+        if sensor is not None:
+            sensor.updateRNG(rng)
+
+        fft_objects, phot_objects, faint_objects = self.partition_objects(
+            self.load_objects(todo, config, base, logger), self.nbatch)
+        logger.info("Found %d FFT objects, %d photon shooting objects and %d faint objects", len(fft_objects),
+                    len(phot_objects), len(faint_objects))
+        if self.checkpoint is not None:
+            if not fft_objects:
+                logger.warning('All FFT objects already rendered for this image.')
+            else:
+                logger.warning("%d objects already rendered", len(book["obj_nums"]))
+        self._draw_fft_batches(base, logger, fft_objects, full_image, book, chk_name, image_num)
+
+        # photon batches: nbatch clipped to the bright objects, nsubbatch to the shortest batch (Q9)
+        nbatch = max(min(self.nbatch, len(phot_objects)), 1)
+        batches = self.make_photon_batches(config, base, logger, phot_objects, faint_objects, nbatch)
+        done = book["photon_batch"]
+        if done > 0:
+            logger.warning("Photon batches [0, %d) / %d already rendered - skipping", done, nbatch)
+            batches = batches[done:]
+        nsub = max(min(self.nsubbatch, min((len(b) for b in batches), default=0)), 1)
+        logger.warning("Splitting photon batches into %d subbatches.", nsub)
+
+        base["image_pos"] = None
+        base["stamp_center"] = None
+        ops_cfg = {"photon_ops": base.get("stamp", {}).get("photon_ops", [])}
+        photon_ops = galsim.config.BuildPhotonOps(ops_cfg, 'photon_ops', base, logger)
+        local_wcs = base['wcs'].local(full_image.true_center)
+        if sensor is None:
+            sensor = galsim.Sensor()
+
+        path = None
+        if full_image.dtype in (np.float32, np.float64) and any(batches):
+            path = PooledDevicePath.recognise(photon_ops, sensor, local_wcs)
+        self.last_route = "host" if path is None else "device"
+        if path is not None:
+            path.begin(full_image)
+        for batch_num, batch in enumerate(batches, start=done):
+            if not batch:
+                continue
+            if nbatch > 1:
+                logger.warning("Starting photon batch %d/%d.", batch_num + 1, nbatch)
+            base['index_key'] = 'image_num'
+            for sub_num, sub in enumerate(self.make_photon_subbatches(batch, nsub)):
+                stamps, current_vars = self.build_stamps(base, logger, sub)
+                resume = batch_num > done or sub_num > 0
+                recalc = sub_num == 0
+                if path is not None:
+                    path.add([stamp.photons for stamp in stamps])
+                    del stamps
+                    path.step(resume=resume, recalc=recalc)
+                else:
+                    photons = self.merge_photon_arrays(stamps)
+                    del stamps
+                    for op in photon_ops:
+                        op.applyTo(photons, local_wcs, rng)
+                    self.accumulate_photons(photons, full_image, sensor, resume=resume, recalc=recalc)
+                    del photons
+                book["vars"].extend(v for v in current_vars if v != 0)
+            if self.checkpoint is not None:
+                if path is not None:
+                    path.read_back(full_image)
+                self.save_checkpoint(self.checkpoint, chk_name, base, full_image, book["stamps"], book["vars"],
+                                     book["obj_nums"], batch_num + 1)
+        if path is not None:
+            path.read_back(full_image)
+            self.last_pooled_photons, self.last_h2d_bytes = path.photons, path.h2d_bytes
+
+        current_var = galsim.config.FlattenNoiseVariance(base, full_image, book["stamps"], tuple(book["vars"]), logger)
+        return full_image, current_var
+
+
+galsim.config.RegisterImageType('LSST_PhotonPoolingImage', B200PhotonPoolingImageBuilder())
+
+# LSST_Photons / LSST_Flat: imSim's own builders behind the device sensor (re-registered so that listing this
+# module alone in ``modules:`` still provides every type name of the path)
+try:
+    from imsim.flat import LSST_FlatBuilder as _ImsimFlatBuilder  # noqa: E402
+    from imsim.stamp import LSST_PhotonsBuilder as _ImsimPhotonsBuilder  # noqa: E402
+
+    galsim.config.RegisterStampType('LSST_Photons', _ImsimPhotonsBuilder())
+    galsim.config.RegisterImageType('LSST_Flat', _ImsimFlatBuilder())
+except ImportError:  # a stripped-down imsim: the two types stay whatever ``imsim`` registered
+    pass

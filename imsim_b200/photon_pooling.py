@@ -412,3 +412,137 @@ class PhotonPool:
         copied.synchronize()
         arr[...] = host_img.numpy()
         return h2d, d2h
+
+
+# ---------------------------------------------------------------------------
+# the pooled loop of buildImage on the device, fed with GalSim's host photon arrays
+# ---------------------------------------------------------------------------
+_POOLED_CHAIN = ("TimeSampler", "PupilAnnulusSampler", "PhotonDCR", "RubinOptics", "RubinDiffractionOptics",
+                 "FocusDepth", "Refraction")
+
+
+class PooledDevicePath:
+    """What ``LSST_PhotonPoolingImageBuilder.buildImage`` does per sub-batch -- merge the stamps' photon arrays,
+    apply the pooled photon ops, ``accumulate_photons`` onto ``full_image`` (imsim/photon_pooling.py:149-160) --
+    with the image, the sensor state and the pool resident in HBM:
+
+    * ``recognise(photon_ops, sensor, local_wcs)`` accepts the op list of config/imsim-config.yaml:281-320
+      (TimeSampler, PupilAnnulusSampler, [PhotonDCR], RubinOptics | RubinDiffractionOptics, [FocusDepth], [Refraction],
+      in that order) together with a device ``SiliconSensor`` running the pooled cadence (``nrecalc == 0``) and
+      returns None for anything else -- the caller then keeps the reference's host loop;
+    * ``begin(full_image)`` uploads the image as it stands (FFT objects already drawn, a restored checkpoint);
+    * ``add(photon_arrays)`` gathers the stamps' pageable arrays into one device pool (``b2_photons_upload``: the
+      merge happens in the pinned ring, no host-side copy of the pool);
+    * ``step(resume, recalc)`` is one ``b2_pool_step``; ``read_back(full_image)`` copies the image to the host
+      (checkpoints, the return of ``buildImage``).
+    """
+
+    def __init__(self, pool: PhotonPool, sensor):
+        self.pool, self.sensor = pool, sensor
+        self.ctx = pool.ctx
+        self.dp: Optional[DevicePhotons] = None
+        self.image = None
+        self.photons = 0
+        self.h2d_bytes = 0
+
+    @classmethod
+    def recognise(cls, photon_ops, sensor, local_wcs=None, seed=None):
+        from .photon_ops import RubinDiffractionOptics, RubinOptics, set_dcr_options  # noqa: PLC0415
+        from .sensor import SiliconSensor  # noqa: PLC0415
+
+        if not isinstance(sensor, SiliconSensor) or sensor.pod.nrecalc != 0.0:
+            return None
+        names = [type(op).__name__ for op in photon_ops]
+        if any(n not in _POOLED_CHAIN for n in names):
+            return None
+        order = [_POOLED_CHAIN.index(n) for n in names]
+        if order != sorted(order) or len(set(names)) != len(names):
+            return None
+        byname = dict(zip(names, photon_ops))
+        optics = byname.get("RubinDiffractionOptics") or byname.get("RubinOptics")
+        if optics is None or not isinstance(optics, (RubinOptics, RubinDiffractionOptics)) \
+                or "TimeSampler" not in byname or "PupilAnnulusSampler" not in byname:
+            return None
+        if optics.stamp_center is not None:  # the pooled pipeline builds its ops with stamp_center None (Q2)
+            return None
+        ts, ps = byname["TimeSampler"], byname["PupilAnnulusSampler"]
+        ctx = optics._context()
+        sensor.move_to(ctx)
+        fd = byname.get("FocusDepth")
+        rf = byname.get("Refraction")
+        pool = PhotonPool(ctx, sensor, exptime=float(ts.exptime), t0=float(ts.t0), r_inner=float(ps.R_inner),
+                          r_outer=float(ps.R_outer), focus_depth=float(fd.depth) if fd is not None else 0.0,
+                          index_ratio=float(rf.index_ratio) if rf is not None else 1.0,
+                          seed=int(seed) if seed is not None else sensor._seed + 0x5DEECE66D)
+        pool.opt.do_refraction = int(rf is not None)
+        dcr = byname.get("PhotonDCR")
+        if dcr is not None:
+            if local_wcs is None:
+                return None
+            jac = local_wcs.getMatrix() if hasattr(local_wcs, "getMatrix") else np.asarray(local_wcs, float)
+            zen = getattr(dcr, "zenith_angle", None)
+            par = getattr(dcr, "parallactic_angle", None)
+            if zen is None or par is None:
+                return None
+            rad = (lambda a: float(a.rad) if hasattr(a, "rad") else float(a))
+            unit = getattr(dcr, "scale_unit", None)
+            set_dcr_options(pool.opt, float(dcr.base_wavelength), rad(zen), rad(par), jac,
+                            alpha=float(getattr(dcr, "alpha", 0.0)),
+                            scale_unit_rad=rad(unit) if unit is not None else np.pi / (180.0 * 3600.0),
+                            pressure=float(getattr(dcr, "pressure", 69.328)),
+                            temperature=float(getattr(dcr, "temperature", 293.15)),
+                            H2O_pressure=float(getattr(dcr, "H2O_pressure", 1.067)))
+        return cls(pool, sensor)
+
+    def begin(self, full_image):
+        """Bind ``full_image`` (a galsim.Image or ``sensor.Image``) on the device, pixels as they stand."""
+        self.sensor._bind(full_image)
+        self.sensor._last_image = None
+        self.image = full_image
+        self._first = True
+
+    def add(self, photon_arrays):
+        """The photons of a sub-batch: a list of (GalSim) PhotonArrays with x, y, flux and wavelengths."""
+        import ctypes as C  # noqa: PLC0415
+
+        arrays = [pa for pa in photon_arrays if pa is not None and len(pa) > 0]
+        n = int(sum(len(pa) for pa in arrays))
+        self.dp = None
+        if n == 0:
+            return 0
+        fields = ("x", "y", "flux", "wavelength")
+        for pa in arrays:
+            if not pa.hasAllocatedWavelengths():
+                raise _lib.B2Error("pooled photons need wavelengths (the stamps' WavelengthSampler assigns them)")
+        dp = DevicePhotons(n, device="cuda:%d" % self.ctx.device)
+        nseg = len(arrays)
+        ptrs = (C.c_void_p * (len(fields) * nseg))()
+        keep = []
+        for f, name in enumerate(fields):
+            for g, pa in enumerate(arrays):
+                a = np.ascontiguousarray(getattr(pa, name), dtype=np.float64)
+                keep.append(a)
+                ptrs[f * nseg + g] = a.ctypes.data
+        lens = (C.c_int64 * nseg)(*[len(pa) for pa in arrays])
+        dst = (C.c_void_p * len(fields))(*[getattr(dp, name).data_ptr() for name in fields])
+        _lib.check(_lib.load().b2_photons_upload(self.ctx.handle, len(fields), nseg, C.cast(ptrs, C.c_void_p),
+                                                 C.cast(lens, C.c_void_p), C.cast(dst, C.c_void_p)))
+        dp._has.update(wavelength=True)
+        self.dp = dp
+        self.photons += n
+        self.h2d_bytes += n * 8 * len(fields)
+        return n
+
+    def step(self, resume: bool, recalc: bool):
+        """SiliconSensor.accumulate(resume, recalc) of the uploaded pool after the pooled ops, one fused launch."""
+        if self.dp is None:
+            if not resume:  # an empty first sub-batch still initialises the image (as GalSim does)
+                from .photon_array import PhotonArray  # noqa: PLC0415
+
+                self.sensor.accumulate(PhotonArray(0), self.image, resume=False, sync_image=False, prebound=True)
+            return
+        self.pool.process(self.dp, self.image, resume=resume, recalc=recalc, fused=True, prebound=True)
+        self.dp = None
+
+    def read_back(self, full_image=None):
+        self.sensor.read_image(self.image if full_image is None else full_image)

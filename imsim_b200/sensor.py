@@ -152,7 +152,7 @@ def find_sensor_files(name: str, data_dir: Optional[str] = None):
         import galsim  # noqa: PLC0415
 
         cands.append(os.path.join(galsim.meta_data.share_dir, 'sensors', name))
-    except ImportError:
+    except (ImportError, AttributeError):
         pass
     cands.append(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data', name))
     for c in cands:
@@ -241,14 +241,29 @@ class SiliconSensor:
         self.ctx = context if context is not None else OpticsContext(device=device, stream=stream)
         self._lib = _lib.load()
         self._h = C.c_void_p()
+        self._create_handle()
+        self.last_stats = None
+
+    def _create_handle(self):
+        tr = self._tr
         tr_r = tr[0].ctypes.data if tr is not None else None
         tr_f = tr[1].ctypes.data if tr is not None else None
         tr_y2 = tr[2].ctypes.data if (tr is not None and tr[2] is not None) else None
-        _lib.check(self._lib.b2_sensor_create(self.ctx.handle, C.byref(pod), self.vertex_data.ctypes.data, tr_r, tr_f,
-                                              tr_y2, self.abs_wave.ctypes.data, self.abs_len.ctypes.data,
+        _lib.check(self._lib.b2_sensor_create(self.ctx.handle, C.byref(self.pod), self.vertex_data.ctypes.data, tr_r,
+                                              tr_f, tr_y2, self.abs_wave.ctypes.data, self.abs_len.ctypes.data,
                                               C.byref(self._h)))
         self._bound_shape = None
-        self.last_stats = None
+        self._last_image = None
+
+    def move_to(self, context: OpticsContext):
+        """Re-create the device side of this sensor on another context (the fused pooled step needs the sensor
+        and the optics on one context / stream).  Tables are uploaded again; a bound image is dropped."""
+        if context is self.ctx:
+            return self
+        self.close()
+        self.ctx, self._own_ctx = context, False
+        self._create_handle()
+        return self
 
     @staticmethod
     def _treering_arrays(func):

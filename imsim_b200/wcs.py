@@ -45,6 +45,34 @@ class TanSipWCS:
         w.order = int(self.order)
         return w
 
+    def intermediate(self, x, y):
+        """Tangent-plane coordinates (xi, eta) in degrees of pixel (x, y): SIP polynomial, then CD."""
+        u, v = np.asarray(x, float) - self.crpix[0], np.asarray(y, float) - self.crpix[1]
+        f, g = u, v
+        if self.order > 0:
+            a = np.asarray(self.ab, float)
+            f = sum(a[0, i, j] * u**i * v**j for i in range(a.shape[1]) for j in range(a.shape[2]) if a[0, i, j] != 0.0)
+            g = sum(a[1, i, j] * u**i * v**j for i in range(a.shape[1]) for j in range(a.shape[2]) if a[1, i, j] != 0.0)
+        cd = np.asarray(self.cd, float).reshape(2, 2)
+        return cd[0, 0] * f + cd[0, 1] * g, cd[1, 0] * f + cd[1, 1] * g
+
+    def local(self, image_pos=None):
+        """``galsim.BaseWCS.local``: the Jacobian [[dudx, dudy], [dvdx, dvdy]] in arcsec per pixel at ``image_pos``
+        (u towards west like GalSim: u = -xi), as an object with ``getMatrix()`` -- what ``PhotonDCR`` uses."""
+        x0, y0 = (self.crpix if image_pos is None else
+                  ((image_pos.x, image_pos.y) if hasattr(image_pos, "x") else image_pos))
+        h = 0.5
+        xi = [self.intermediate(x0 + dx, y0 + dy) for dx, dy in ((h, 0), (-h, 0), (0, h), (0, -h))]
+        dxi_dx, deta_dx = (xi[0][0] - xi[1][0]) / (2 * h), (xi[0][1] - xi[1][1]) / (2 * h)
+        dxi_dy, deta_dy = (xi[2][0] - xi[3][0]) / (2 * h), (xi[2][1] - xi[3][1]) / (2 * h)
+        m = 3600.0 * np.array([[-dxi_dx, -dxi_dy], [deta_dx, deta_dy]])
+
+        class _Jacobian:
+            def getMatrix(self_inner):
+                return m
+
+        return _Jacobian()
+
 
 def tan_project(ra, dec, ra0, dec0):
     """Gnomonic projection, FITS convention: (xi, eta) radians, xi east, eta north."""

@@ -494,6 +494,14 @@ int b2_sensor_pixel_areas(b2_sensor* s, int32_t orig_center_x, int32_t orig_cent
    (imsim/photon_pooling.py:139-140,212) */
 int b2_plain_accumulate(b2_sensor* s, int64_t n, const double* x, const double* y, const double* flux,
                         int where, double* added_flux);
+/* replaces: merge_photon_arrays (imsim/photon_pooling.py:177-192) + the upload of the pool.  The photon arrays of
+   many stamps (pageable host memory, as GalSim leaves them) are gathered into one device array per field: the
+   merge happens inside a ring of pinned chunks filled by host copy threads (B2_HOST_THREADS) while the copy engine
+   moves the previous chunk.  seg: nfields * nseg HOST pointers, field-major (seg[f * nseg + g] = field f of stamp g);
+   seg_len[g]: photons of stamp g; dst[f]: DEVICE array of sum(seg_len) doubles.  Returns once the host arrays have
+   been read; the device copies are ordered before later work on the context's stream. */
+int b2_photons_upload(b2_ctx* ctx, int32_t nfields, int64_t nseg, const double* const* seg, const int64_t* seg_len,
+                      double* const* dst);
 /* One photon batch of the pooled pipeline as a single kernel, on DEVICE arrays
    (imsim/photon_pooling.py:149-160 with the op list of config/imsim-config.yaml:281-320):
    TimeSampler + PupilAnnulusSampler -> [PhotonDCR] -> RubinDiffractionOptics -> FocusDepth -> Refraction ->

@@ -45,3 +45,33 @@ def GetRNG(config, base, logger=None, tag=None):
 
 
 from . import sensor, util  # noqa: E402,F401
+
+
+# ---- image / stamp types and the two helpers the pooled builder calls (round 2) ------------------------------------
+REGISTRY.update({"image": {}, "stamp": {}})
+
+
+def RegisterImageType(name, builder):
+    REGISTRY["image"][name] = builder
+
+
+def RegisterStampType(name, builder):
+    REGISTRY["stamp"][name] = builder
+
+
+def BuildPhotonOps(config, key, base, logger):
+    """list of dicts -> photon ops: registered types through their builders, GalSim's own by class name"""
+    import galsim
+
+    ops = []
+    for cfg in config.get(key, []):
+        t = cfg["type"]
+        if t in REGISTRY["photon_op"]:
+            ops.append(REGISTRY["photon_op"][t][0].buildPhotonOp(cfg, base, logger))
+        else:
+            ops.append(getattr(galsim, t)(**{k: v for k, v in cfg.items() if k != "type"}))
+    return ops
+
+
+def FlattenNoiseVariance(base, full_image, stamps, current_vars, logger):
+    return 0.0

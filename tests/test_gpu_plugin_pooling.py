@@ -1,0 +1,82 @@
+"""``LSST_PhotonPoolingImage`` of the plugin, end to end on the image section of imsim-config-photon-pooling.yaml
+(stand-in config engine, tests/pooled_config.py): the builder must take the device route for the configured op
+list, keep the reference's batching (nbatch photon batches, faint objects whole in one batch), and produce the same
+image -- statistically, the device route draws its samplers from Philox -- as the reference's host loop
+(merge_photon_arrays -> op.applyTo ... -> accumulate_photons) run through the very same builder."""
+import numpy as np
+import pytest
+
+import helpers
+import pooled_config as pc
+
+pytestmark = pytest.mark.gpu
+
+
+def _catalog(rng, n, nx, ny):
+    flux = np.concatenate([rng.integers(20000, 90000, n - 6), rng.integers(1, 9, 6)])  # six faint ones (< nbatch)
+    return [dict(x=float(rng.uniform(150, nx - 150)), y=float(rng.uniform(150, ny - 150)), flux=int(f)) for f in flux]
+
+
+def _source(catalog, seed):
+    """stamps' photons: Gaussian star images, r-band wavelengths, unit flux -- ordinary numpy arrays"""
+    from imsim_b200.photon_array import PhotonArray
+
+    def shoot(obj):
+        c = catalog[obj.index]
+        g = np.random.default_rng(seed + 7919 * obj.index + int(obj.phot_flux))
+        n = int(obj.phot_flux)
+        return PhotonArray(n, x=c["x"] + g.normal(0, 1.6, n), y=c["y"] + g.normal(0, 1.6, n), flux=np.ones(n),
+                           wavelength=g.uniform(550.0, 690.0, n))
+
+    return shoot
+
+
+def _run(route, catalog, su, nbatch=4, nsubbatch=3):
+    builder, cfg, base = pc.make_run(su, catalog, _source(catalog, 5), nbatch=nbatch, nsubbatch=nsubbatch,
+                                     sensor_nrecalc=0.0 if route == "device" else 0.0)
+    if route == "host":  # make the op list unrecognisable: an extra (identity) op in front
+        class Identity:
+            def applyTo(self, photon_array, local_wcs=None, rng=None):
+                pass
+
+        import galsim
+
+        galsim.Identity = Identity
+        base["stamp"]["photon_ops"].insert(0, {"type": "Identity"})
+    builder.setup(cfg, base, 0, 0, [], pc.Quiet())
+    image, var = builder.buildImage(cfg, base, 0, 0, pc.Quiet())
+    assert builder.last_route == route and var == 0.0
+    return image, builder
+
+
+def test_pooled_builder_takes_the_device_route_and_matches_the_host_loop():
+    su = helpers.oracle_setup("R22_S11")
+    rng = np.random.default_rng(1)
+    cat = _catalog(rng, 40, su.detector.nx, su.detector.ny)
+    total = sum(c["flux"] for c in cat)
+    img_d, b = _run("device", cat, su)
+    assert b.last_pooled_photons == total and b.last_h2d_bytes == 32 * total
+    img_h, _ = _run("host", cat, su)
+    a, h = img_d.array.astype(np.float64), img_h.array.astype(np.float64)
+    assert a.shape == (su.detector.ny, su.detector.nx)
+    assert 0.9 * total < a.sum() <= total and abs(a.sum() - h.sum()) < 6 * np.sqrt(total - min(a.sum(), h.sum()) + 1)
+    # object by object: same electrons (up to the photons lost to vignetting) and the same centroid
+    for c in cat[:34]:
+        x0, y0 = int(c["x"]), int(c["y"])
+        sa, sh = a[y0 - 12:y0 + 13, x0 - 12:x0 + 13], h[y0 - 12:y0 + 13, x0 - 12:x0 + 13]
+        assert abs(sa.sum() - sh.sum()) < 6 * np.sqrt(c["flux"] * 0.2 + 1)
+        gy, gx = np.mgrid[y0 - 12:y0 + 13, x0 - 12:x0 + 13]
+        for g in (gx, gy):
+            assert abs((sa * g).sum() / sa.sum() - (sh * g).sum() / sh.sum()) < 0.06
+    assert np.all(a == np.round(a))  # unit-flux photons: integer electrons
+
+
+def test_pooled_builder_batches_like_the_reference():
+    """nbatch photon batches with recalc at each batch start; nbatch clipped to the bright objects (Q9)."""
+    su = helpers.oracle_setup("R22_S11")
+    rng = np.random.default_rng(2)
+    cat = _catalog(rng, 9, su.detector.nx, su.detector.ny)  # 3 bright objects + 6 faint
+    image, b = _run("device", cat, su, nbatch=10, nsubbatch=50)
+    sensor_stats = b.last_pooled_photons
+    assert sensor_stats == sum(c["flux"] for c in cat)
+    assert image.array.sum() > 0.9 * sensor_stats

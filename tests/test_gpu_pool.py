@@ -56,8 +56,16 @@ def test_fused_pool_step_equals_separate_kernels():
         stats[fused] = (added, ost.n_vignetted, st)
         sensor.close()
     assert np.array_equal(images[True], images[False])
-    for a, b in zip(traced[True], traced[False]):
-        assert np.array_equal(a, b)
+    # The traced photons agree to rounding, not always to the last bit: the two kernels inline the same source, but
+    # the compiler is free to contract a * b + c * d one way or the other in each of them, and a one-ulp change of a
+    # direction cosine is amplified by the spider kick of the few photons that graze a vane.  Bound: 1e-13 of the
+    # pixel coordinate (the parity bar against the reference arithmetic is 1e-10), on well under 1 % of the photons.
+    for name, a, b in zip(("x", "y", "dxdz", "dydz", "flux"), traced[True], traced[False]):
+        ok = np.isfinite(a) & np.isfinite(b)
+        assert np.array_equal(np.isfinite(a), np.isfinite(b))
+        tol = 4e-10 if name in ("x", "y") else (1e-15 if name != "flux" else 0.0)
+        assert np.abs(a[ok] - b[ok]).max() <= tol, name
+        assert np.count_nonzero(a[ok] != b[ok]) < 0.01 * a.size, name
     assert stats[True] == stats[False]
     assert images[True].sum() > 0.8 * 3 * 400000
 
