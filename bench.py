@@ -356,13 +356,205 @@ def visit_for_line(args, rank, world, local, dev):
                      "segments to pinned host buffers; 189 CCDs by LPT over the ranks, no collective on the path"}
 
 
+def plugin_e2e(su, P, K, rank, hx, hy, hwl, hflux, n_obj=1000):
+    """K pooled photon batches of P photons through ``B200PhotonPoolingImageBuilder.buildImage`` (the registered
+    LSST_PhotonPoolingImage type), driven by the stand-in config engine of tests/stubs (GalSim itself cannot be
+    installed here): the stamps hand over ordinary pageable numpy PhotonArrays, the builder gathers them into the
+    HBM pool (pinned ring), runs one fused launch per batch and copies the image back to the host after every
+    batch.  Wall clock around the call, device drained at the end."""
+    import torch
+
+    import pooled_config as pc
+    from imsim_b200.photon_array import PhotonArray
+
+    per = P // n_obj
+    cat = [dict(x=0.0, y=0.0, flux=per * K) for _ in range(n_obj)]
+    # pageable host arrays (np.array copies): what GalSim's shooters leave in a stamp's PhotonArray
+    arrs = [PhotonArray(per, x=np.array(hx[k * per:(k + 1) * per]), y=np.array(hy[k * per:(k + 1) * per]),
+                        flux=np.array(hflux[k * per:(k + 1) * per]), wavelength=np.array(hwl[k * per:(k + 1) * per]))
+            for k in range(n_obj)]
+    builder, cfg, base = pc.make_run(su, cat, lambda obj: arrs[obj.index], nbatch=K, nsubbatch=1, seed=11 + rank)
+
+    class EveryBatch:  # a checkpointer that keeps nothing: makes the builder bring the image back after each batch
+        file_name = "(memory)"
+        saves = 0
+
+    ck = EveryBatch()
+    builder.setup(cfg, base, 0, 0, [], pc.Quiet())
+    builder.checkpoint = ck
+    builder.load_checkpoint = lambda *a, **k: (None, [], [], [], 0)
+
+    def save(*a, **k):
+        ck.saves += 1
+
+    builder.save_checkpoint = save
+    out = {}
+    for rep in range(2):  # the first call pays the one-time allocations (pinned ring, 2.5 GB of sensor state)
+        ck.saves = 0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        image, _ = builder.buildImage(cfg, base, 0, 0, pc.Quiet())
+        torch.cuda.synchronize()
+        out = {"seconds": time.perf_counter() - t0}
+    n = per * n_obj
+    assert builder.last_route == "device", builder.last_route
+    assert ck.saves >= K, ck.saves  # one per photon batch (+ one after the, here empty, FFT batch)
+    out.update(value=n * K / out["seconds"], photons_per_step=n, electrons=float(image.array.sum(dtype=np.float64)),
+               h2d_bytes_per_step=int(builder.last_h2d_bytes // K + image.array.nbytes // K),
+               d2h_bytes_per_step=int(image.array.nbytes), steps=K, route=builder.last_route,
+               api="imsim_b200.galsim_plugin.B200PhotonPoolingImageBuilder.buildImage (registered as "
+                   "LSST_PhotonPoolingImage), %d stamps per batch with pageable numpy PhotonArrays, stand-in config "
+                   "engine (tests/stubs)" % n_obj)
+    return out
+
+
+def config_results(local, scale=1.0):
+    """One short driver-timed number per BASELINE.json config (N = 1 only; the headline line is C2-pooled and
+    `visit` is C5).  Each entry: what ran, how long, and the rate in the unit natural to it."""
+    import torch
+
+    from imsim_b200 import OpticsContext
+    from imsim_b200 import workload_data as wd
+    from imsim_b200.atmosphere import AtmosphericPSF
+    from imsim_b200.detector import lsstcam_like
+    from imsim_b200.flat import build_flat, flat_nrecalc, wavelength_cdf
+    from imsim_b200.lsst_image import ClassicImageBuilder
+    from imsim_b200.sensor import Image, SiliconSensor
+    from imsim_b200.stage1 import ObjectTable
+    from imsim_b200.synthetic import gpu_tracer, make_detector_setup
+    from imsim_b200.visit import DetectorRunner, synthetic_catalog
+
+    out = {}
+    dev = "cuda:%d" % local
+    cfg, dat = wd.sensor_model("lsst_e2v_50_4")
+    tr = wd.tree_ring_table("R22_S11")
+    wave = np.linspace(550.0, 690.0, 29)
+    seds = [wavelength_cdf(wave, 1.0 + 0.8 * np.sin(wave / (15.0 + 5 * k))) for k in range(8)]
+    sed_cdf, sed_wave = np.array([c for c, _ in seds]), np.array([w for _, w in seds])
+
+    def timed(fn, reps=2):
+        best = None
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = fn()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = (dt, r) if best is None or dt < best[0] else best
+        return best
+
+    def guard(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as e:  # a config that fails must not take the headline line with it
+            out[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+
+    ctx = OpticsContext(device=local, stream=torch.cuda.current_stream())
+    det = lsstcam_like("R22_S11")
+    su = make_detector_setup(gpu_tracer(ctx), "R22_S11", band="r", rot_tel_pos=np.radians(30.0), detector=det)
+    ctx.set_telescope(su.telescope)
+    ctx.set_wcs(su.img_wcs, su.icrf_to_field)
+    ctx.set_detector(su.detector)
+    ctx.set_diffraction(wd.default_diffraction())
+    psf = AtmosphericPSF(1.2, 0.7, "r", rng=1, device=dev)
+
+    def classic(rows, flux, radial, sersic_n, label):
+        sensor = SiliconSensor(config=cfg, vertex_data=dat, nrecalc=10000, strength=1.0, rng=5, treering_func=tr[1],
+                               treering_center=tr[0], absorption_table=wd.absorption(), context=ctx)
+        b = ClassicImageBuilder(ctx, sensor, rows, radial, sersic_n, sed_cdf, sed_wave, psf=psf, seed=2)
+        image = Image(np.zeros((det.ny, det.nx), np.float32), 0, 0)
+        dt, st = timed(lambda: b.build(image, flux, phot_flux=flux.astype(np.int64)))
+        sensor.close()
+        return {"value": st["photons"] / dt, "unit": UNIT, "seconds": dt, "photons": int(st["photons"]),
+                "objects": int(rows.size), "ms_per_object": 1e3 * dt / rows.size, "what": label}
+
+    def c1():
+        cat = synthetic_catalog(1998, det.nx, det.ny, seed=3, total_photons=5e7 * scale)
+        rows, flux = cat.build()
+        return classic(rows, flux, cat.radial_tables(), cat.sersic_n,
+                       "classic per-object pipeline (LSST_Image / LSST_Silicon): catalogue the size of "
+                       "examples/example_instance_catalog.txt (1998 entries -> 4410 rows: stars, bulge / disc / knots), "
+                       "atmosphere + optics + SiliconSensor per stamp with nrecalc = 1e4, tree rings")
+
+    def c2():
+        rng = np.random.default_rng(4)
+        n = int(1000 * scale) or 1
+        tab = ObjectTable()
+        tab.add_points(rng.uniform(100, det.nx - 100, n), rng.uniform(100, det.ny - 100, n), np.ones(n, int))
+        rows, _ = tab.build()
+        return classic(rows, np.full(n, 1.0e5), None, None,
+                       "bright-star stamps: %d stars x 1e5 e-, brighter-fatter recomputed every 1e4 e- inside each stamp "
+                       "(device-side cadence, csrc/stamps.cu), tree rings" % n)
+
+    def c3():
+        runner = DetectorRunner(local, {"e2v": (cfg, dat), "itl": wd.sensor_model("lsst_itl_50_4")}, wd.absorption(),
+                                tree_rings={"R22_S11": tr}, psf=psf)
+        nobj, total = int(1e5 * scale), 3e8 * scale
+        job = dict(det_name="R22_S11", objects=lambda: synthetic_catalog(nobj, det.nx, det.ny, seed=9, total_photons=total),
+                   nbatch=10, wavelength_cdf=(sed_cdf, sed_wave), det_index=0)
+        dt, rec = timed(lambda: runner.run(**job)[0])
+        return {"value": rec["photons"] / dt, "unit": UNIT, "seconds": dt, "photons": int(rec["photons"]),
+                "objects": nobj, "gpu_ms": rec["gpu_ms"], "setup_ms": rec["setup_ms"],
+                "what": "pooled dense field (LSST_PhotonPoolingImage cadence): %d catalogue objects on one CCD, stage 1 on "
+                        "the device, 10 photon batches with the boundary recalculation at each batch start" % nobj}
+
+    def c4_area():
+        sensor = SiliconSensor(config=cfg, vertex_data=dat, rng=1, treering_func=tr[1], treering_center=tr[0],
+                               absorption_table=wd.absorption())
+        n, counts = 4096, 1.0e5 * min(scale, 1.0)
+        img = Image(np.zeros((n, n), np.float32), 1, 1)
+        dt, _ = timed(lambda: build_flat(img, counts, sensor, rng=2, nx=8, ny=2, fused=True), reps=1)
+        sensor.close()
+        return {"value": n * n * counts / dt, "unit": "electrons/s", "seconds": dt, "level_e_per_pixel": counts,
+                "what": "examples/flat.yaml: 4096 x 4096 flat at 1e5 e-/pixel through calculate_pixel_areas + exact Poisson, "
+                        "8 x 2 sections, 1000 e- per iteration"}
+
+    def c4_photon():
+        n, counts = 2048, 2000.0 * scale
+        w = np.linspace(930.0, 960.0, 31)
+        cdf = wavelength_cdf(w, 1.0 - np.abs(w - 945.0) / 15.0 + 1e-3)
+        sensor = SiliconSensor(config=cfg, vertex_data=dat, rng=1, nrecalc=flat_nrecalc(n + 10, n + 10, 1, 1),
+                               treering_func=tr[1], treering_center=tr[0], absorption_table=wd.absorption())
+        img = Image(np.zeros((n, n), np.float32), 1, 1)
+        build_flat(img, 1000.0, sensor, rng=1, max_counts_per_iter=1000, nx=1, ny=1, sed_cdf=cdf, fused=True)
+        img = Image(np.zeros((n, n), np.float32), 1, 1)
+        dt, nphot = timed(lambda: build_flat(img, counts, sensor, rng=2, max_counts_per_iter=1000, nx=1, ny=1,
+                                             sed_cdf=cdf, fused=True), reps=1)
+        sensor.close()
+        return {"value": nphot / dt, "unit": UNIT, "seconds": dt, "photons": int(nphot),
+                "what": "examples/flat_with_sed.yaml: photon-shot flat, %d x %d section, %.0f e-/pixel, y-band sed, photons "
+                        "generated inside the deposit kernel (k_flat_step)" % (n, n, counts)}
+
+    guard("C1", c1)
+    guard("C2-stamps", c2)
+    guard("C3", c3)
+    guard("C4-area", c4_area)
+    guard("C4-photon", c4_photon)
+    return out
+
+
+def e2e_line(pinned_value, h2d, d2h, steps, plug):
+    """`e2e`: through the plugin's image builder when that leg ran (host numpy arrays in, host image out, every
+    step); the pinned-buffer route of PhotonPool.run_host_batches is kept beside it."""
+    pinned = {"value": pinned_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+              "steps": steps, "api": "PhotonPool.run_host_batches (caller fills pinned buffers)"}
+    if plug and "value" in plug:
+        return {"value": plug["value"], "unit": UNIT, "h2d_bytes_per_step": plug["h2d_bytes_per_step"],
+                "d2h_bytes_per_step": plug["d2h_bytes_per_step"], "steps": plug["steps"], "api": plug["api"],
+                "wall_s": plug["seconds"], "pinned_route": pinned}
+    pinned["plugin_route"] = plug
+    return pinned
+
+
 def workload_config(pool, note=""):
     return {"workload": "C2-pooled: single e2v CCD R22_S11 4096x4004, SiliconSensor lsst_e2v_50_4 brighter-fatter "
                         "(strength 1, boundaries recomputed every step = photon batch) + tree rings, bright-star "
                         "dominated pool (1000 stars, 5 mag range, sigma 1.5 px), RubinDiffractionOptics + "
                         "FocusDepth + Refraction, r band",
             "photons_per_step": pool, "detector": "R22_S11 (+7 neighbours for N>1, one per rank)",
-            "l2_policy": "inputs larger than L2 (each SoA array %d MB)" % (pool * 8 // 2**20), "note": note}
+            "l2_policy": "inputs larger than L2 (each SoA array %d MB)" % (pool * 8 // 2**20),
+            "note": (note + "; " if note else "") + "the ops work in place: before every timed step the inputs are restored "
+                    "by a device-to-device copy (`refill`) that the CUDA events do not bracket"}
 
 
 def main():
@@ -395,6 +587,11 @@ def main():
                          "(steady state; the first also pays the one-time allocations)")
     ap.add_argument("--visit-serial", action="store_true",
                     help="with --visit: no software pipelining (prepare, launch and finish each detector in turn)")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the short per-config runs (C1, C2-stamps, C3, C4-area, C4-photon) added to the line at N = 1")
+    ap.add_argument("--no-plugin-e2e", action="store_true",
+                    help="skip the e2e leg through the plugin's LSST_PhotonPoolingImage builder (e2e is then the "
+                         "pinned-buffer route)")
     ap.add_argument("--no-visit-line", action="store_true",
                     help="skip the synthetic full-chain visit that adds `visit` (visits per hour) to the bench line")
     ap.add_argument("--kernel-timing", action="store_true",
@@ -536,6 +733,29 @@ def main():
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
     e2e_value = world * P * e2e_K / (float(et.item()) * 1e-3)
 
+    # ---- the same steps through the reference-facing plugin call: LSST_PhotonPoolingImage.buildImage of
+    # imsim_b200.galsim_plugin, fed with ordinary (pageable) numpy PhotonArrays by the stamps, image back on the
+    # host after every batch (the checkpoint cadence of imsim/photon_pooling.py:167-168) ----
+    plug = None
+    if not args.no_plugin_e2e:
+        try:
+            plug = plugin_e2e(su, P, e2e_K, rank, hx, hy, hwl, hflux)
+        except Exception as e:  # the headline line must survive a failure of this leg
+            plug = {"error": "%s: %s" % (type(e).__name__, e)}
+        pt = torch.tensor([plug.get("seconds", 0.0), 1.0 if "error" in plug else 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+        if pt[1].item() == 0.0 and pt[0].item() > 0.0:
+            plug["value"] = world * P * e2e_K / float(pt[0].item())
+
+    # ---- one short number per BASELINE config (rank 0 of a single-GPU run only) ----
+    cfgs = None
+    if world == 1 and not args.no_configs:
+        try:
+            cfgs = config_results(local)
+        except Exception as e:
+            cfgs = {"error": "%s: %s" % (type(e).__name__, e)}
+
     # ---- the other half of the metric: LSSTCam visits per hour on these GPUs (every rank takes part) ----
     visit = None if args.no_visit_line else visit_for_line(args, rank, world, local, dev)
 
@@ -559,8 +779,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(P),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_K},
+            "e2e": e2e_line(e2e_value, h2d, d2h, e2e_K, plug),
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"kernel": dominant, "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak,
@@ -578,6 +797,8 @@ def main():
         }
         if visit is not None:
             line["visit"] = visit
+        if cfgs is not None:
+            line["configs"] = cfgs
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample, 1)
         print(json.dumps(line))

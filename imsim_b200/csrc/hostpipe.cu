@@ -10,6 +10,8 @@
 // counters are offset by the chunk start.
 #include <unistd.h>
 
+#include <chrono>
+
 #include <algorithm>
 #include <condition_variable>
 #include <cstdlib>
@@ -256,10 +258,15 @@ extern "C" int b2_photons_upload(b2_ctx* ctx, int32_t nfields, int64_t nseg, con
     std::vector<Piece> pieces;
     const int64_t nch = (n + chunk - 1) / chunk;
     int64_t sfirst = 0;  // first segment that reaches into the current chunk
+    const bool prof = getenv("B2_PIPE_PROFILE") != nullptr;
+    double t_wait = 0.0, t_copy = 0.0, t_issue = 0.0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     for (int64_t k = 0; k < nch; ++k) {
         const int s = (int)(k % NSLOT);
         const int64_t off = k * chunk, cnt = std::min(chunk, n - off);
+        double t0 = prof ? now() : 0.0;
         if (k >= NSLOT) B2_CUDA(cudaEventSynchronize(p.done[s]));  // the copy that last read this slot
+        if (prof) t_wait += now() - t0;
         while (sfirst < nseg && start[sfirst + 1] <= off) ++sfirst;
         pieces.clear();
         for (int64_t g = sfirst; g < nseg && start[g] < off + cnt; ++g) {
@@ -272,12 +279,19 @@ extern "C" int b2_photons_upload(b2_ctx* ctx, int32_t nfields, int64_t nseg, con
                 for (size_t o = 0; o < bytes; o += PIECE) pieces.push_back(Piece{dstp + o, src + o, std::min(PIECE, bytes - o)});
             }
         }
+        t0 = prof ? now() : 0.0;
         cp.run(pieces);
+        if (prof) t_copy += now() - t0;
+        t0 = prof ? now() : 0.0;
         cudaStream_t st = p.st[k & 1];
         for (int f = 0; f < nfields; ++f)
             B2_CUDA(cudaMemcpyAsync(dst[f] + off, slot(s, f), (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, st));
         B2_CUDA(cudaEventRecord(p.done[s], st));
+        if (prof) t_issue += now() - t0;
     }
+    if (prof)
+        fprintf(stderr, "b2_photons_upload: %lld photons x %d fields, %lld chunks, %d threads: wait %.1f ms, host copy %.1f ms, issue %.1f ms\n",
+                (long long)n, nfields, (long long)nch, cp.threads(), 1e3 * t_wait, 1e3 * t_copy, 1e3 * t_issue);
     // later work on the context's stream sees the uploaded arrays; the host does not wait for the copies
     for (int i = 0; i < 2; ++i) {
         B2_CUDA(cudaEventRecord(p.entry, p.st[i]));

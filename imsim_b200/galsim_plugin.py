@@ -82,12 +82,17 @@ def _camera(name):
     return get_camera(name)
 
 
+_N_GPUS = None
+
+
 def _device(base):
     """One GPU per worker process: det_num % n_gpus (GalSim forks workers per output file)."""
-    import torch
+    global _N_GPUS
+    if _N_GPUS is None:
+        import torch
 
-    n = max(torch.cuda.device_count(), 1)
-    return int(base.get("det_num", base.get("file_num", 0))) % n
+        _N_GPUS = max(torch.cuda.device_count(), 1)  # asked once: the NVML query costs ~20 ms a call
+    return int(base.get("det_num", base.get("file_num", 0))) % _N_GPUS
 
 
 _rubin_optics_base_args = ("stamp_center",)

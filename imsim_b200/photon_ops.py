@@ -72,22 +72,35 @@ def _seed_offset(rng):
     raise TypeError("rng must be None, an int or a galsim.BaseDeviate")
 
 
+#: device index -> the context shared by the photon ops of this process on that device
+_SHARED_CONTEXTS: dict = {}
+
+
 class _DeviceOp:
     """Shared plumbing: lazily creates the per-detector device context."""
 
     device = 0
 
     def _context(self) -> OpticsContext:
-        ctx = getattr(self, "_ctx", None)
+        """The device context of this op's GPU, holding this op's telescope / WCS / detector / spider set-up.
+
+        One context per (process, device) is shared by all ops -- GalSim rebuilds the op objects for every image
+        (and every stamp in the classic pipeline), and a context of its own for each would also force the sensor,
+        which must live on the optics' context for the fused pooled step, to re-create its 2.5 GB of boundary
+        arrays per image.  The context remembers which op's description it holds; another op re-uploads its own
+        (a few kB of structs, no device work)."""
+        ctx = _SHARED_CONTEXTS.get(self.device)
         if ctx is None:
-            ctx = OpticsContext(device=self.device)
+            ctx = _SHARED_CONTEXTS[self.device] = OpticsContext(device=self.device)
+        if getattr(ctx, "_described_by", None) is not self:
             ctx.set_telescope(_as_telescope(self.telescope))
             ctx.set_wcs(_as_wcs(self.img_wcs), _as_wcs(self.icrf_to_field))
             det = getattr(self, "detector", None)
             if det is not None:
                 ctx.set_detector(_as_detector(det))
             ctx.set_diffraction(self._diffraction_pod())
-            self._ctx = ctx
+            ctx._described_by = self
+        self._ctx = ctx
         return ctx
 
     def _diffraction_pod(self):

@@ -516,17 +516,21 @@ class PooledDevicePath:
                 raise _lib.B2Error("pooled photons need wavelengths (the stamps' WavelengthSampler assigns them)")
         dp = DevicePhotons(n, device="cuda:%d" % self.ctx.device)
         nseg = len(arrays)
-        ptrs = (C.c_void_p * (len(fields) * nseg))()
+        # pointer table [field][stamp] without a ctypes object per array
+        ptrs = np.empty((len(fields), nseg), dtype=np.uint64)
         keep = []
         for f, name in enumerate(fields):
+            row = ptrs[f]
             for g, pa in enumerate(arrays):
-                a = np.ascontiguousarray(getattr(pa, name), dtype=np.float64)
-                keep.append(a)
-                ptrs[f * nseg + g] = a.ctypes.data
-        lens = (C.c_int64 * nseg)(*[len(pa) for pa in arrays])
-        dst = (C.c_void_p * len(fields))(*[getattr(dp, name).data_ptr() for name in fields])
-        _lib.check(_lib.load().b2_photons_upload(self.ctx.handle, len(fields), nseg, C.cast(ptrs, C.c_void_p),
-                                                 C.cast(lens, C.c_void_p), C.cast(dst, C.c_void_p)))
+                a = getattr(pa, name)
+                if a.dtype != np.float64 or not a.flags.c_contiguous:
+                    a = np.ascontiguousarray(a, dtype=np.float64)
+                    keep.append(a)
+                row[g] = a.__array_interface__["data"][0]
+        lens = np.fromiter((len(pa) for pa in arrays), dtype=np.int64, count=nseg)
+        dst = np.array([getattr(dp, name).data_ptr() for name in fields], dtype=np.uint64)
+        _lib.check(_lib.load().b2_photons_upload(self.ctx.handle, len(fields), nseg, ptrs.ctypes.data, lens.ctypes.data,
+                                                 dst.ctypes.data))
         dp._has.update(wavelength=True)
         self.dp = dp
         self.photons += n
