@@ -12,6 +12,20 @@ import pooled_config as pc
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, scope="module")
+def _stand_in_engine_only_here():
+    """The stand-in ``galsim`` / ``imsim`` of tests/stubs must not leak into other test modules (the package
+    looks for a real GalSim in a few places)."""
+    import sys
+
+    yield
+    if pc.STUBS in sys.path:
+        sys.path.remove(pc.STUBS)
+    for name in [m for m in sys.modules if m in ("galsim", "imsim", "imsim_b200.galsim_plugin")
+                 or m.startswith("galsim.") or m.startswith("imsim.")]:
+        sys.modules.pop(name, None)
+
+
 def _catalog(rng, n, nx, ny):
     flux = np.concatenate([rng.integers(20000, 90000, n - 6), rng.integers(1, 9, 6)])  # six faint ones (< nbatch)
     return [dict(x=float(rng.uniform(150, nx - 150)), y=float(rng.uniform(150, ny - 150)), flux=int(f)) for f in flux]
