@@ -121,6 +121,7 @@ _SIGNATURES = {
                                               C.c_uint64, C.c_int32, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32,
                                               C.c_int32, C.c_int32, C.POINTER(_abi.B2AccumStats), vp]),
     "b2_photons_upload": (C.c_int, [vp, C.c_int32, C.c_int64, vp, vp, vp]),
+    "b2_host_memcpy": (C.c_int, [vp, vp, C.c_int64]),
     "b2_xytov_compile": (C.c_int, [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, dp]),
     "b2_pool_step": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.POINTER(_abi.B2OpticsOptions), C.c_double,
                                C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,

@@ -30,12 +30,14 @@ class OpticsContext:
         self._lib = _lib.load()
         self._h = C.c_void_p()
         self.device = int(device)
+        self.stream = stream  # None: the legacy default stream
         _lib.check(self._lib.b2_ctx_create(self.device, _stream_handle(stream), C.byref(self._h)))
         self.telescope = None
         self._keep = []
 
     # -- uploads ----------------------------------------------------------
     def set_stream(self, stream):
+        self.stream = stream
         _lib.check(self._lib.b2_ctx_set_stream(self._h, _stream_handle(stream)))
 
     def set_telescope(self, tel):

@@ -261,6 +261,20 @@ class B200PhotonPoolingImageBuilder(_ImsimPoolingBuilder):
         self.last_route = "host" if path is None else "device"
         if path is not None:
             path.begin(full_image)
+        # With the device route a checkpoint's image travels to the host while the NEXT sub-batch's photons are
+        # gathered and uploaded (the image is snapshotted on the device right after its batch, so what is saved is
+        # exactly the state after that batch); the file is written once the upload has been queued.
+        pending = None  # batch number whose checkpoint awaits its image
+        image_current = False  # full_image.array holds the final pixels already
+
+        def flush_pending():
+            nonlocal pending
+            if pending is not None:
+                path.snapshot_finish(full_image)
+                self.save_checkpoint(self.checkpoint, chk_name, base, full_image, book["stamps"], book["vars"],
+                                     book["obj_nums"], pending)
+                pending = None
+
         for batch_num, batch in enumerate(batches, start=done):
             if not batch:
                 continue
@@ -274,7 +288,9 @@ class B200PhotonPoolingImageBuilder(_ImsimPoolingBuilder):
                 if path is not None:
                     path.add([stamp.photons for stamp in stamps])
                     del stamps
+                    flush_pending()
                     path.step(resume=resume, recalc=recalc)
+                    image_current = False
                 else:
                     photons = self.merge_photon_arrays(stamps)
                     del stamps
@@ -285,11 +301,17 @@ class B200PhotonPoolingImageBuilder(_ImsimPoolingBuilder):
                 book["vars"].extend(v for v in current_vars if v != 0)
             if self.checkpoint is not None:
                 if path is not None:
-                    path.read_back(full_image)
-                self.save_checkpoint(self.checkpoint, chk_name, base, full_image, book["stamps"], book["vars"],
-                                     book["obj_nums"], batch_num + 1)
+                    path.snapshot_begin()
+                    pending = batch_num + 1
+                else:
+                    self.save_checkpoint(self.checkpoint, chk_name, base, full_image, book["stamps"], book["vars"],
+                                         book["obj_nums"], batch_num + 1)
         if path is not None:
-            path.read_back(full_image)
+            if pending is not None:
+                flush_pending()
+                image_current = True  # the last checkpoint's image is the final one
+            if not image_current:
+                path.read_back(full_image)
             self.last_pooled_photons, self.last_h2d_bytes = path.photons, path.h2d_bytes
 
         current_var = galsim.config.FlattenNoiseVariance(base, full_image, book["stamps"], tuple(book["vars"]), logger)

@@ -550,3 +550,42 @@ class PooledDevicePath:
 
     def read_back(self, full_image=None):
         self.sensor.read_image(self.image if full_image is None else full_image)
+
+    # -- the image of a finished batch, travelling to the host while the next batch uploads --------------------
+    def snapshot_begin(self):
+        """Copy the image as it stands now into a device buffer (in stream order, after the batch just queued) and
+        start its transfer to pinned host memory on a side stream.  Returns at once."""
+        import torch  # noqa: PLC0415
+
+        from .sensor import _image_parts  # noqa: PLC0415
+
+        arr, _, _ = _image_parts(self.image)
+        dev = torch.device("cuda", self.ctx.device)
+        if getattr(self, "_snap", None) is None or tuple(self._snap.shape) != arr.shape:
+            tdt = torch.float32 if arr.dtype == np.float32 else torch.float64
+            self._snap = torch.empty(arr.shape, dtype=tdt, device=dev)
+            self._pin = torch.empty(arr.shape, dtype=tdt).pin_memory()
+            self._side = torch.cuda.Stream(device=dev)
+        main = self.ctx.stream if self.ctx.stream is not None else torch.cuda.default_stream(dev)
+        self.sensor.snapshot_image(self._snap)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            self._pin.copy_(self._snap, non_blocking=True)
+            self._done = torch.cuda.Event()
+            self._done.record(self._side)
+        self._snap_pending = True
+
+    def snapshot_finish(self, full_image=None):
+        """Wait for the transfer started by ``snapshot_begin`` and put the pixels into ``full_image.array``."""
+        from .sensor import _image_parts  # noqa: PLC0415
+
+        if not getattr(self, "_snap_pending", False):
+            return False
+        arr, _, _ = _image_parts(self.image if full_image is None else full_image)
+        self._done.synchronize()
+        src = self._pin.numpy()
+        _lib.check(_lib.load().b2_host_memcpy(arr.ctypes.data, src.ctypes.data, arr.nbytes))
+        self._snap_pending = False
+        return True

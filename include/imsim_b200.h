@@ -502,6 +502,9 @@ int b2_plain_accumulate(b2_sensor* s, int64_t n, const double* x, const double* 
    been read; the device copies are ordered before later work on the context's stream. */
 int b2_photons_upload(b2_ctx* ctx, int32_t nfields, int64_t nseg, const double* const* seg, const int64_t* seg_len,
                       double* const* dst);
+/* host-to-host copy on the library's copy threads (B2_HOST_THREADS): used to hand a pinned snapshot of the image to
+   the caller's pageable array when a checkpoint is written while the next batch is already uploading */
+int b2_host_memcpy(void* dst, const void* src, int64_t bytes);
 /* One photon batch of the pooled pipeline as a single kernel, on DEVICE arrays
    (imsim/photon_pooling.py:149-160 with the op list of config/imsim-config.yaml:281-320):
    TimeSampler + PupilAnnulusSampler -> [PhotonDCR] -> RubinDiffractionOptics -> FocusDepth -> Refraction ->

@@ -94,3 +94,41 @@ def test_pooled_builder_batches_like_the_reference():
     sensor_stats = b.last_pooled_photons
     assert sensor_stats == sum(c["flux"] for c in cat)
     assert image.array.sum() > 0.9 * sensor_stats
+
+
+def test_checkpoints_hold_the_image_after_their_batch():
+    """With a checkpointer configured the builder writes one checkpoint per photon batch (photon_pooling.py:167-168).
+    On the device route the image of batch k travels to the host while batch k+1 uploads; what is saved must still be
+    the state after batch k exactly, and the last checkpoint the final image."""
+    su = helpers.oracle_setup("R22_S11")
+    rng = np.random.default_rng(3)
+    cat = _catalog(rng, 30, su.detector.nx, su.detector.ny)
+    builder, cfg, base = pc.make_run(su, cat, _source(cat, 5), nbatch=5, nsubbatch=2)
+    builder.setup(cfg, base, 0, 0, [], pc.Quiet())
+    saved = []
+
+    class Ck:
+        file_name = "(memory)"
+
+    builder.checkpoint = Ck()
+    builder.load_checkpoint = lambda *a, **k: (None, [], [], [], 0)
+    builder.save_checkpoint = lambda ck, name, b, img, stamps, vars_, objs, nb: saved.append((nb, img.array.copy()))
+    try:
+        image, _ = builder.buildImage(cfg, base, 0, 0, pc.Quiet())
+    finally:
+        builder.checkpoint = None
+        del builder.load_checkpoint, builder.save_checkpoint
+    assert builder.last_route == "device"
+    assert [nb for nb, _ in saved] == [0, 1, 2, 3, 4, 5]  # after the (empty) FFT batch, then after each photon batch
+    sums = [float(a.sum(dtype=np.float64)) for _, a in saved]
+    assert sums[0] == 0.0 and all(b > a for a, b in zip(sums, sums[1:]))
+    total = sum(c["flux"] for c in cat)
+    for k in range(1, 6):
+        assert abs(sums[k] / sums[5] - k / 5.0) < 0.01  # every batch carries a fifth of every bright object
+    assert 0.9 * total < sums[5] <= total
+    np.testing.assert_array_equal(saved[-1][1], image.array)
+    # the same run without checkpoints gives the same final image (same seeds, same batches)
+    builder2, cfg2, base2 = pc.make_run(su, cat, _source(cat, 5), nbatch=5, nsubbatch=2)
+    builder2.setup(cfg2, base2, 0, 0, [], pc.Quiet())
+    image2, _ = builder2.buildImage(cfg2, base2, 0, 0, pc.Quiet())
+    np.testing.assert_array_equal(image2.array, image.array)
