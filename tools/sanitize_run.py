@@ -72,3 +72,43 @@ np.fill_diagonal(xt, 0.0)
 raw = CcdReadout(ctx, amps, xtalk=xt).build_amp_images(e, seed=1)
 torch.cuda.synchronize()
 print("raw", tuple(raw.shape), int(raw.sum()))
+# round 2: per-object stamps with the cadence inside the kernel (csrc/stamps.cu), the compiled XyToV (set_detector above
+# compiled it), the pooled upload of host segments and the threaded host copy
+sensor = SiliconSensor(config=cfg, vertex_data=dat, nrecalc=1500, strength=1.0, rng=3, treering_func=tr[1],
+                       treering_center=tr[0], absorption_table=helpers.absorption(), context=ctx)
+rng = np.random.default_rng(1)
+jobs, p0, xs, ys = [], 0, [], []
+for k, (n, size) in enumerate([(9000, 24), (400, 12), (0, 10), (6000, 31), (2500, 16)]):
+    cx, cy = rng.uniform(20, 80, 2)
+    jobs.append((p0, n, int(cx) - size // 2, int(cy) - size // 2, size, size, int(k == 4)))
+    xs.append(cx + rng.normal(0, 1.2, n))
+    ys.append(cy + rng.normal(0, 1.2, n))
+    p0 += n
+dp = DevicePhotons(p0)
+dp.x.copy_(torch.as_tensor(np.concatenate(xs)))
+dp.y.copy_(torch.as_tensor(np.concatenate(ys)))
+dp.flux.fill_(1.0)
+dp.wavelength.fill_(620.0)
+dp.dxdz.zero_()
+dp.dydz.zero_()
+dp._has.update(dxdz=True, dydz=True, wavelength=True)
+full = torch.zeros((100, 100), dtype=torch.float32, device="cuda")
+stt = sensor.accumulate_stamps(jobs, dp, full, 1, 1)
+print("stamps", float(full.sum()), stt.n_updates)
+import ctypes as C  # noqa: E402
+
+from imsim_b200 import _lib  # noqa: E402
+
+segs = [rng.uniform(0, 1, m) for m in (1000, 0, 70000, 333)]
+n = sum(len(a) for a in segs)
+dst = torch.empty(n, dtype=torch.float64, device="cuda")
+ptrs = np.array([a.ctypes.data for a in segs], dtype=np.uint64)
+lens = np.array([len(a) for a in segs], dtype=np.int64)
+dptr = np.array([dst.data_ptr()], dtype=np.uint64)
+_lib.check(_lib.load().b2_photons_upload(ctx.handle, 1, len(segs), ptrs.ctypes.data, lens.ctypes.data, dptr.ctypes.data))
+torch.cuda.synchronize()
+assert np.array_equal(dst.cpu().numpy(), np.concatenate(segs))
+a, b = rng.uniform(0, 1, 300000), np.empty(300000)
+_lib.check(_lib.load().b2_host_memcpy(b.ctypes.data, a.ctypes.data, a.nbytes))
+assert np.array_equal(a, b)
+print("upload / host copy ok")
