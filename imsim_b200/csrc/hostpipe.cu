@@ -110,8 +110,10 @@ long env_long(const char* name, long dflt) {
 CopyPool& pool() {
     std::lock_guard<std::mutex> lk(g_pool_mu);
     if (!g_pool || g_pool_pid != getpid()) {
+        // up to 8 copy threads, fewer when several ranks share the host's cores (torchrun exports LOCAL_WORLD_SIZE)
         long hw = (long)std::thread::hardware_concurrency();
-        long n = env_long("B2_HOST_THREADS", std::max(1L, std::min(8L, hw)));
+        long share = std::max(1L, hw / env_long("LOCAL_WORLD_SIZE", 1));
+        long n = env_long("B2_HOST_THREADS", std::max(1L, std::min(8L, share)));
         g_pool = new CopyPool((int)std::min(n, 64L));  // the previous pool (parent's, after a fork) is abandoned
         g_pool_pid = getpid();
     }

@@ -859,6 +859,13 @@ static void sensor_release_device(b2_sensor* s) {
     if (s->stamp_meta.ptr) cudaFree(s->stamp_meta.ptr);
     if (s->stamp_arena.ptr) cudaFree(s->stamp_arena.ptr);
     s->cum = s->slow = s->stamp_meta = s->stamp_arena = Scratch{};
+    if (s->stamp_aux) {
+        cudaStreamSynchronize(s->stamp_aux);
+        cudaStreamDestroy(s->stamp_aux);
+        cudaEventDestroy(s->stamp_ev[0]);
+        cudaEventDestroy(s->stamp_ev[1]);
+        s->stamp_aux = nullptr;
+    }
     s->bound = s->initialized = false;
 }
 

@@ -48,6 +48,8 @@ struct b2_sensor {
     size_t tr_cap = 0;
     unsigned long long* dnslow = nullptr;
     Scratch stamp_meta, stamp_arena;  // stamps.cu: job tables + per-block lists; boundary state of the stamps in flight
+    cudaStream_t stamp_aux = nullptr;  // stamps.cu: the cluster launch runs beside the one-block-per-stamp launch
+    cudaEvent_t stamp_ev[2] = {nullptr, nullptr};
 };
 
 enum { ST_POLY = 0, ST_NEIGH = 1, ST_NOTFOUND = 2, ST_B9 = 3, ST_DROP = 4, ST_N = 8 };

@@ -20,6 +20,8 @@
 // b2_sensor_bind_image + b2_sensor_accumulate on the same photons (tests/test_gpu_stamps.py).
 #include "sensor_device.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <numeric>
 #include <vector>
@@ -270,8 +272,31 @@ __device__ __forceinline__ void stamp_fold_delta(const DevSensor& s, int x, int 
     }
 }
 
-template <int NV>
-__global__ void __launch_bounds__(ST_THREADS, 2)
+// A stamp is worked on by a team: one thread block, or -- for the few stamps that hold most of the photons, whose
+// update loop would otherwise keep one SM busy long after the others have finished -- a thread-block cluster of CS
+// blocks on CS SMs.  The boundary state lives in the arena (global memory) either way; the members of a cluster
+// split photons, charged pixels and pixels by index, keep their own lists and queues, read each other's few control
+// words through distributed shared memory and meet at cluster barriers (release / acquire, so plain loads of
+// boundary points another member has moved are safe afterwards).
+namespace cg = cooperative_groups;
+
+template <int CS>
+struct Team {
+    __device__ static __forceinline__ unsigned rank() { return cg::this_cluster().block_rank(); }
+    __device__ static __forceinline__ void sync() { cg::this_cluster().sync(); }
+    template <typename T>
+    __device__ static __forceinline__ T* peer(T* p, unsigned r) { return cg::this_cluster().map_shared_rank(p, r); }
+};
+template <>
+struct Team<1> {
+    __device__ static __forceinline__ unsigned rank() { return 0u; }
+    __device__ static __forceinline__ void sync() { __syncthreads(); }
+    template <typename T>
+    __device__ static __forceinline__ T* peer(T* p, unsigned) { return p; }
+};
+
+template <int NV, int CS>
+__global__ void __launch_bounds__(ST_THREADS, CS == 1 ? 2 : 1)
 k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restrict__ jobs, const StampSlot* __restrict__ slots,
              const int* __restrict__ order, int njobs, int* __restrict__ next, unsigned char* __restrict__ arena,
              const __grid_constant__ StampPhotons ph, double nrecalc, int ocx, int ocy, const __grid_constant__ FullImage full,
@@ -283,8 +308,13 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
     __shared__ int sh_job, sh_cut, pend[4];  // pend: box of the pixels holding charge since the last update
     __shared__ unsigned sh_nslow, sh_nupd, sh_npix, sh_nq;
     __shared__ unsigned queue[ST_QCAP];  // sh_npix: length of the charged-pixel list (may exceed its capacity)
-    __shared__ double sh_warp[ST_THREADS / 32], sh_tile_sum;
+    __shared__ double sh_warp[ST_THREADS / 32], sh_tile_sum;  // sh_tile_sum: flux of this block's share of the pass
+    using T = Team<CS>;
+    constexpr int TT = ST_THREADS * CS;  // threads and photons per pass of the team
+    constexpr int TTILE = ST_TILE * CS;
+    const unsigned rank = T::rank();
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int gtid = (int)rank * ST_THREADS + tid;
     const int nKH = base.nx9 * base.ny9 * (NV + 2), nKV = base.nx9 * base.ny9 * NV;
     for (int k = tid; k < nKH; k += ST_THREADS) sK[k] = base.KH[k];
     for (int k = tid; k < nKV; k += ST_THREADS) sK[nKH + k] = base.KV[k];
@@ -306,17 +336,18 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
     }
 
     for (;;) {
-        __syncthreads();
-        if (tid == 0) sh_job = atomicAdd(next, 1);
-        __syncthreads();
-        if (sh_job >= njobs) break;
-        const int jid = order[sh_job];
+        T::sync();
+        if (gtid == 0) sh_job = atomicAdd(next, 1);
+        T::sync();
+        const int job_k = *T::peer(&sh_job, 0);
+        if (job_k >= njobs) break;
+        const int jid = order[job_k];
         const B2StampJob job = jobs[jid];
         const int64_t p0 = job.p0, p1 = job.p0 + job.n;
         double my_added = 0.0;
         if (job.plain) {
             // galsim.Sensor (faint objects, imsim/stamp.py:534-537): photons binned on the stamp, no silicon
-            for (int64_t i = p0 + tid; i < p1; i += ST_THREADS) {
+            for (int64_t i = p0 + gtid; i < p1; i += TT) {
                 int ix = (int)floor(ph.x[i] + 0.5), iy = (int)floor(ph.y[i] + 0.5);
                 if (ix >= job.xmin && ix < job.xmin + job.nx && iy >= job.ymin && iy < job.ymin + job.ny) {
                     double f = ph.flux[i];
@@ -346,14 +377,14 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
             uint8_t* changed = arena + slots[jid].changed;
             StampBits cb;
             cb.wpr = (s.nx + 31) / 32;
-            cb.global = cb.wpr * s.ny > smem_bit_words;
+            cb.global = CS > 1 || cb.wpr * s.ny > smem_bit_words;
             cb.w = cb.global ? reinterpret_cast<unsigned*>(arena + slots[jid].cbits)
                              : reinterpret_cast<unsigned*>(sK + nKH + nKV);
             unsigned* const cbits = cb.w;
             const int wpr = cb.wpr;
             const int nx = s.nx, ny = s.ny;
             const bool tr = s.ntr > 2;
-            for (int idx = tid; idx < (nx + 1) * (ny + 1); idx += ST_THREADS) {
+            for (int idx = gtid; idx < (nx + 1) * (ny + 1); idx += TT) {
                 const int x = idx % (nx + 1), y = idx / (nx + 1);
                 if (x < nx) {
                     float2* h = s.H + Hidx(s, x, y);
@@ -384,19 +415,19 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
                     else reinterpret_cast<double*>(s.target)[i] = 0.0;
                 }
             }
-            __syncthreads();
-            for (int idx = tid; idx < nx * ny; idx += ST_THREADS) stamp_bounds_pixel<NV>(s, idx % nx, idx / nx);
-            __syncthreads();
+            T::sync();
+            for (int idx = gtid; idx < nx * ny; idx += TT) stamp_bounds_pixel<NV>(s, idx % nx, idx / nx);
+            T::sync();
             ST_PROF(0)
 
             // ---- Silicon::accumulate with the boundary update every nrecalc electrons
             double accum = 0.0;  // flux since the last update (block-uniform)
             int64_t i0 = p0;
             while (i0 < p1) {
-                const int64_t tend = (p1 - i0 < ST_TILE) ? p1 : i0 + ST_TILE;
-                __syncthreads();  // the previous pass (or the set-up) is complete
+                const int64_t tend = (p1 - i0 < TTILE) ? p1 : i0 + TTILE;
+                T::sync();  // the previous pass (or the set-up) is complete, its control words have been read
                 if (tid == 0) {
-                    sh_cut = ST_TILE + 1;
+                    sh_cut = TTILE + 1;
                     sh_nslow = 0;
                 }
                 double f[ST_PER], run = 0.0, incl = 0.0;
@@ -404,7 +435,7 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
                     // inclusive prefix sums of this pass's fluxes in photon order: thread t holds photons 4t .. 4t+3
 #pragma unroll
                     for (int k = 0; k < ST_PER; ++k) {
-                        int64_t i = i0 + (int64_t)tid * ST_PER + k;
+                        int64_t i = i0 + (int64_t)gtid * ST_PER + k;
                         f[k] = (i < tend) ? ph.flux[i] : 0.0;
                         run += f[k];
                     }
@@ -417,30 +448,46 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
                     if (lane == 31) sh_warp[wid] = incl;
                 }
                 __syncthreads();
+                double tile_sum = 0.0;
                 if (nrecalc > 0.0) {
                     double before = 0.0;
                     for (int w = 0; w < wid; ++w) before += sh_warp[w];
                     if (tid == ST_THREADS - 1) sh_tile_sum = before + incl;
+                    if (CS > 1) {
+                        // the blocks ahead of this one in the pass
+                        T::sync();
+                        for (unsigned r = 0; r < (unsigned)CS; ++r) {
+                            const double t = *T::peer(&sh_tile_sum, r);
+                            if (r < rank) before += t;
+                            tile_sum += t;
+                        }
+                    }
                     double cum = accum + before + (incl - run);
 #pragma unroll
                     for (int k = 0; k < ST_PER; ++k) {
                         cum += f[k];
-                        int64_t i = i0 + (int64_t)tid * ST_PER + k;
+                        int64_t i = i0 + (int64_t)gtid * ST_PER + k;
                         if (i < tend && cum >= nrecalc) {
-                            atomicMin(&sh_cut, tid * ST_PER + k);
+                            atomicMin(&sh_cut, gtid * ST_PER + k);
                             break;
                         }
                     }
                 }
-                __syncthreads();
-                const bool hit = sh_cut <= ST_TILE;
+                T::sync();
+                int cut_at = sh_cut;
+                if (CS > 1) {
+                    for (unsigned r = 0; r < (unsigned)CS; ++r) cut_at = min(cut_at, *T::peer(&sh_cut, r));
+                } else {
+                    tile_sum = sh_tile_sum;
+                }
+                const bool hit = cut_at <= TTILE;
                 ST_PROF(1)
-                const int64_t cut = hit ? i0 + sh_cut + 1 : tend;
+                const int64_t cut = hit ? i0 + cut_at + 1 : tend;
                 // ---- deposit photons [i0, cut): fast path, the rest to the block's list
                 int bx0 = 1 << 30, bx1 = -1, by0 = 1 << 30, by1 = -1;
 #pragma unroll 1
                 for (int k = 0; k < ST_PER; ++k) {
-                    int64_t i = i0 + tid + (int64_t)k * ST_THREADS;
+                    int64_t i = i0 + gtid + (int64_t)k * TT;
                     bool to_slow = false;
                     SlowRec rec;
                     if (i < cut) {
@@ -510,13 +557,27 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
                     atomicMin(&pend[0], bx0); atomicMax(&pend[1], bx1);
                     atomicMin(&pend[2], by0); atomicMax(&pend[3], by1);
                 }
-                __syncthreads();
+                T::sync();
                 ST_PROF(3)
                 if (hit) {
                     // ---- Silicon::update, restricted to the reach of the charge deposited since the last one
                     const int q = s.qdist;
-                    const unsigned npix = sh_npix;
-                    if (npix > 0 && npix <= ST_PIXCAP && q == ST_QMAX && nx < 65536 && ny < 65536) {
+                    const unsigned npix = sh_npix;  // this block's list; the team's lists together hold every charged pixel
+                    unsigned npix_team = npix;
+                    bool listed = npix <= ST_PIXCAP;
+                    int pb[4] = {pend[0], pend[1], pend[2], pend[3]};
+                    if (CS > 1) {
+                        npix_team = 0;
+                        for (unsigned r = 0; r < (unsigned)CS; ++r) {
+                            const unsigned m = *T::peer(&sh_npix, r);
+                            npix_team += m;
+                            listed = listed && m <= ST_PIXCAP;
+                            const int* pr = T::peer(&pend[0], r);
+                            pb[0] = min(pb[0], pr[0]); pb[1] = max(pb[1], pr[1]);
+                            pb[2] = min(pb[2], pr[2]); pb[3] = max(pb[3], pr[3]);
+                        }
+                    }
+                    if (npix_team > 0 && listed && q == ST_QMAX && nx < 65536 && ny < 65536) {
                         // the usual case: work proportional to the number of charged pixels (see
                         // stamp_update_slot_owned): boundary slots within reach first, then the boxes of the pixels
                         // Owners are few and scattered among the proposals (one in ~50 in a star's core), so the
@@ -575,6 +636,7 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
                                 }
                                 __syncthreads();
                             }
+                            T::sync();  // every block's slots are in place before the boxes, the boxes before the fold
                             ST_PROF(4 + pass)
                         }
                         for (unsigned k = tid; k < npix; k += ST_THREADS) {
@@ -584,48 +646,48 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
                             else stamp_fold_delta<double>(s, x, y);
                             atomicAnd(&cbits[y * wpr + (x >> 5)], ~(1u << (x & 31)));
                         }
-                        __syncthreads();
+                        T::sync();
                         ST_PROF(6)
-                    } else if (pend[1] >= 0) {
+                    } else if (pb[1] >= 0) {
                         // more charged pixels than the list holds: scan the box of the pending charge
-                        const int sx0 = max(pend[0] - q, 0), sx1 = min(pend[1] + q + 1, nx);      // boundary slots
-                        const int sy0 = max(pend[2] - q, 0), sy1 = min(pend[3] + q + 1, ny);
+                        const int sx0 = max(pb[0] - q, 0), sx1 = min(pb[1] + q + 1, nx);      // boundary slots
+                        const int sy0 = max(pb[2] - q, 0), sy1 = min(pb[3] + q + 1, ny);
                         const int sw = sx1 - sx0 + 1, shh = sy1 - sy0 + 1;
-                        for (int idx = tid; idx < sw * shh; idx += ST_THREADS)
+                        for (int idx = gtid; idx < sw * shh; idx += TT)
                             stamp_update_slot<NV>(s, KH, KV, changed, sx0 + idx % sw, sy0 + idx / sw);
-                        __syncthreads();
+                        T::sync();
                         const int cx0 = max(sx0 - 1, 0), cx1 = min(sx1, nx - 1), cy0 = max(sy0 - 1, 0), cy1 = min(sy1, ny - 1);
                         const int cw = cx1 - cx0 + 1, chh = cy1 - cy0 + 1;
-                        for (int idx = tid; idx < cw * chh; idx += ST_THREADS) {
+                        for (int idx = gtid; idx < cw * chh; idx += TT) {
                             const int x = cx0 + idx % cw, y = cy0 + idx / cw;
                             const size_t pix = (size_t)y * nx + x;
-                            if (changed[pix]) {
+                            if (CS > 1 ? __ldcg(changed + pix) : changed[pix]) {
                                 changed[pix] = 0;
                                 stamp_bounds_pixel<NV>(s, x, y);
                             }
-                            if (x >= pend[0] && x <= pend[1] && y >= pend[2] && y <= pend[3]) {
+                            if (x >= pb[0] && x <= pb[1] && y >= pb[2] && y <= pb[3]) {
                                 if (f32) stamp_fold_delta<float>(s, x, y);
                                 else stamp_fold_delta<double>(s, x, y);
                             }
                         }
-                        for (int idx = tid; idx < ny * wpr; idx += ST_THREADS) cbits[idx] = 0u;
-                        __syncthreads();
+                        for (int idx = gtid; idx < ny * wpr; idx += TT) cbits[idx] = 0u;
+                        T::sync();
                     }
                     if (tid == 0) {
                         pend[0] = pend[2] = 1 << 30;
                         pend[1] = pend[3] = -1;
                         sh_npix = 0;
-                        sh_nupd++;
+                        if (rank == 0) sh_nupd++;
                     }
                     accum = 0.0;
                 } else if (nrecalc > 0.0) {
-                    accum += sh_tile_sum;
+                    accum += tile_sum;
                 }
                 i0 = cut;
             }
-            __syncthreads();
+            T::sync();
             // ---- Silicon::addDelta, then full_image[bounds] += stamp[bounds]
-            for (int idx = tid; idx < nx * ny; idx += ST_THREADS) {
+            for (int idx = gtid; idx < nx * ny; idx += TT) {
                 const int x = idx % nx, y = idx / nx;
                 double v;
                 if (f32) {
@@ -650,10 +712,14 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
         if (tid == 0) {
             double t = 0.0;
             for (int w = 0; w < ST_THREADS / 32; ++w) t += sh_warp[w];
-            if (added_job) added_job[jid] = t;
+            if (added_job) {
+                if (CS > 1) atomicAdd(&added_job[jid], t);  // zeroed by the host
+                else added_job[jid] = t;
+            }
             if (t != 0.0) atomicAdd(added_total, t);
         }
     }
+    if (CS > 1) T::sync();  // nobody leaves while a team mate may still read its shared memory
     unsigned long long w0 = warp_sum(npoly), w1 = warp_sum(nneigh), w2 = warp_sum(nnf), w3 = warp_sum(nb9), w4 = warp_sum(ndrop);
     if (lane == 0) {
         if (w0) atomicAdd(&stats[ST_POLY], w0);
@@ -688,6 +754,81 @@ static size_t stamp_state_bytes(int nx, int ny, int nv, int dtype_bytes, StampSl
     t.cbits = take((size_t)ny * ((nx + 31) / 32) * sizeof(unsigned));  // one bit per pixel: charge since the last update
     if (sl) *sl = t;
     return off;
+}
+
+struct StampLaunch {
+    DevSensor d;
+    const B2StampJob* jobs;
+    const StampSlot* slots;
+    unsigned char* arena;
+    StampPhotons ph;
+    double nrecalc;
+    int ocx, ocy;
+    FullImage full;
+    unsigned long long* stats;
+    double *added_total, *added_job;
+    int bit_words;
+    unsigned long long* prof;
+};
+
+// one launch of k_stamp_jobs<NV, CS> over ``nw`` entries of the order table; CS > 1: thread-block clusters
+template <int NV, int CS>
+static int stamp_launch(const StampLaunch& a, const int* order, int nw, int* next, SlowRec* slow, int* pix, int teams,
+                        size_t smem, cudaStream_t st) {
+    auto kern = k_stamp_jobs<NV, CS>;
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(teams * CS));
+    cfg.blockDim = dim3(ST_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CS > 1 ? 1 : 0;
+    B2_CUDA(cudaLaunchKernelEx(&cfg, kern, a.d, a.jobs, a.slots, order, nw, next, a.arena, a.ph, a.nrecalc, a.ocx, a.ocy,
+                               a.full, a.stats, a.added_total, a.added_job, slow, pix, a.bit_words, a.prof));
+    return 0;
+}
+
+template <int CS>
+static int stamp_launch_nv(int nv, const StampLaunch& a, const int* order, int nw, int* next, SlowRec* slow, int* pix,
+                           int teams, size_t smem, cudaStream_t st) {
+    return nv == 4 ? stamp_launch<4, CS>(a, order, nw, next, slow, pix, teams, smem, st)
+                   : stamp_launch<8, CS>(a, order, nw, next, slow, pix, teams, smem, st);
+}
+
+// how many clusters of CS blocks the device runs at once
+template <int CS>
+static int stamp_max_clusters(int nv, size_t smem) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CS * 64);
+    cfg.blockDim = dim3(ST_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    cudaError_t e;
+    if (nv == 4) {
+        cudaFuncSetAttribute(k_stamp_jobs<4, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveClusters(&n, k_stamp_jobs<4, CS>, &cfg);
+    } else {
+        cudaFuncSetAttribute(k_stamp_jobs<8, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveClusters(&n, k_stamp_jobs<8, CS>, &cfg);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
 }
 
 // galsim.SiliconSensor.accumulate for a list of objects, each on its own zero stamp (fresh boundaries, the
@@ -735,8 +876,9 @@ extern "C" int b2_sensor_accumulate_stamps(b2_sensor* s, int32_t njobs, const B2
     const int grid_max = 2 * s->sm_count;
     const size_t jobs_b = up256((size_t)njobs * sizeof(B2StampJob)), slots_b = up256((size_t)njobs * sizeof(StampSlot));
     const size_t order_b = up256((size_t)njobs * sizeof(int)), added_b = up256((size_t)njobs * sizeof(double));
-    const size_t slow_b = up256((size_t)grid_max * ST_TILE * sizeof(SlowRec));
-    const size_t pix_b = up256((size_t)grid_max * ST_PIXCAP * sizeof(int));
+    // per-block lists: the blocks of the one-block-per-stamp launch, then those of the cluster launch
+    const size_t slow_b = up256((size_t)2 * grid_max * ST_TILE * sizeof(SlowRec));
+    const size_t pix_b = up256((size_t)2 * grid_max * ST_PIXCAP * sizeof(int));
     if (b2_scratch_reserve(ctx, s->stamp_meta, jobs_b + slots_b + order_b + added_b + slow_b + pix_b + 512)) return 1;
     unsigned char* m = (unsigned char*)s->stamp_meta.ptr;
     B2StampJob* djobs = (B2StampJob*)m;
@@ -748,6 +890,13 @@ extern "C" int b2_sensor_accumulate_stamps(b2_sensor* s, int32_t njobs, const B2
     int* dnext = (int*)(m + jobs_b + slots_b + order_b + added_b + slow_b + pix_b);
     unsigned long long* dprof = getenv("B2_STAMP_PROFILE") ? (unsigned long long*)(dnext + 16) : nullptr;
     if (dprof) B2_CUDA(cudaMemsetAsync(dprof, 0, 8 * sizeof(unsigned long long), st));
+    B2_CUDA(cudaMemsetAsync(dadded_job, 0, (size_t)njobs * sizeof(double), st));
+    // stamps that hold a large share of the photons go to clusters of ``cs`` blocks (B2_STAMP_CLUSTER = 1 turns that off)
+    int cs = 8;
+    if (const char* e = getenv("B2_STAMP_CLUSTER")) cs = atoi(e);
+    cs = cs >= 8 ? 8 : (cs >= 4 ? 4 : 1);
+    double heavy_cost = 2.0e5;
+    if (const char* e = getenv("B2_STAMP_HEAVY")) heavy_cost = atof(e);
     B2_CUDA(cudaMemsetAsync(s->dstats, 0, ST_N * sizeof(unsigned long long) + 64, st));
     B2_CUDA(cudaMemcpyAsync(djobs, jobs, (size_t)njobs * sizeof(B2StampJob), cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaMemcpyAsync(dorder, order.data(), (size_t)njobs * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -780,22 +929,45 @@ extern "C" int b2_sensor_accumulate_stamps(b2_sensor* s, int32_t njobs, const B2
         B2_CUDA(cudaMemcpyAsync(dslots, abs_slots.data(), (size_t)njobs * sizeof(StampSlot), cudaMemcpyHostToDevice, st));
         B2_CUDA(cudaStreamSynchronize(st));  // abs_slots / pageable staging is reused by the next wave
         slots_sent = true;
-        B2_CUDA(cudaMemsetAsync(dnext, 0, sizeof(int), st));
-        const int nw = w1 - w0;
-        const unsigned grid = (unsigned)std::min(nw, grid_max);
+        B2_CUDA(cudaMemsetAsync(dnext, 0, 8 * sizeof(int), st));
+        // the sorted list starts with the heaviest stamps: those above the threshold are the cluster launch's
+        int wh = w0;
+        int max_clusters = 0;
+        if (cs > 1) {
+            while (wh < w1 && !jobs[order[wh]].plain && cost(order[wh]) >= heavy_cost) ++wh;
+            if (wh > w0) {
+                max_clusters = cs == 8 ? stamp_max_clusters<8>(nv, smem_k) : stamp_max_clusters<4>(nv, smem_k);
+                max_clusters = std::min(max_clusters, grid_max / cs);
+                if (max_clusters < 1) wh = w0;
+            }
+        }
+        StampLaunch a{s->d, djobs, dslots, (unsigned char*)s->stamp_arena.ptr, ph, s->cfg.nrecalc, ocx, ocy, full,
+                      s->dstats, s->dadded, dadded_job, (int)bit_words, dprof};
         {
             B2_TIMED("k_stamp_jobs", st);
-            if (nv == 4) {
-                B2_CUDA(cudaFuncSetAttribute(k_stamp_jobs<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_stamp_jobs<4><<<grid, ST_THREADS, smem, st>>>(s->d, djobs, dslots, dorder + w0, nw, dnext,
-                                                               (unsigned char*)s->stamp_arena.ptr, ph, s->cfg.nrecalc, ocx, ocy,
-                                                               full, s->dstats, s->dadded, dadded_job, dslow, dpix, (int)bit_words, dprof);
-            } else {
-                B2_CUDA(cudaFuncSetAttribute(k_stamp_jobs<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_stamp_jobs<8><<<grid, ST_THREADS, smem, st>>>(s->d, djobs, dslots, dorder + w0, nw, dnext,
-                                                               (unsigned char*)s->stamp_arena.ptr, ph, s->cfg.nrecalc, ocx, ocy,
-                                                               full, s->dstats, s->dadded, dadded_job, dslow, dpix, (int)bit_words, dprof);
+            if (wh > w0) {
+                if (!s->stamp_aux) {
+                    int lo = 0, hi = 0;
+                    B2_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                    B2_CUDA(cudaStreamCreateWithPriority(&s->stamp_aux, cudaStreamNonBlocking, hi));
+                    B2_CUDA(cudaEventCreateWithFlags(&s->stamp_ev[0], cudaEventDisableTiming));
+                    B2_CUDA(cudaEventCreateWithFlags(&s->stamp_ev[1], cudaEventDisableTiming));
+                }
+                B2_CUDA(cudaEventRecord(s->stamp_ev[0], st));
+                B2_CUDA(cudaStreamWaitEvent(s->stamp_aux, s->stamp_ev[0], 0));
+                const int teams = std::min(wh - w0, max_clusters);
+                SlowRec* hslow = dslow + (size_t)grid_max * ST_TILE;
+                int* hpix = dpix + (size_t)grid_max * ST_PIXCAP;
+                int rc = cs == 8 ? stamp_launch_nv<8>(nv, a, dorder + w0, wh - w0, dnext + 4, hslow, hpix, teams, smem_k, s->stamp_aux)
+                                 : stamp_launch_nv<4>(nv, a, dorder + w0, wh - w0, dnext + 4, hslow, hpix, teams, smem_k, s->stamp_aux);
+                if (rc) return rc;
+                B2_CUDA(cudaEventRecord(s->stamp_ev[1], s->stamp_aux));
             }
+            if (w1 > wh) {
+                const int nw = w1 - wh;
+                if (stamp_launch_nv<1>(nv, a, dorder + wh, nw, dnext, dslow, dpix, std::min(nw, grid_max), smem, st)) return 1;
+            }
+            if (wh > w0) B2_CUDA(cudaStreamWaitEvent(st, s->stamp_ev[1], 0));
             B2_CHECK_LAUNCH();
         }
         w0 = w1;

@@ -22,6 +22,7 @@ scope: objects brighter than ``fft_flux_limit`` are still photon shot.
 """
 from __future__ import annotations
 
+import os
 import time
 from typing import Optional
 
@@ -30,7 +31,8 @@ import numpy as np
 from .photon_pooling import DevicePhotons, PhotonPool
 from .sensor import Image
 from .stage1 import Stage1
-from .stamp_utils import get_stamp_size
+from .sensor import STAMP_JOB_DTYPE
+from .stamp_utils import get_stamp_size, get_stamp_sizes
 
 
 class ClassicImageBuilder:
@@ -66,6 +68,15 @@ class ClassicImageBuilder:
         icx, icy = int(np.floor(r["x"] + 0.5)), int(np.floor(r["y"] + 0.5))
         return icx - size // 2, icy - size // 2, size
 
+    def all_stamp_bounds(self, nominal_flux):
+        """``stamp_bounds`` of every catalogue row at once: arrays (xmin, ymin, size)."""
+        size = get_stamp_sizes(self.rows, nominal_flux, self.noise_var, airmass=self.airmass,
+                               rawSeeing=self.rawSeeing, band=self.band, radial_tables=self.radial_tables,
+                               sersic_n=self.sersic_n, arcsec_to_pix=self.arcsec_to_pix)
+        icx = np.floor(self.rows["x"] + 0.5).astype(np.int64)
+        icy = np.floor(self.rows["y"] + 0.5).astype(np.int64)
+        return icx - size // 2, icy - size // 2, size
+
     #: photons per group of objects handed to the device at once (9 float64 arrays each)
     GROUP_PHOTONS = 1 << 27
 
@@ -87,54 +98,66 @@ class ClassicImageBuilder:
         ny, nx = arr.shape
         t0 = time.perf_counter()
         # host: which objects are drawn, on which stamps (SkipThisObject / off-image stamps, lsst_image.py:361-366)
-        bright, faint = [], []
-        n_skipped = 0
-        for j in range(self.rows.size):
-            n = int(phot_flux[j])
-            if n == 0:
-                n_skipped += 1
-                continue
-            xmin, ymin, size = self.stamp_bounds(j, float(nominal_flux[j]))
-            if max(xmin, X0) >= min(xmin + size, X0 + nx) or max(ymin, Y0) >= min(ymin + size, Y0 + ny):
-                n_skipped += 1
-                continue
-            (faint if nominal_flux[j] < self.max_flux_simple else bright).append((j, n, xmin, ymin, size))
+        xmin, ymin, size = self.all_stamp_bounds(nominal_flux)
+        on_image = (np.maximum(xmin, X0) < np.minimum(xmin + size, X0 + nx)) & \
+                   (np.maximum(ymin, Y0) < np.minimum(ymin + size, Y0 + ny))
+        drawn = np.flatnonzero((phot_flux > 0) & on_image)
+        is_faint = nominal_flux[drawn] < self.max_flux_simple
+        n_skipped = int(self.rows.size - drawn.size)
+        n_faint = int(is_faint.sum())
         t_host = time.perf_counter() - t0
+        phases = {}
+        profile = bool(os.environ.get("B2_CLASSIC_PROFILE"))  # synchronises after every phase
+
+        def lap(name, t_start):
+            if profile:
+                torch.cuda.synchronize()
+                phases[name] = phases.get(name, 0.0) + time.perf_counter() - t_start
+            return time.perf_counter()
+
+        t = time.perf_counter()
         full = torch.as_tensor(arr, device=dev).clone()
+        t = lap("upload", t)
         n_photons = 0
-        # groups: bright objects first inside a group, so that the optics run on one contiguous range
-        todo = [(o, False) for o in bright] + [(o, True) for o in faint]
-        todo.sort(key=lambda t: t[0][0])
+        # groups of consecutive objects; non-faint objects first inside a group, so that the optics run on one
+        # contiguous range
+        cum = np.concatenate([[0], np.cumsum(phot_flux[drawn])])
         k = 0
-        while k < len(todo):
-            grp, tot = [], 0
-            while k < len(todo) and (not grp or tot + todo[k][0][1] <= self.GROUP_PHOTONS):
-                grp.append(todo[k])
-                tot += todo[k][0][1]
-                k += 1
-            grp.sort(key=lambda t: t[1])  # stable: non-faint first
-            sel = np.array([o[0] for o, _ in grp], dtype=np.int64)
-            counts = np.array([o[1] for o, _ in grp], dtype=np.int64)
-            n_opt = int(sum(o[1] for o, f in grp if not f))
+        while k < drawn.size:
+            k1 = max(int(np.searchsorted(cum, cum[k] + self.GROUP_PHOTONS, side="right")) - 1, k + 1)
+            order = np.argsort(is_faint[k:k1], kind="stable") + k
+            sel = drawn[order]
+            counts = phot_flux[sel]
+            tot = int(counts.sum())
+            n_opt = int(counts[~is_faint[order]].sum())
             dp = DevicePhotons(tot, device=dev)
             self.stage1.shoot(dp, counts, seed=self.seed, photon_offset=n_photons, select=sel)
             if self.stage1.cdf is None:
                 dp.wavelength.fill_(self.wlen_eff)  # monochromatic at the band's effective wavelength
+            t = lap("stage1", t)
             if n_opt:
                 self.pool.trace(dp, n_opt)
+            t = lap("optics", t)
             dp._has.update(dxdz=True, dydz=True)
-            jobs, p0 = [], 0
-            for (j, n, xmin, ymin, size), is_faint in grp:
-                jobs.append((p0, n, xmin, ymin, size, size, int(is_faint)))
-                p0 += n
+            jobs = np.zeros(sel.size, dtype=STAMP_JOB_DTYPE)
+            jobs["p0"][1:] = np.cumsum(counts)[:-1]
+            jobs["n"] = counts
+            jobs["xmin"], jobs["ymin"] = xmin[sel], ymin[sel]
+            jobs["nx"] = jobs["ny"] = size[sel]
+            jobs["plain"] = is_faint[order]
             if n_opt < tot:  # faint objects carry no slopes: the plain jobs do not read them
                 dp.dxdz[n_opt:].zero_()
                 dp.dydz[n_opt:].zero_()
             sensor.accumulate_stamps(jobs, dp, full, X0, Y0, want_stats=False)
+            t = lap("stamps", t)
             n_photons += tot
+            k = k1
         arr[:, :] = full.cpu().numpy()
-        self.stats = {"phot": len(bright), "faint": len(faint), "skipped": n_skipped, "photons": n_photons,
-                      "seconds": time.perf_counter() - t0, "host_setup_seconds": t_host}
+        lap("read_back", t)
+        self.stats = {"phot": int(drawn.size) - n_faint, "faint": n_faint, "skipped": n_skipped,
+                      "photons": n_photons, "seconds": time.perf_counter() - t0, "host_setup_seconds": t_host}
+        if profile:
+            self.stats["phases"] = phases
         return self.stats
 
     def build_per_object(self, image: Image, nominal_flux, phot_flux=None, rng=None):

@@ -26,6 +26,11 @@ from . import _abi, _lib
 from .context import OpticsContext
 from .treerings import RadialTable
 
+#: numpy layout of ``B2StampJob`` (include/imsim_b200.h)
+STAMP_JOB_DTYPE = np.dtype([("p0", "<i8"), ("n", "<i8"), ("xmin", "<i4"), ("ymin", "<i4"), ("nx", "<i4"),
+                            ("ny", "<i4"), ("plain", "<i4"), ("pad", "<i4")])
+assert STAMP_JOB_DTYPE.itemsize == C.sizeof(_abi.B2StampJob)
+
 
 class Image:
     """Minimal ``galsim.Image`` stand-in: ``array`` (ny, nx) + integer origin."""
@@ -356,11 +361,14 @@ class SiliconSensor:
         Returns the stats (``added_flux`` summed over the stamps) and, if asked, the flux per job."""
         import torch
 
-        jobs = list(jobs)
-        arr = (_abi.B2StampJob * max(len(jobs), 1))()
-        for k, j in enumerate(jobs):
-            arr[k].p0, arr[k].n, arr[k].xmin, arr[k].ymin, arr[k].nx, arr[k].ny = (int(v) for v in j[:6])
-            arr[k].plain = int(bool(j[6])) if len(j) > 6 else 0
+        if isinstance(jobs, np.ndarray) and jobs.dtype == STAMP_JOB_DTYPE:
+            arr = np.ascontiguousarray(jobs)
+        else:
+            jobs = list(jobs)
+            arr = np.zeros(len(jobs), dtype=STAMP_JOB_DTYPE)
+            for k, j in enumerate(jobs):
+                arr[k] = tuple(int(v) for v in j[:6]) + (int(bool(j[6])) if len(j) > 6 else 0, 0)
+        jobs = arr
         if not (full.is_cuda and full.dim() == 2 and full.is_contiguous() and full.dtype in (torch.float32, torch.float64)):
             raise _lib.B2Error("accumulate_stamps needs a contiguous 2-d float32 / float64 CUDA tensor as full image")
         n = len(photons)
@@ -369,7 +377,7 @@ class SiliconSensor:
         stats = _abi.B2AccumStats() if want_stats else None
         added = np.zeros(max(len(jobs), 1)) if want_added else None
         _lib.check(self._lib.b2_sensor_accumulate_stamps(
-            self._h, len(jobs), C.cast(arr, C.c_void_p), n, _lib.ptr(photons.x), _lib.ptr(photons.y),
+            self._h, len(jobs), C.c_void_p(arr.ctypes.data if len(jobs) else None), n, _lib.ptr(photons.x), _lib.ptr(photons.y),
             _lib.ptr(photons.dxdz) if has_ang else None, _lib.ptr(photons.dydz) if has_ang else None,
             _lib.ptr(photons.wavelength) if has_wl else None, _lib.ptr(photons.flux), _lib.ptr(rand4),
             self._seed & 0xFFFFFFFFFFFFFFFF, self._photon_offset, int(orig_center[0]), int(orig_center[1]),

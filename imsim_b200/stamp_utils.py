@@ -164,3 +164,60 @@ def get_stamp_size(row, nominal_flux, noise_var, Nmax=NMAX, pixel_scale=PIXEL_SC
     if int(row["kind"]) == _abi.PROF_DELTA:
         return get_star_stamp_size(nominal_flux, noise_var, Nmax, pixel_scale, airmass, rawSeeing, band)
     return get_gal_stamp_size(row, nominal_flux, noise_var, radial_tables, sersic_n, Nmax, pixel_scale, arcsec_to_pix)
+
+
+def get_stamp_sizes(rows, nominal_flux, noise_var, Nmax=NMAX, pixel_scale=PIXEL_SCALE, airmass=None, rawSeeing=None,
+                    band=None, radial_tables=None, sersic_n=None, arcsec_to_pix=None):
+    """``get_stamp_size`` for a whole catalogue at once (same sizes, object for object): stars share the few
+    e-folding levels of the folding threshold, galaxies take the batched singular values of their matrices,
+    and only the bright ones (the growing loop of stamp_utils.py:262-330) go through the per-object code."""
+    from .stage1 import RADIAL_TMAX
+
+    rows = np.asarray(rows)
+    flux = np.asarray(nominal_flux, dtype=np.float64)
+    n = rows.size
+    out = np.full(n, 32, dtype=np.int64)
+    kind = rows["kind"].astype(np.int64)
+    live = flux >= TINY_FLUX
+    star = live & (kind == _abi.PROF_DELTA)
+    if star.any():
+        with np.errstate(divide="ignore"):
+            ft = noise_var / flux[star]
+        level = np.where((ft >= FT_DEFAULT) | (ft == 0), np.inf, np.floor(np.log(np.where(ft > 0, ft, 1.0))))
+        sizes = np.empty(level.size, dtype=np.int64)
+        for lv in np.unique(level):
+            pick = level == lv
+            # any flux of the level gives the level's size
+            f = float(flux[star][pick][0])
+            sizes[pick] = get_star_stamp_size(f, noise_var, Nmax, pixel_scale, airmass, rawSeeing, band)
+        out[star] = sizes
+    gal = np.flatnonzero(live & ~star)
+    if gal.size:
+        a2p = np.eye(2) / pixel_scale if arcsec_to_pix is None else np.asarray(arcsec_to_pix, float)
+        M = np.linalg.solve(a2p, np.asarray(rows["m"][gal], float).reshape(-1, 2, 2))
+        sv0 = np.linalg.svd(M, compute_uv=False)[:, 0]
+        k = kind[gal]
+        r_unit = np.zeros(gal.size)
+        rad = k == _abi.PROF_RADIAL
+        if rad.any():
+            lut = rows["lut"][gal][rad].astype(np.int64)
+            per_lut = {}
+            for u in np.unique(lut):
+                tab = radial_tables[int(u)]
+                t = np.linspace(0.0, RADIAL_TMAX, tab.size)
+                per_lut[int(u)] = max(float(np.interp(-np.log(FT_DEFAULT), t, tab)), STEPK_MINIMUM_HLR)
+            r_unit[rad] = [per_lut[int(u)] for u in lut]
+        r_unit[k == _abi.PROF_KNOTS] = gaussian_radius(1.0 / 1.1774100225154747, FT_DEFAULT)
+        r_unit[k == _abi.PROF_GAUSSIAN] = gaussian_radius(1.0, FT_DEFAULT)
+        box = k == _abi.PROF_BOX
+        if box.any():
+            r_unit[box] = 0.5 * np.hypot(rows["p0"][gal][box], rows["p1"][gal][box])
+        nn = np.ceil(2.0 * np.hypot(r_unit * sv0, _double_gaussian_radius()) / pixel_scale).astype(np.int64)
+        size = nn + (nn % 2)
+        bright = (flux[gal] > 10 * size ** 2) | (size > Nmax)
+        for i in np.flatnonzero(bright):
+            j = gal[i]
+            size[i] = get_gal_stamp_size(rows[j], float(flux[j]), noise_var, radial_tables, sersic_n, Nmax,
+                                         pixel_scale, arcsec_to_pix)
+        out[gal] = size
+    return out

@@ -47,3 +47,17 @@ def test_galaxy_stamp_sizes():
     bright = get_gal_stamp_size(rows[1], 1e9, 800.0, **kw)
     assert bright > s[1] and bright <= 4096
     assert FT_DEFAULT == 5e-3 and _abi.PROF_RADIAL == 2
+
+
+def test_catalogue_wide_stamp_sizes_equal_the_per_object_ones():
+    from imsim_b200.stamp_utils import get_stamp_sizes
+    from imsim_b200.visit import synthetic_catalog
+
+    for n_obj, total in ((300, 5e7), (120, 5e10)):
+        cat = synthetic_catalog(n_obj, 4096, 4004, seed=7, total_photons=total)
+        rows, flux = cat.build()
+        flux = flux.astype(float)
+        flux[::17] = 3.0  # tiny fluxes take the fixed 32-pixel stamp
+        kw = dict(radial_tables=cat.radial_tables(), sersic_n=cat.sersic_n)
+        want = [get_stamp_size(rows[j], float(flux[j]), 800.0, **kw) for j in range(rows.size)]
+        np.testing.assert_array_equal(get_stamp_sizes(rows, flux, 800.0, **kw), want)

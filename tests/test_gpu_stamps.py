@@ -52,10 +52,23 @@ def _device_photons(x, y, wl, flux, dxdz, dydz):
     return dp
 
 
+#: one thread block per stamp; every silicon stamp on a cluster of 8 / of 4 blocks (B2_STAMP_HEAVY = 1: all are "heavy")
+TEAMS = [("1", None), ("8", "1"), ("4", "1")]
+
+
+def _team_env(monkeypatch, cluster, heavy):
+    monkeypatch.setenv("B2_STAMP_CLUSTER", cluster)
+    if heavy is not None:
+        monkeypatch.setenv("B2_STAMP_HEAVY", heavy)
+
+
+@pytest.mark.parametrize("cluster,heavy", TEAMS)
 @pytest.mark.parametrize("model,nrecalc,dtype", [("lsst_itl_50_4", 10000, np.float32), ("lsst_e2v_50_8", 3000, np.float64),
                                                  ("lsst_itl_50_4", 0, np.float32)])
-def test_stamps_equal_host_driven_accumulate(model, nrecalc, dtype):
+def test_stamps_equal_host_driven_accumulate(model, nrecalc, dtype, cluster, heavy, monkeypatch):
     import torch
+
+    _team_env(monkeypatch, cluster, heavy)
 
     from imsim_b200 import PhotonArray
 
@@ -136,3 +149,42 @@ def test_stamps_leave_the_bound_image_alone():
     sensor.accumulate_stamps(jobs, _device_photons(x, y, wl, flux, dxdz, dydz), full)
     sensor.accumulate(pa, img, resume=True)
     assert img.array.sum() == before.sum() + n
+
+
+@pytest.mark.parametrize("cluster,heavy", [("1", None), ("8", "1")])
+def test_one_wide_stamp_with_more_charged_pixels_than_the_list_holds(cluster, heavy, monkeypatch):
+    """A flat-ish 400 x 400 stamp updated once after 8e5 electrons: far more charged pixels than the per-block list
+    takes, so the update scans the box of the pending charge -- same image as the host-driven accumulate; a second,
+    bright star on a small stamp takes the list path beside it."""
+    import torch
+
+    from imsim_b200 import PhotonArray
+
+    _team_env(monkeypatch, cluster, heavy)
+    rng = np.random.default_rng(12)
+    n1, n2 = 1_000_000, 150_000
+    x = np.concatenate([rng.uniform(0.6, 400.4, n1), 500.0 + rng.normal(0, 1.2, n2)])
+    y = np.concatenate([rng.uniform(0.6, 400.4, n1), 40.0 + rng.normal(0, 1.2, n2)])
+    n = n1 + n2
+    wl = rng.uniform(400.0, 1000.0, n)
+    flux = np.ones(n)
+    dxdz, dydz = rng.normal(0, 0.15, n), rng.normal(0, 0.15, n)
+    jobs = [(0, n1, 1, 1, 400, 400, 0), (n1, n2, 480, 20, 40, 40, 0)]
+    nrecalc = 800_000
+    sensor = _sensor("lsst_itl_50_4", nrecalc)
+    full = torch.zeros((420, 560), dtype=torch.float32, device="cuda:0")
+    stats = sensor.accumulate_stamps(jobs, _device_photons(x, y, wl, flux, dxdz, dydz), full, 1, 1)
+    ref_sensor = _sensor("lsst_itl_50_4", nrecalc)
+    ref_sensor.updateRNG(11)
+    want = np.zeros((420, 560), np.float32)
+    n_upd, p_off = 0, 0
+    for p0, m, xmin, ymin, nx, ny, _ in jobs:
+        sl = slice(p0, p0 + m)
+        stamp = Image(np.zeros((ny, nx), np.float32), xmin, ymin)
+        pa = PhotonArray(m, x=x[sl].copy(), y=y[sl].copy(), flux=flux[sl].copy(), dxdz=dxdz[sl].copy(),
+                         dydz=dydz[sl].copy(), wavelength=wl[sl].copy())
+        ref_sensor.accumulate(pa, stamp)
+        n_upd += ref_sensor.last_stats.n_updates
+        want[ymin - 1:ymin - 1 + ny, xmin - 1:xmin - 1 + nx] += stamp.array
+    np.testing.assert_array_equal(full.cpu().numpy(), want)
+    assert stats.n_updates == n_upd and n_upd >= 1

@@ -54,7 +54,7 @@ for which, reps in (("build", 3), ("build_per_object", 1)):
     dt = time.perf_counter() - t0
     res[which] = {"seconds": dt, "photons_per_s": st["photons"] / dt, "host_setup_s": st.get("host_setup_seconds"),
                   "electrons": float(image.array.sum(dtype=np.float64)), "objects": int(rows.size),
-                  "photons": int(st["photons"])}
+                  "photons": int(st["photons"]), "phases": st.get("phases")}
     print(which, "classic pipeline: %d catalogue rows (%d phot, %d faint), %d photons: %.2f s = %.3e photons/s, %.2f ms / object; "
           "electrons %.4e" % (rows.size, st["phot"], st["faint"], st["photons"], dt, st["photons"] / dt,
                               1e3 * dt / rows.size, image.array.sum(dtype=np.float64)), "host set-up %s s" % st.get("host_setup_seconds"))
