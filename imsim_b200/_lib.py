@@ -74,6 +74,8 @@ _SIGNATURES = {
     "b2_ctx_set_stream": (C.c_int, [vp, vp]),
     "b2_ctx_synchronize": (C.c_int, [vp]),
     "b2_fma_peak": (C.c_int, [vp, C.c_int32, dp]),
+    "b2_copy_through_ring": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int32]),
+    "b2_test_round_f32": (C.c_int, [vp, C.c_int64, dp, dp]),
     "b2_timing_report": (C.c_int, [C.c_char_p, C.c_int64]),
     "b2_ctx_record_kernel_events": (C.c_int, [vp, C.c_int32]),
     "b2_ctx_kernel_ms": (C.c_int, [vp, dp, C.POINTER(C.c_int64)]),

@@ -266,7 +266,9 @@ k_update_distortions(const __grid_constant__ DevSensor s, const CT* __restrict__
 // the pixels that actually hold charge (photon pools are sparse outside star cores), in the
 // reference's (row, column) order; its boundary points live in registers and are written back once.
 // Arithmetic per visited pixel is identical to k_update_distortions (bit-identical results).
-template <typename CT, int NV>
+// ADDER: the running points are float-valued doubles rounded on the FP64 adder (bf_term); otherwise floats with
+// GalSim's conversions.  Same bits either way.
+template <typename CT, int NV, bool ADDER>
 __global__ void __launch_bounds__(256)
 k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __restrict__ charge,
                            uint8_t* __restrict__ changed) {
@@ -279,8 +281,10 @@ k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __rest
     unsigned long long* rowbits = reinterpret_cast<unsigned long long*>(sc + MAXHR * HW);  // [MAXHR]
     // the 9 x 9 distortion tables (6.5 / 11.7 KB) are read through the L1 / read-only path: every block touches
     // all of them, so they stay cached, and not staging them saves a pass and a barrier per tile
-    const float2* __restrict__ KH = s.KH;
-    const float2* __restrict__ KV = s.KV;
+    const double2* __restrict__ KH = s.KHd;
+    const double2* __restrict__ KV = s.KVd;
+    const float2* __restrict__ KHf = s.KH;
+    const float2* __restrict__ KVf = s.KV;
     const int tid = threadIdx.y * TX + threadIdx.x;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
     const int nx = s.nx, ny = s.ny;
@@ -368,47 +372,68 @@ k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __rest
             const int tx = sid & 31, ty = sid >> 5;
             const int x = x0 + tx, y = y0 + ty;
             if (phase == 0) {
+                // the points live in registers as float-valued doubles (bf_term): widened once, narrowed once
                 float2* hp = s.H + Hidx(s, x, y);
-                float2 h[NV + 2];
+                double hx[NV + 2], hy[NV + 2];
 #pragma unroll
-                for (int k = 0; k < NV + 2; ++k) h[k] = hp[k];
+                for (int k = 0; k < NV + 2; ++k) {
+                    const float2 t = hp[k];
+                    hx[k] = (double)t.x;
+                    hy[k] = (double)t.y;
+                }
                 while (bits) {
                     const int pos = __ffsll((long long)bits) - 1;
                     bits &= bits - 1;
                     const int dj = pos >> 3, di = pos & 7;
                     const double c = sc[(ty + dj) * HW + tx + 1 + di];
-                    const float2* kh = KH + ((q + 1 - dj + cyk) * s.nx9 + (q - di + cxk)) * (NV + 2);
+                    const int kk = ((q + 1 - dj + cyk) * s.nx9 + (q - di + cxk)) * (NV + 2);
 #pragma unroll
                     for (int k = 0; k < NV + 2; ++k) {
-                        float2 d = __ldg(kh + k);
-                        h[k].x = (float)__dadd_rn((double)h[k].x, __dmul_rn((double)d.x, c));
-                        h[k].y = (float)__dadd_rn((double)h[k].y, __dmul_rn((double)d.y, c));
+                        if (ADDER) {
+                            const double2 d = __ldg(KH + kk + k);
+                            bf_term(hx[k], d.x, c);
+                            bf_term(hy[k], d.y, c);
+                        } else {
+                            const float2 d = __ldg(KHf + kk + k);
+                            hx[k] = (double)(float)__dadd_rn(hx[k], __dmul_rn((double)d.x, c));
+                            hy[k] = (double)(float)__dadd_rn(hy[k], __dmul_rn((double)d.y, c));
+                        }
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < NV + 2; ++k) hp[k] = h[k];
+                for (int k = 0; k < NV + 2; ++k) hp[k] = make_float2((float)hx[k], (float)hy[k]);
                 if (y < ny) changed[(size_t)y * nx + x] = 1;
                 if (y > 0) changed[(size_t)(y - 1) * nx + x] = 1;
             } else {
                 float2* vp = s.V + Vidx(s, x, y);
-                float2 v[NV];
+                double vx[NV], vy[NV];
 #pragma unroll
-                for (int k = 0; k < NV; ++k) v[k] = vp[k];
+                for (int k = 0; k < NV; ++k) {
+                    const float2 t = vp[k];
+                    vx[k] = (double)t.x;
+                    vy[k] = (double)t.y;
+                }
                 while (bits) {
                     const int pos = __ffsll((long long)bits) - 1;
                     bits &= bits - 1;
                     const int dj = (pos >> 3) + 1, di = pos & 7;
                     const double c = sc[(ty + dj) * HW + tx + di];
-                    const float2* kv = KV + ((q + 1 - dj + cyk) * s.nx9 + (q + 1 - di + cxk)) * NV;
+                    const int kk = ((q + 1 - dj + cyk) * s.nx9 + (q + 1 - di + cxk)) * NV;
 #pragma unroll
                     for (int k = 0; k < NV; ++k) {
-                        float2 d = __ldg(kv + k);
-                        v[k].x = (float)__dadd_rn((double)v[k].x, __dmul_rn((double)d.x, c));
-                        v[k].y = (float)__dadd_rn((double)v[k].y, __dmul_rn((double)d.y, c));
+                        if (ADDER) {
+                            const double2 d = __ldg(KV + kk + k);
+                            bf_term(vx[k], d.x, c);
+                            bf_term(vy[k], d.y, c);
+                        } else {
+                            const float2 d = __ldg(KVf + kk + k);
+                            vx[k] = (double)(float)__dadd_rn(vx[k], __dmul_rn((double)d.x, c));
+                            vy[k] = (double)(float)__dadd_rn(vy[k], __dmul_rn((double)d.y, c));
+                        }
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < NV; ++k) vp[k] = v[k];
+                for (int k = 0; k < NV; ++k) vp[k] = make_float2((float)vx[k], (float)vy[k]);
                 if (x < nx) changed[(size_t)y * nx + x] = 1;
                 if (x > 0) changed[(size_t)y * nx + x - 1] = 1;
             }
@@ -756,6 +781,13 @@ extern "C" int b2_sensor_create(b2_ctx* ctx, const B2SensorConfig* cfg, const do
             }
     if (dev_upload(ctx, s->owned, KH.data(), KH.size(), &d.KH)) return 1;
     if (dev_upload(ctx, s->owned, KV.data(), KV.size(), &d.KV)) return 1;
+    {
+        std::vector<double2> KHd(KH.size()), KVd(KV.size());
+        for (size_t k = 0; k < KH.size(); ++k) KHd[k] = make_double2((double)KH[k].x, (double)KH[k].y);
+        for (size_t k = 0; k < KV.size(); ++k) KVd[k] = make_double2((double)KV[k].x, (double)KV[k].y);
+        if (dev_upload(ctx, s->owned, KHd.data(), KHd.size(), &d.KHd)) return 1;
+        if (dev_upload(ctx, s->owned, KVd.data(), KVd.size(), &d.KVd)) return 1;
+    }
     d.ntr = cfg->n_treering;
     if (d.ntr > 2) {
         if (dev_upload(ctx, s->owned, tr_r, (size_t)d.ntr, &d.tr_r)) return 1;
@@ -975,12 +1007,13 @@ static int launch_update_tiled(b2_sensor* s, const CT* charge) {
     size_t smem = (size_t)24 * 64 * sizeof(double) + 24 * sizeof(unsigned long long);
     dim3 block(32, 8, 1);
     dim3 grid((d.nx + 1 + 31) / 32, (d.ny + 1 + 7) / 8, 1);
+    static const bool adder = getenv("B2_UPDATE_ADDER") ? atoi(getenv("B2_UPDATE_ADDER")) != 0 : true;
     if (d.nv == 4) {
-        if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(k_update_distortions_tiled<CT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_update_distortions_tiled<CT, 4><<<grid, block, smem, st>>>(d, charge, s->changed);
+        if (adder) k_update_distortions_tiled<CT, 4, true><<<grid, block, smem, st>>>(d, charge, s->changed);
+        else k_update_distortions_tiled<CT, 4, false><<<grid, block, smem, st>>>(d, charge, s->changed);
     } else {
-        if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(k_update_distortions_tiled<CT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_update_distortions_tiled<CT, 8><<<grid, block, smem, st>>>(d, charge, s->changed);
+        if (adder) k_update_distortions_tiled<CT, 8, true><<<grid, block, smem, st>>>(d, charge, s->changed);
+        else k_update_distortions_tiled<CT, 8, false><<<grid, block, smem, st>>>(d, charge, s->changed);
     }
     B2_CHECK_LAUNCH();
     return 0;
@@ -1359,4 +1392,47 @@ extern "C" int b2_sensor_get_pixel(b2_sensor* s, int32_t ix, int32_t iy, double*
     B2_CUDA(cudaMemcpyAsync(bounds, dp + 2 * npoly, 64, cudaMemcpyDeviceToHost, ctx->stream));
     B2_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+// ---- test aid: the rounding primitive of the boundary update
+__global__ void k_round_f32(int64_t n, const double* __restrict__ in, double* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = round_to_f32(in[i]);
+}
+
+extern "C" int b2_test_round_f32(b2_ctx* ctx, int64_t n, const double* in, double* out) {
+    B2_REQUIRE(ctx && n >= 0 && (n == 0 || (in && out)), "b2_test_round_f32: null argument");
+    if (n == 0) return 0;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    double* d = nullptr;
+    B2_CUDA(cudaMalloc(&d, 2 * (size_t)n * sizeof(double)));
+    B2_CUDA(cudaMemcpyAsync(d, in, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    k_round_f32<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, d, d + n);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    B2_CUDA(e);
+    return 0;
+}
+
+extern "C" int b2_copy_through_ring(b2_ctx* ctx, void* host, void* device, int64_t bytes, int32_t to_device) {
+    B2_REQUIRE(ctx && bytes >= 0 && (bytes == 0 || (host && device)), "b2_copy_through_ring: null argument");
+    B2_REQUIRE(bytes % 8 == 0, "b2_copy_through_ring: the size must be a multiple of 8 bytes");
+    if (bytes == 0) return 0;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    if (bytes < ((int64_t)1 << 20) || getenv("B2_IMAGE_PLAIN_COPY")) {
+        B2_CUDA(cudaMemcpyAsync(to_device ? device : host, to_device ? host : device, (size_t)bytes,
+                                to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+        B2_CUDA(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
+    if (to_device) {
+        const double* hin[1] = {(const double*)host};
+        double* din[1] = {(double*)device};
+        return b2_pipe_run(ctx, bytes / 8, 1, hin, din, 0, nullptr, nullptr, nullptr);
+    }
+    double* hout[1] = {(double*)host};
+    const double* dout[1] = {(const double*)device};
+    return b2_pipe_run(ctx, bytes / 8, 0, nullptr, nullptr, 1, hout, dout, nullptr);
 }

@@ -19,6 +19,7 @@ struct DevSensor {
     const double *abs_w, *abs_l;
     double abs_x0, abs_inv_dx;  // uniform absorption table: direct index (inv_dx = 0: binary search)
     const float2 *KH, *KV;
+    const double2 *KHd, *KVd;  // the same tables widened to double (the boundary update adds in double)
     float2 *H, *V;
     double *inner, *outer;
     double* delta;
@@ -51,6 +52,24 @@ struct b2_sensor {
     cudaStream_t stamp_aux = nullptr;  // stamps.cu: the cluster launch runs beside the one-block-per-stamp launch
     cudaEvent_t stamp_ev[2] = {nullptr, nullptr};
 };
+
+// x rounded to the nearest float (ties to even, float denormals included) and kept as a double: (double)(float)x
+// without the two trips through the conversion unit (16 lanes / clock / SM).  Adding 1.5 * 2^(e+29), e the exponent
+// of x, pushes the bits below float precision out of the double's significand under the FP64 adder's own
+// round-to-nearest-even (the sum stays inside the magic's binade for either sign of x); subtracting it again is
+// exact.  Below 2^-126 the magic is pinned so that the spacing is the float denormals' 2^-149.  (No float overflow
+// handling: boundary points are pixel fractions; -0.0 returns +0.0.)
+__device__ __forceinline__ double round_to_f32(double x) {
+    const int e = max(__double2hiint(x) & 0x7ff00000, 897 << 20);
+    const double m = __hiloint2double(e + ((29 << 20) | 0x00080000), 0);
+    return __dsub_rn(__dadd_rn(x, m), m);
+}
+
+// one term of Silicon::updatePixelDistortions on a boundary coordinate held as a float-valued double:
+// p = float(double(p) + double(d) * c), GalSim's float += float * double
+__device__ __forceinline__ void bf_term(double& p, double d, double c) {
+    p = round_to_f32(__dadd_rn(p, __dmul_rn(d, c)));
+}
 
 enum { ST_POLY = 0, ST_NEIGH = 1, ST_NOTFOUND = 2, ST_B9 = 3, ST_DROP = 4, ST_N = 8 };
 

@@ -185,8 +185,8 @@ __device__ __forceinline__ bool stamp_slot_owner(unsigned long long W, int x, in
 
 // the gather of slot (x, y): boundary points in registers, one delta load per charged pixel, one store at the end
 template <int NV>
-__device__ __forceinline__ void stamp_slot_apply(const DevSensor& s, const float2* __restrict__ KH,
-                                                 const float2* __restrict__ KV, unsigned long long W, int x, int y) {
+__device__ __forceinline__ void stamp_slot_apply(const DevSensor& s, const double2* __restrict__ KH,
+                                                 const double2* __restrict__ KV, unsigned long long W, int x, int y) {
     const int nx = s.nx, ny = s.ny;
     const int c0 = x - 4, r0 = y - 4;
     const int cxk = (s.nx9 - 1) / 2, cyk = (s.ny9 - 1) / 2;
@@ -194,10 +194,15 @@ __device__ __forceinline__ void stamp_slot_apply(const DevSensor& s, const float
     if (x < nx) {
         // horizontal boundary: all rows of the window, columns x-3 .. x+3 (not column c0)
         unsigned long long Wh = W & 0xfefefefefefefefeull;
+        // points as float-valued doubles (bf_term, sensor_device.cuh): widened once, narrowed once
         float2* h = s.H + Hidx(s, x, y);
-        float2 hp[NV + 2];
+        double hx[NV + 2], hy[NV + 2];
 #pragma unroll
-        for (int k = 0; k <= NV + 1; ++k) hp[k] = h[k];
+        for (int k = 0; k <= NV + 1; ++k) {
+            const float2 t = h[k];
+            hx[k] = (double)t.x;
+            hy[k] = (double)t.y;
+        }
         bool any = false;
         while (Wh) {
             const int b = __ffsll((long long)Wh) - 1;
@@ -206,26 +211,30 @@ __device__ __forceinline__ void stamp_slot_apply(const DevSensor& s, const float
             const double c = __ldcg(charge + (size_t)j * nx + i);
             if (c == 0.0) continue;
             any = true;
-            const float2* kh = KH + ((y - j + cyk) * s.nx9 + (x - i + cxk)) * (NV + 2);
+            const double2* kh = KH + ((y - j + cyk) * s.nx9 + (x - i + cxk)) * (NV + 2);
 #pragma unroll
             for (int k = 0; k <= NV + 1; ++k) {
-                const float2 d = kh[k];
-                hp[k].x = (float)__dadd_rn((double)hp[k].x, __dmul_rn((double)d.x, c));
-                hp[k].y = (float)__dadd_rn((double)hp[k].y, __dmul_rn((double)d.y, c));
+                const double2 d = kh[k];
+                bf_term(hx[k], d.x, c);
+                bf_term(hy[k], d.y, c);
             }
         }
         if (any) {
 #pragma unroll
-            for (int k = 0; k <= NV + 1; ++k) h[k] = hp[k];
+            for (int k = 0; k <= NV + 1; ++k) h[k] = make_float2((float)hx[k], (float)hy[k]);
         }
     }
     if (y < ny) {
         // vertical boundary: rows y-3 .. y+3 (not row r0), all columns of the window
         unsigned long long Wv = W & ~0xffull;
         float2* v = s.V + Vidx(s, x, y);
-        float2 vp[NV];
+        double vx[NV], vy[NV];
 #pragma unroll
-        for (int k = 0; k < NV; ++k) vp[k] = v[k];
+        for (int k = 0; k < NV; ++k) {
+            const float2 t = v[k];
+            vx[k] = (double)t.x;
+            vy[k] = (double)t.y;
+        }
         bool any = false;
         while (Wv) {
             const int b = __ffsll((long long)Wv) - 1;
@@ -234,17 +243,17 @@ __device__ __forceinline__ void stamp_slot_apply(const DevSensor& s, const float
             const double c = __ldcg(charge + (size_t)j * nx + i);
             if (c == 0.0) continue;
             any = true;
-            const float2* kv = KV + ((y - j + cyk) * s.nx9 + (x - i + cxk)) * NV;
+            const double2* kv = KV + ((y - j + cyk) * s.nx9 + (x - i + cxk)) * NV;
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
-                const float2 d = kv[k];
-                vp[k].x = (float)__dadd_rn((double)vp[k].x, __dmul_rn((double)d.x, c));
-                vp[k].y = (float)__dadd_rn((double)vp[k].y, __dmul_rn((double)d.y, c));
+                const double2 d = kv[k];
+                bf_term(vx[k], d.x, c);
+                bf_term(vy[k], d.y, c);
             }
         }
         if (any) {
 #pragma unroll
-            for (int k = 0; k < NV; ++k) v[k] = vp[k];
+            for (int k = 0; k < NV; ++k) v[k] = make_float2((float)vx[k], (float)vy[k]);
         }
     }
 }
@@ -303,7 +312,7 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
              unsigned long long* __restrict__ stats, double* __restrict__ added_total, double* __restrict__ added_job,
              SlowRec* __restrict__ slow_scratch, int* __restrict__ pix_scratch, int smem_bit_words,
              unsigned long long* __restrict__ prof) {
-    extern __shared__ float2 sK[];  // KH then KV
+    extern __shared__ double2 sK[];  // KH then KV, widened to double (bf_term)
     __shared__ DevSensor s;
     __shared__ int sh_job, sh_cut, pend[4];  // pend: box of the pixels holding charge since the last update
     __shared__ unsigned sh_nslow, sh_nupd, sh_npix, sh_nq;
@@ -316,10 +325,10 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int gtid = (int)rank * ST_THREADS + tid;
     const int nKH = base.nx9 * base.ny9 * (NV + 2), nKV = base.nx9 * base.ny9 * NV;
-    for (int k = tid; k < nKH; k += ST_THREADS) sK[k] = base.KH[k];
-    for (int k = tid; k < nKV; k += ST_THREADS) sK[nKH + k] = base.KV[k];
-    const float2* KH = sK;
-    const float2* KV = sK + nKH;
+    for (int k = tid; k < nKH; k += ST_THREADS) sK[k] = base.KHd[k];
+    for (int k = tid; k < nKV; k += ST_THREADS) sK[nKH + k] = base.KVd[k];
+    const double2* KH = sK;
+    const double2* KV = sK + nKH;
     SlowRec* slow = slow_scratch + (size_t)blockIdx.x * ST_TILE;
     int* pixlist = pix_scratch + (size_t)blockIdx.x * ST_PIXCAP;
     unsigned npoly = 0, nneigh = 0, nnf = 0, nb9 = 0, ndrop = 0;
@@ -654,7 +663,7 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
                         const int sy0 = max(pb[2] - q, 0), sy1 = min(pb[3] + q + 1, ny);
                         const int sw = sx1 - sx0 + 1, shh = sy1 - sy0 + 1;
                         for (int idx = gtid; idx < sw * shh; idx += TT)
-                            stamp_update_slot<NV>(s, KH, KV, changed, sx0 + idx % sw, sy0 + idx / sw);
+                            stamp_update_slot<NV>(s, s.KH, s.KV, changed, sx0 + idx % sw, sy0 + idx / sw);
                         T::sync();
                         const int cx0 = max(sx0 - 1, 0), cx1 = min(sx1, nx - 1), cy0 = max(sy0 - 1, 0), cy1 = min(sy1, ny - 1);
                         const int cw = cx1 - cx0 + 1, chh = cy1 - cy0 + 1;
@@ -902,12 +911,13 @@ extern "C" int b2_sensor_accumulate_stamps(b2_sensor* s, int32_t njobs, const B2
     B2_CUDA(cudaMemcpyAsync(dorder, order.data(), (size_t)njobs * sizeof(int), cudaMemcpyHostToDevice, st));
     const StampPhotons ph{x, y, dxdz, dydz, wl, flux, rand4, n, seed, offset};
     const FullImage full{full_pixels, full_xmin, full_ymin, full_nx, full_ny, dtype_bytes};
-    const size_t smem_k = (size_t)s->d.nx9 * s->d.ny9 * (2 * nv + 2) * sizeof(float2);
+    const size_t smem_k = (size_t)s->d.nx9 * s->d.ny9 * (2 * nv + 2) * sizeof(double2);
     // occupancy bitmap of the stamp in flight in shared memory: two blocks per SM share ~220 KB
     size_t bit_words = 0;
     for (int j = 0; j < njobs; ++j)
         if (!jobs[j].plain) bit_words = std::max(bit_words, (size_t)((jobs[j].nx + 31) / 32) * jobs[j].ny);
-    bit_words = std::min(bit_words, (size_t)(80 * 1024) / sizeof(unsigned));
+    // (two blocks per SM: ~110 KB each, minus the tables and ~18 KB of static lists)
+    bit_words = std::min(bit_words, ((size_t)92 * 1024 - smem_k) / sizeof(unsigned));
     const size_t smem = smem_k + bit_words * sizeof(unsigned);
     // waves: consecutive jobs of the sorted list whose stamp states fit the arena together
     int w0 = 0;

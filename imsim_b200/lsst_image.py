@@ -28,6 +28,7 @@ from typing import Optional
 
 import numpy as np
 
+from . import _lib
 from .photon_pooling import DevicePhotons, PhotonPool
 from .sensor import Image
 from .stage1 import Stage1
@@ -67,6 +68,23 @@ class ClassicImageBuilder:
                               arcsec_to_pix=self.arcsec_to_pix)
         icx, icy = int(np.floor(r["x"] + 0.5)), int(np.floor(r["y"] + 0.5))
         return icx - size // 2, icy - size // 2, size
+
+    def _to_device(self, arr, dev):
+        """The caller's (pageable) full image as a device tensor, through the pinned ring."""
+        import torch
+
+        full = torch.empty(arr.shape, dtype=torch.float32 if arr.dtype == np.float32 else torch.float64, device=dev)
+        if arr.flags.c_contiguous and arr.nbytes % 8 == 0 and arr.dtype in (np.float32, np.float64):
+            _lib.check(_lib.load().b2_copy_through_ring(self.ctx.handle, arr.ctypes.data, full.data_ptr(), arr.nbytes, 1))
+        else:
+            full.copy_(torch.as_tensor(np.ascontiguousarray(arr)))
+        return full
+
+    def _to_host(self, full, arr):
+        if arr.flags.c_contiguous and arr.nbytes % 8 == 0 and arr.dtype in (np.float32, np.float64):
+            _lib.check(_lib.load().b2_copy_through_ring(self.ctx.handle, arr.ctypes.data, full.data_ptr(), arr.nbytes, 0))
+        else:
+            arr[:, :] = full.cpu().numpy()
 
     def all_stamp_bounds(self, nominal_flux):
         """``stamp_bounds`` of every catalogue row at once: arrays (xmin, ymin, size)."""
@@ -116,7 +134,7 @@ class ClassicImageBuilder:
             return time.perf_counter()
 
         t = time.perf_counter()
-        full = torch.as_tensor(arr, device=dev).clone()
+        full = self._to_device(arr, dev)
         t = lap("upload", t)
         n_photons = 0
         # groups of consecutive objects; non-faint objects first inside a group, so that the optics run on one
@@ -152,7 +170,7 @@ class ClassicImageBuilder:
             t = lap("stamps", t)
             n_photons += tot
             k = k1
-        arr[:, :] = full.cpu().numpy()
+        self._to_host(full, arr)
         lap("read_back", t)
         self.stats = {"phot": int(drawn.size) - n_faint, "faint": n_faint, "skipped": n_skipped,
                       "photons": n_photons, "seconds": time.perf_counter() - t0, "host_setup_seconds": t_host}

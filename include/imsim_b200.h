@@ -319,6 +319,9 @@ int b2_ctx_synchronize(b2_ctx* ctx);
    non-tensor FMA rate (fp64 != 0: double, else float) in TFLOP/s.  The roofline
    denominator of the compute-bound trace kernel (MEASURED_PEAKS.json has none). */
 int b2_fma_peak(b2_ctx* ctx, int32_t fp64, double* tflops);
+/* test aid: out[i] = the device's round_to_f32(in[i]) -- the FP64-adder rounding to float precision the boundary
+   update uses instead of double -> float -> double conversions; must equal (double)(float)in[i] (host arrays) */
+int b2_test_round_f32(b2_ctx* ctx, int64_t n, const double* in, double* out);
 /* measured atomicAdd throughput [atomics/s] on an nx x ny image (fp64: double, else float): pattern 0 uniform random
    pixels, 1 one hot pixel, 2 a thousand Gaussian star images -- the ceiling of the charge deposit */
 int b2_atomic_peak(b2_ctx* ctx, int32_t fp64, int32_t pattern, int32_t nx, int32_t ny, int64_t n, double* atomics_per_s);
@@ -502,6 +505,11 @@ int b2_plain_accumulate(b2_sensor* s, int64_t n, const double* x, const double* 
    been read; the device copies are ordered before later work on the context's stream. */
 int b2_photons_upload(b2_ctx* ctx, int32_t nfields, int64_t nseg, const double* const* seg, const int64_t* seg_len,
                       double* const* dst);
+/* a large array between pageable HOST memory and DEVICE memory through the pinned ring (to_device != 0: host -> device):
+   what b2_sensor_bind_image / b2_sensor_read_image do for a full CCD, for arrays the caller keeps on the device itself
+   (the full image of the classic pipeline, imsim/lsst_image.py:359-368).  bytes must be a multiple of 8.  Returns once
+   the host array has been read / written. */
+int b2_copy_through_ring(b2_ctx* ctx, void* host, void* device, int64_t bytes, int32_t to_device);
 /* host-to-host copy on the library's copy threads (B2_HOST_THREADS): used to hand a pinned snapshot of the image to
    the caller's pageable array when a checkpoint is written while the next batch is already uploading */
 int b2_host_memcpy(void* dst, const void* src, int64_t bytes);

@@ -185,3 +185,31 @@ def test_statistical_moments_against_reference_regression():
         assert res[0] - exp0 == pytest.approx(dx, abs=0.003)
         assert res[1] - exp0 == pytest.approx(dy, abs=0.008)
         assert res[1] > res[0]  # brighter-fatter is stronger along y
+
+
+def test_round_to_f32_on_the_fp64_adder_equals_the_conversion():
+    """The boundary update rounds every term to float precision with two FP64 additions instead of a
+    double -> float -> double round trip (sensor_device.cuh: round_to_f32); it must be the same function."""
+    import ctypes as C
+
+    from imsim_b200 import OpticsContext, _lib
+
+    rng = np.random.default_rng(3)
+    f = rng.standard_normal(200000).astype(np.float32)
+    fl = f.astype(np.float64)
+    up = np.nextafter(f, np.float32(np.inf)).astype(np.float64)
+    mid = 0.5 * (fl + up)  # exact ties
+    cases = [rng.standard_normal(400000) * 10.0 ** rng.uniform(-12, 3, 400000), fl, mid, np.nextafter(mid, np.inf),
+             np.nextafter(mid, -np.inf), -mid, np.array([0.0, -0.0, 1.0, -1.0, 2.0 ** -126, 2.0 ** -127, 2.0 ** -149,
+                                                           2.0 ** -150, 1.5 * 2.0 ** -149, 3e-39, -3e-39, 1e-45, 1e-46,
+                                                           1.0 - 2.0 ** -25, 1.0 - 2.0 ** -26, 2.0 - 2.0 ** -24, 1e30]),
+             (rng.integers(1, 2 ** 24, 100000) * 2.0 ** -149) + rng.choice([0.0, 2.0 ** -150, 2.0 ** -151], 100000)]
+    x = np.ascontiguousarray(np.concatenate(cases))
+    out = np.empty_like(x)
+    ctx = OpticsContext(device=0)
+    _lib.check(_lib.load().b2_test_round_f32(ctx.handle, x.size, x.ctypes.data_as(C.POINTER(C.c_double)),
+                                             out.ctypes.data_as(C.POINTER(C.c_double))))
+    want = x.astype(np.float32).astype(np.float64)
+    # (-0.0 comes back as +0.0: x - x under round-to-nearest; no boundary arithmetic can tell them apart)
+    bad = np.flatnonzero((out != want) | ((np.signbit(out) != np.signbit(want)) & (want != 0.0)))
+    assert bad.size == 0, (x[bad[:5]], out[bad[:5]], want[bad[:5]])
