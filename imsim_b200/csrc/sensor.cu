@@ -266,9 +266,10 @@ k_update_distortions(const __grid_constant__ DevSensor s, const CT* __restrict__
 // the pixels that actually hold charge (photon pools are sparse outside star cores), in the
 // reference's (row, column) order; its boundary points live in registers and are written back once.
 // Arithmetic per visited pixel is identical to k_update_distortions (bit-identical results).
-// ADDER: the running points are float-valued doubles rounded on the FP64 adder (bf_term); otherwise floats with
-// GalSim's conversions.  Same bits either way.
-template <typename CT, int NV, bool ADDER>
+// The running points are float-valued doubles.  MODE 0: float tables, GalSim's conversions (3 conversions + 2 FP64
+// operations per term); 1: double tables, rounding on the FP64 adder (bf_term: 4 FP64 + 2 integer); 2: double tables,
+// rounding by the narrowing / widening conversion pair (2 + 2: both pipes share the term).  Same bits in all three.
+template <typename CT, int NV, int MODE>
 __global__ void __launch_bounds__(256)
 k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __restrict__ charge,
                            uint8_t* __restrict__ changed) {
@@ -349,14 +350,16 @@ k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __rest
         int rank = 0;
         if (bin >= 0) rank = atomicAdd(&s_bin[bin], 1);
         __syncthreads();
-        if (tid == 0) {
-            int t = 0;
-            for (int b = 0; b < NBIN; ++b) {
-                int c = s_bin[b];
-                s_bin[b] = t;
-                t += c;
+        if (tid < NBIN) {  // exclusive prefix over the bins: one warp, five shuffles (NBIN == 32)
+            const int c = s_bin[tid];
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < NBIN; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += t;
             }
-            s_total = t;
+            s_bin[tid] = incl - c;
+            if (tid == NBIN - 1) s_total = incl;
         }
         __syncthreads();
         if (bin >= 0) {
@@ -389,10 +392,14 @@ k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __rest
                     const int kk = ((q + 1 - dj + cyk) * s.nx9 + (q - di + cxk)) * (NV + 2);
 #pragma unroll
                     for (int k = 0; k < NV + 2; ++k) {
-                        if (ADDER) {
+                        if (MODE == 1) {
                             const double2 d = __ldg(KH + kk + k);
                             bf_term(hx[k], d.x, c);
                             bf_term(hy[k], d.y, c);
+                        } else if (MODE == 2) {
+                            const double2 d = __ldg(KH + kk + k);
+                            hx[k] = (double)(float)__dadd_rn(hx[k], __dmul_rn(d.x, c));
+                            hy[k] = (double)(float)__dadd_rn(hy[k], __dmul_rn(d.y, c));
                         } else {
                             const float2 d = __ldg(KHf + kk + k);
                             hx[k] = (double)(float)__dadd_rn(hx[k], __dmul_rn((double)d.x, c));
@@ -421,10 +428,14 @@ k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __rest
                     const int kk = ((q + 1 - dj + cyk) * s.nx9 + (q + 1 - di + cxk)) * NV;
 #pragma unroll
                     for (int k = 0; k < NV; ++k) {
-                        if (ADDER) {
+                        if (MODE == 1) {
                             const double2 d = __ldg(KV + kk + k);
                             bf_term(vx[k], d.x, c);
                             bf_term(vy[k], d.y, c);
+                        } else if (MODE == 2) {
+                            const double2 d = __ldg(KV + kk + k);
+                            vx[k] = (double)(float)__dadd_rn(vx[k], __dmul_rn(d.x, c));
+                            vy[k] = (double)(float)__dadd_rn(vy[k], __dmul_rn(d.y, c));
                         } else {
                             const float2 d = __ldg(KVf + kk + k);
                             vx[k] = (double)(float)__dadd_rn(vx[k], __dmul_rn((double)d.x, c));
@@ -1007,13 +1018,15 @@ static int launch_update_tiled(b2_sensor* s, const CT* charge) {
     size_t smem = (size_t)24 * 64 * sizeof(double) + 24 * sizeof(unsigned long long);
     dim3 block(32, 8, 1);
     dim3 grid((d.nx + 1 + 31) / 32, (d.ny + 1 + 7) / 8, 1);
-    static const bool adder = getenv("B2_UPDATE_ADDER") ? atoi(getenv("B2_UPDATE_ADDER")) != 0 : true;
+    static const int mode = getenv("B2_UPDATE_MODE") ? atoi(getenv("B2_UPDATE_MODE")) : 2;
     if (d.nv == 4) {
-        if (adder) k_update_distortions_tiled<CT, 4, true><<<grid, block, smem, st>>>(d, charge, s->changed);
-        else k_update_distortions_tiled<CT, 4, false><<<grid, block, smem, st>>>(d, charge, s->changed);
+        if (mode == 1) k_update_distortions_tiled<CT, 4, 1><<<grid, block, smem, st>>>(d, charge, s->changed);
+        else if (mode == 2) k_update_distortions_tiled<CT, 4, 2><<<grid, block, smem, st>>>(d, charge, s->changed);
+        else k_update_distortions_tiled<CT, 4, 0><<<grid, block, smem, st>>>(d, charge, s->changed);
     } else {
-        if (adder) k_update_distortions_tiled<CT, 8, true><<<grid, block, smem, st>>>(d, charge, s->changed);
-        else k_update_distortions_tiled<CT, 8, false><<<grid, block, smem, st>>>(d, charge, s->changed);
+        if (mode == 1) k_update_distortions_tiled<CT, 8, 1><<<grid, block, smem, st>>>(d, charge, s->changed);
+        else if (mode == 2) k_update_distortions_tiled<CT, 8, 2><<<grid, block, smem, st>>>(d, charge, s->changed);
+        else k_update_distortions_tiled<CT, 8, 0><<<grid, block, smem, st>>>(d, charge, s->changed);
     }
     B2_CHECK_LAUNCH();
     return 0;
