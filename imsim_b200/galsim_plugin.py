@@ -19,14 +19,18 @@ It re-registers, under the reference's own names,
   the photon pool in HBM -- the stamps' photon arrays go straight from GalSim's shooters into the device pool,
   one fused launch per sub-batch, the image comes back at checkpoints and at the end.  Object loading,
   partitioning, FFT objects, checkpoint files and the faint-object rule stay imSim's own code (inherited),
-* stamp type ``LSST_Photons`` (imsim/stamp.py:747) and image type ``LSST_Flat`` (imsim/flat.py:300): imSim's
-  builders, re-registered so that a config naming them gets the device sensor behind them.
+* image type ``LSST_Flat`` (imsim/flat.py:300): imSim's builder with the section loop of ``addNoise`` on the
+  device (``B200FlatBuilder``: pixel-area branch and ``sed`` branch; other sensors / noise types / checkpointed
+  runs keep imSim's loop),
+* stamp type ``LSST_Photons`` (imsim/stamp.py:747): imSim's builder, re-registered so that a config naming it gets
+  the device sensor behind it.
 
 ``B200SiliconSensor`` subclasses ``galsim.SiliconSensor`` so the ``isinstance`` test at
 photon_pooling.py:209 keeps passing ``recalc`` on the host route as well.
 
-GalSim, batoid and the LSST stack are not available in the build container: this
-module is import-guarded and UNTESTED there.
+GalSim, batoid and the LSST stack are not available in the build container: the module is exercised against the
+stand-in config engine of tests/stubs (tests/test_gpu_plugin_pooling.py, tests/test_gpu_plugin_flat.py), not against
+a real GalSim.
 """
 from __future__ import annotations
 
@@ -320,13 +324,79 @@ class B200PhotonPoolingImageBuilder(_ImsimPoolingBuilder):
 
 galsim.config.RegisterImageType('LSST_PhotonPoolingImage', B200PhotonPoolingImageBuilder())
 
-# LSST_Photons / LSST_Flat: imSim's own builders behind the device sensor (re-registered so that listing this
-# module alone in ``modules:`` still provides every type name of the path)
+# LSST_Photons: imSim's own builder behind the device sensor (re-registered so that listing this module alone in
+# ``modules:`` still provides every type name of the path).  LSST_Flat: imSim's set-up, the section loop of addNoise
+# on the device.
 try:
     from imsim.flat import LSST_FlatBuilder as _ImsimFlatBuilder  # noqa: E402
     from imsim.stamp import LSST_PhotonsBuilder as _ImsimPhotonsBuilder  # noqa: E402
-
-    galsim.config.RegisterStampType('LSST_Photons', _ImsimPhotonsBuilder())
-    galsim.config.RegisterImageType('LSST_Flat', _ImsimFlatBuilder())
 except ImportError:  # a stripped-down imsim: the two types stay whatever ``imsim`` registered
-    pass
+    _ImsimFlatBuilder = _ImsimPhotonsBuilder = None
+
+
+def _sed_bandpass_cdf(sed, bandpass, n=2048):
+    """CDF table of the photon wavelengths ``galsim.WavelengthSampler(sed, bandpass)`` draws: density
+    sed(w) * bandpass(w) on the bandpass's range (flat.py:172-175)."""
+    from .flat import wavelength_cdf
+
+    lo, hi = float(bandpass.blue_limit), float(bandpass.red_limit)
+    wave = np.union1d(np.linspace(lo, hi, n), np.asarray(getattr(bandpass, "wave_list", ()), dtype=float))
+    wave = wave[(wave >= lo) & (wave <= hi)]
+    return wavelength_cdf(wave, np.asarray(sed(wave), dtype=float) * np.asarray(bandpass(wave), dtype=float))
+
+
+if _ImsimFlatBuilder is not None:
+    class B200FlatBuilder(_ImsimFlatBuilder):
+        """``LSST_Flat`` (imsim/flat.py:15-300).  ``setup`` / ``buildImage`` are imSim's; ``addNoise`` keeps its
+        sequence -- sections with a border, ``niter`` iterations of ``max_counts_per_iter``, pixel areas from the charge
+        collected so far times the WCS sky image in the area branch, photons with SED wavelengths through
+        ``SiliconSensor.accumulate`` in the ``sed`` branch (flat.py:131-279) -- but runs it through
+        ``imsim_b200.flat.build_flat``: sections stay in HBM, the Poisson realisation and the photon generation
+        happen on the device.  Anything the device loop does not cover (another sensor class, a noise type other
+        than Poisson, checkpointed sections) goes to imSim's own loop, which then drives the device sensor per
+        section."""
+
+        last_route = None
+
+        def addNoise(self, image, config, base, image_num, obj_num, current_var, logger):
+            from .flat import build_flat
+
+            sensor = base.get('sensor', None)
+            noise_type = (base.get('image', {}).get('noise', {}) or {}).get('type', 'Poisson')
+            if not isinstance(sensor, _B200Sensor) or getattr(self, 'checkpoint', None) is not None \
+                    or noise_type != 'Poisson':
+                self.last_route = "host"
+                return super().addNoise(image, config, base, image_num, obj_num, current_var, logger)
+            self.last_route = "device"
+            base['current_noise_image'] = base['current_image']
+            rng = galsim.config.GetRNG(config, base, logger=logger, tag='LSST_Flat')
+            sensor.updateRNG(rng)
+            seed = (int(rng.raw()) << 32) | int(rng.raw())
+            b = image.bounds
+            sed_cdf = base_level = None
+            if self.sed is None:
+                # relative pixel areas from the WCS, mean 1 over the bordered image (flat.py:160-168)
+                sky = galsim.ImageF(b.withBorder(self.buffer_size), wcs=image.wcs)
+                sky.wcs.makeSkyImage(sky, sky_level=1.)
+                rel = np.asarray(sky.array, dtype=np.float64) / float(sky.array.mean())
+                sx0, sy0 = sky.bounds.xmin, sky.bounds.ymin
+
+                def base_level(sec):
+                    ny_, nx_ = sec.array.shape
+                    return rel[sec.ymin - sy0:sec.ymin - sy0 + ny_, sec.xmin - sx0:sec.xmin - sx0 + nx_]
+            else:
+                if 'bandpass' not in base:
+                    raise RuntimeError('Using sed with flat builder requires a valid bandpass')
+                sed_cdf = _sed_bandpass_cdf(self.sed, base['bandpass'])
+            from .sensor import Image as _Image
+
+            target = _Image(image.array, b.xmin, b.ymin)
+            nphot = build_flat(target, self.counts_per_pixel, sensor, rng=np.random.default_rng(seed),
+                               max_counts_per_iter=self.max_counts_per_iter, nx=self.nx, ny=self.ny,
+                               buffer_size=self.buffer_size, sed_cdf=sed_cdf, base_level=base_level, logger=logger)
+            if self.sed is not None:
+                logger.info('Accumulated %s photons in total.', nphot)
+
+    galsim.config.RegisterImageType('LSST_Flat', B200FlatBuilder())
+if _ImsimPhotonsBuilder is not None:
+    galsim.config.RegisterStampType('LSST_Photons', _ImsimPhotonsBuilder())

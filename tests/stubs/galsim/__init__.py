@@ -59,6 +59,9 @@ class BoundsI:
     def __and__(self, o):
         return BoundsI(max(self.xmin, o.xmin), min(self.xmax, o.xmax), max(self.ymin, o.ymin), min(self.ymax, o.ymax))
 
+    def withBorder(self, n):
+        return BoundsI(self.xmin - n, self.xmax + n, self.ymin - n, self.ymax + n)
+
 
 class JacobianWCS:
     def __init__(self, dudx, dudy, dvdx, dvdy):
@@ -75,11 +78,17 @@ class PixelScale:
     def local(self, pos=None):
         return JacobianWCS(self.scale, 0.0, 0.0, self.scale)
 
+    def makeSkyImage(self, image, sky_level):
+        image.array[:, :] = sky_level * self.scale ** 2
+
 
 class ImageF:
     """array + integer bounds + wcs, the part of galsim.Image the builders use"""
 
-    def __init__(self, ncol, nrow, xmin=1, ymin=1, wcs=None, dtype=_np.float32):
+    def __init__(self, ncol, nrow=None, xmin=1, ymin=1, wcs=None, dtype=_np.float32):
+        if isinstance(ncol, BoundsI):  # galsim.ImageF(bounds, wcs=...)
+            b = ncol
+            ncol, nrow, xmin, ymin = b.xmax - b.xmin + 1, b.ymax - b.ymin + 1, b.xmin, b.ymin
         self.array = _np.zeros((nrow, ncol), dtype=dtype)
         self.bounds = BoundsI(xmin, xmin + ncol - 1, ymin, ymin + nrow - 1)
         self.wcs = wcs
