@@ -305,7 +305,7 @@ struct Team<1> {
 };
 
 template <int NV, int CS>
-__global__ void __launch_bounds__(ST_THREADS, CS == 1 ? 2 : 1)
+__global__ void __launch_bounds__(ST_THREADS, 2)
 k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restrict__ jobs, const StampSlot* __restrict__ slots,
              const int* __restrict__ order, int njobs, int* __restrict__ next, unsigned char* __restrict__ arena,
              const __grid_constant__ StampPhotons ph, double nrecalc, int ocx, int ocy, const __grid_constant__ FullImage full,
@@ -904,7 +904,7 @@ extern "C" int b2_sensor_accumulate_stamps(b2_sensor* s, int32_t njobs, const B2
     int cs = 8;
     if (const char* e = getenv("B2_STAMP_CLUSTER")) cs = atoi(e);
     cs = cs >= 8 ? 8 : (cs >= 4 ? 4 : 1);
-    double heavy_cost = 2.0e5;
+    double heavy_cost = 1.0e5;
     if (const char* e = getenv("B2_STAMP_HEAVY")) heavy_cost = atof(e);
     B2_CUDA(cudaMemsetAsync(s->dstats, 0, ST_N * sizeof(unsigned long long) + 64, st));
     B2_CUDA(cudaMemcpyAsync(djobs, jobs, (size_t)njobs * sizeof(B2StampJob), cudaMemcpyHostToDevice, st));

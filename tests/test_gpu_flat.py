@@ -32,7 +32,10 @@ def test_silicon_flat_area_branch(fused):
     assert a.var() < tot
     cov10, cov01, cov11 = _cov(a)
     # expectation k * N^2 with the kernel's neighbour area coefficients: ~0.015, ~0.005, ~0.003 (x N)
-    assert cov10 > 5e-3 * tot and cov01 > 1e-3 * tot and cov11 > 0
+    if fused:  # at 1024^2 the estimates are good to ~1e-3 tot: the reference's own thresholds (test_flats.py:106-110)
+        assert cov10 > 1e-2 * tot and cov01 > 3e-3 * tot and cov11 > 2e-3 * tot
+    else:
+        assert cov10 > 5e-3 * tot and cov01 > 1e-3 * tot and cov11 > 0
     assert cov10 > cov01 > cov11
 
 

@@ -95,6 +95,13 @@ dp._has.update(dxdz=True, dydz=True, wavelength=True)
 full = torch.zeros((100, 100), dtype=torch.float32, device="cuda")
 stt = sensor.accumulate_stamps(jobs, dp, full, 1, 1)
 print("stamps", float(full.sum()), stt.n_updates)
+# the same stamps on thread-block clusters (every silicon stamp counted as heavy)
+os.environ["B2_STAMP_HEAVY"] = "1"
+sensor.updateRNG(3)
+full2 = torch.zeros((100, 100), dtype=torch.float32, device="cuda")
+stt2 = sensor.accumulate_stamps(jobs, dp, full2, 1, 1)
+print("stamps on clusters", float(full2.sum()), stt2.n_updates, bool(torch.equal(full, full2)))
+del os.environ["B2_STAMP_HEAVY"]
 import ctypes as C  # noqa: E402
 
 from imsim_b200 import _lib  # noqa: E402
