@@ -317,9 +317,11 @@ def test_sensor_moments_against_reference_regression(model):
     is compared, which removes the shot noise the two reference runs share (same seed, same photons) and leaves
     the noise of its diffusion draws, 1.0e-3 per axis.  Averaged over realisations the oracle gives
     x: +0.0000 / +0.0001 (ITL 4 / 8), -0.0012 / -0.0004 (e2v) -- inside that noise;
-    y: -0.0033 / -0.0030 (ITL), -0.0053 / -0.0048 (e2v) -- 3 to 5 sigma low, 0.25 - 0.4 % of Myy: either the
-    reference's single y-realisation, or a y-specific detail of Silicon.cpp this restatement does not have
-    (the static distortion of a charged pixel reproduces the vertex table exactly in both axes)."""
+    y: -0.0033 / -0.0030 (ITL), -0.0053 / -0.0048 (e2v) -- 3 to 5 sigma low, 0.25 - 0.4 % of Myy.  The ITL and e2v
+    reference runs share their draws, so the difference between the two deficits is real: about 10 % of the y part of
+    the brighter-fatter broadening is missing, a detail of Silicon.cpp near distorted pixel corners this restatement
+    does not have (DESIGN.md section 6 lists what was ruled out; the static distortion of a charged pixel reproduces
+    the vertex table exactly in both axes)."""
     cfg, dat = helpers.sensor_model(model)
     res = []
     for seed in range(8):
