@@ -18,6 +18,8 @@
 #include <mutex>
 #include <thread>
 
+#include <emmintrin.h>
+
 #include "b2_common.cuh"
 
 namespace {
@@ -26,7 +28,41 @@ struct Piece {
     char* dst;
     const char* src;
     size_t n;
+    bool to_ring = false;  // destination is a pinned ring slot: the CPU never reads it back
 };
+
+// Copy into a pinned ring slot with non-temporal stores: the slot is read next by the copy engine, not by the CPU,
+// so its lines are neither fetched for ownership nor left to evict the caller's arrays from the cache
+// (B2_COPY_NT=0: plain memcpy).
+bool g_copy_nt = false;
+
+void copy_piece(const Piece& q) {
+    if (!q.to_ring || !g_copy_nt || q.n < 4096) {
+        memcpy(q.dst, q.src, q.n);
+        return;
+    }
+    char* d = q.dst;
+    const char* s = q.src;
+    size_t n = q.n;
+    const size_t head = (64 - ((uintptr_t)d & 63)) & 63;
+    if (head) {
+        memcpy(d, s, head);
+        d += head; s += head; n -= head;
+    }
+    const size_t body = n & ~(size_t)63;
+    for (size_t o = 0; o < body; o += 64) {
+        const __m128i a = _mm_loadu_si128((const __m128i*)(s + o));
+        const __m128i b = _mm_loadu_si128((const __m128i*)(s + o + 16));
+        const __m128i c = _mm_loadu_si128((const __m128i*)(s + o + 32));
+        const __m128i e = _mm_loadu_si128((const __m128i*)(s + o + 48));
+        _mm_stream_si128((__m128i*)(d + o), a);
+        _mm_stream_si128((__m128i*)(d + o + 16), b);
+        _mm_stream_si128((__m128i*)(d + o + 32), c);
+        _mm_stream_si128((__m128i*)(d + o + 48), e);
+    }
+    _mm_sfence();
+    if (n > body) memcpy(d + body, s + body, n - body);
+}
 
 // Persistent memcpy workers.  Never destroyed (a joinable std::thread in a static destructor of a forked or
 // exiting interpreter is a hang waiting to happen); re-created in a forked child, where the parent's threads
@@ -45,7 +81,7 @@ class CopyPool {
         for (;;) {
             size_t i = next_.fetch_add(1);
             if (i >= p.size()) break;
-            memcpy(p[i].dst, p[i].src, p[i].n);
+            copy_piece(p[i]);
         }
     }
     void worker() {
@@ -78,7 +114,7 @@ public:
     void run(const std::vector<Piece>& p) {
         std::lock_guard<std::mutex> serial(run_mu_);
         if (th_.empty() || p.size() <= 1) {
-            for (const Piece& q : p) memcpy(q.dst, q.src, q.n);
+            for (const Piece& q : p) copy_piece(q);
             return;
         }
         {
@@ -115,6 +151,10 @@ CopyPool& pool() {
         long share = std::max(1L, hw / env_long("LOCAL_WORLD_SIZE", 1));
         long n = env_long("B2_HOST_THREADS", std::max(1L, std::min(8L, share)));
         g_pool = new CopyPool((int)std::min(n, 64L));  // the previous pool (parent's, after a fork) is abandoned
+        // measured (profiles/README.md): with eight ranks on one host the copies are bound by the memory system and
+        // non-temporal stores give 6 %; a single rank is 2 % faster with plain memcpy
+        g_copy_nt = env_long("LOCAL_WORLD_SIZE", 1) > 1;
+        if (const char* e = getenv("B2_COPY_NT")) g_copy_nt = atoi(e) != 0;
         g_pool_pid = getpid();
     }
     return *g_pool;
@@ -189,7 +229,7 @@ int b2_pipe_run(b2_ctx* ctx, int64_t n, int nin, const double* const* hin, doubl
             char* user = in ? (char*)const_cast<double*>(hin[f] + off) : (char*)(hout[f] + off);
             for (size_t o = 0; o < bytes; o += PIECE) {
                 size_t m = std::min(PIECE, bytes - o);
-                pieces.push_back(in ? Piece{pinned + o, user + o, m} : Piece{user + o, pinned + o, m});
+                pieces.push_back(in ? Piece{pinned + o, user + o, m, true} : Piece{user + o, pinned + o, m, false});
             }
         }
         cp.run(pieces);
@@ -278,7 +318,7 @@ extern "C" int b2_photons_upload(b2_ctx* ctx, int32_t nfields, int64_t nseg, con
                 const char* src = (const char*)(seg[(size_t)f * nseg + g] + (a - start[g]));
                 char* dstp = slot(s, f) + (size_t)(a - off) * sizeof(double);
                 const size_t bytes = (size_t)(b - a) * sizeof(double);
-                for (size_t o = 0; o < bytes; o += PIECE) pieces.push_back(Piece{dstp + o, src + o, std::min(PIECE, bytes - o)});
+                for (size_t o = 0; o < bytes; o += PIECE) pieces.push_back(Piece{dstp + o, src + o, std::min(PIECE, bytes - o), true});
             }
         }
         t0 = prof ? now() : 0.0;
