@@ -151,12 +151,12 @@ CopyPool& pool() {
         long share = std::max(1L, hw / env_long("LOCAL_WORLD_SIZE", 1));
         long n = env_long("B2_HOST_THREADS", std::max(1L, std::min(8L, share)));
         g_pool = new CopyPool((int)std::min(n, 64L));  // the previous pool (parent's, after a fork) is abandoned
-        // measured (profiles/README.md): with eight ranks on one host the copies are bound by the memory system and
-        // non-temporal stores give 6 %; a single rank is 2 % faster with plain memcpy
-        g_copy_nt = env_long("LOCAL_WORLD_SIZE", 1) > 1;
-        if (const char* e = getenv("B2_COPY_NT")) g_copy_nt = atoi(e) != 0;
         g_pool_pid = getpid();
     }
+    // measured (profiles/README.md): with eight ranks on one host the copies are bound by the memory system and
+    // non-temporal stores give 6 %; a single rank is 2 % faster with plain memcpy
+    g_copy_nt = env_long("LOCAL_WORLD_SIZE", 1) > 1;
+    if (const char* e = getenv("B2_COPY_NT")) g_copy_nt = atoi(e) != 0;
     return *g_pool;
 }
 

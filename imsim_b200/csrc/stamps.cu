@@ -904,7 +904,11 @@ extern "C" int b2_sensor_accumulate_stamps(b2_sensor* s, int32_t njobs, const B2
     int cs = 8;
     if (const char* e = getenv("B2_STAMP_CLUSTER")) cs = atoi(e);
     cs = cs >= 8 ? 8 : (cs >= 4 ? 4 : 1);
-    double heavy_cost = 1.0e5;
+    // "heavy": a stamp that alone would take more than half of what a block's fair share of the whole list takes
+    // (1000 equal stars: none; a catalogue whose photons sit in a few stars: those), never below 5e4
+    double total_cost = 0.0;
+    for (int j = 0; j < njobs; ++j) total_cost += cost(j);
+    double heavy_cost = std::max(5.0e4, 0.5 * total_cost / (2.0 * s->sm_count));
     if (const char* e = getenv("B2_STAMP_HEAVY")) heavy_cost = atof(e);
     B2_CUDA(cudaMemsetAsync(s->dstats, 0, ST_N * sizeof(unsigned long long) + 64, st));
     B2_CUDA(cudaMemcpyAsync(djobs, jobs, (size_t)njobs * sizeof(B2StampJob), cudaMemcpyHostToDevice, st));

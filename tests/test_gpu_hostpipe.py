@@ -99,3 +99,29 @@ def test_accumulate_pipelined_upload_equals_staged(inject):
         images.append((added, img.array.copy()))
     assert images[0][0] == images[1][0] > 0.9 * n
     assert np.array_equal(images[0][1], images[1][1])
+
+
+def test_copy_through_ring_round_trip():
+    """b2_copy_through_ring: a pageable host array to the device and back (large: through the pinned ring, also with
+    non-temporal stores; small: plain copy); the size must be a multiple of 8 bytes."""
+    import torch
+
+    from imsim_b200 import OpticsContext, _lib
+
+    ctx = OpticsContext(device=0)
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for n, env in ((1 << 22) + 3, {}), ((1 << 22) + 3, dict(B2_COPY_NT=1)), (1000, {}):
+        with _Env(**env):
+            a = rng.standard_normal(n).astype(np.float32)[: n - (n % 2)]  # 8-byte multiple
+            dev = torch.empty(a.size, dtype=torch.float32, device="cuda:0")
+            _lib.check(lib.b2_copy_through_ring(ctx.handle, a.ctypes.data, dev.data_ptr(), a.nbytes, 1))
+            torch.cuda.synchronize()
+            assert np.array_equal(dev.cpu().numpy(), a)
+            dev.mul_(2.0)
+            torch.cuda.synchronize()
+            back = np.empty_like(a)
+            _lib.check(lib.b2_copy_through_ring(ctx.handle, back.ctypes.data, dev.data_ptr(), back.nbytes, 0))
+            assert np.array_equal(back, 2.0 * a)
+    with pytest.raises(_lib.B2Error):
+        _lib.check(lib.b2_copy_through_ring(ctx.handle, back.ctypes.data, dev.data_ptr(), 12, 0))

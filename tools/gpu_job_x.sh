@@ -1,6 +1,7 @@
 #!/bin/bash
-for cs in 8 4; do for h in 5e4 1e5 2e5; do
-  echo "== cluster $cs heavy $h"
-  B2_STAMP_CLUSTER=$cs B2_STAMP_HEAVY=$h timeout 600 python tools/classic_bench.py 1998 5e7 2>&1 | grep "^build " | tail -2 | cut -c1-160
-done; done
-timeout 600 python -m pytest tests/test_gpu_stamps.py -q -x 2>&1 | tail -2
+timeout 600 python tools/classic_bench.py 1998 5e7 2>&1 | grep "^build " | tail -2 | cut -c1-160
+timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-visit-line --no-plugin-e2e 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print({k:'%.3e'%v['value'] for k,v in d['configs'].items()})"
+timeout 600 python -m pytest tests/test_gpu_stamps.py tests/test_gpu_classic.py tests/test_gpu_hostpipe.py -q -x 2>&1 | tail -2
