@@ -399,6 +399,8 @@ def plugin_e2e(su, P, K, rank, hx, hy, hwl, hflux, n_obj=1000):
     n = per * n_obj
     assert builder.last_route == "device", builder.last_route
     assert ck.saves >= K, ck.saves  # one per photon batch (+ one after the, here empty, FFT batch)
+    if getattr(builder, "last_profile", None):
+        out["host_phase_seconds"] = {k: round(v, 4) for k, v in builder.last_profile.items()}
     out.update(value=n * K / out["seconds"], photons_per_step=n, electrons=float(image.array.sum(dtype=np.float64)),
                h2d_bytes_per_step=int(builder.last_h2d_bytes // K + image.array.nbytes // K),
                d2h_bytes_per_step=int(image.array.nbytes), steps=K, route=builder.last_route,

@@ -112,8 +112,10 @@ public:
     int threads() const { return (int)th_.size() + 1; }
     // copies every piece; the calling thread takes its share
     void run(const std::vector<Piece>& p) {
-        std::lock_guard<std::mutex> serial(run_mu_);
-        if (th_.empty() || p.size() <= 1) {
+        // one job at a time on the workers; a caller that finds them busy (another context, or the checkpoint copy of
+        // a builder whose next upload is already running) copies its pieces itself instead of queueing behind it
+        std::unique_lock<std::mutex> serial(run_mu_, std::try_to_lock);
+        if (!serial.owns_lock() || th_.empty() || p.size() <= 1) {
             for (const Piece& q : p) copy_piece(q);
             return;
         }

@@ -265,11 +265,24 @@ class B200PhotonPoolingImageBuilder(_ImsimPoolingBuilder):
         self.last_route = "host" if path is None else "device"
         if path is not None:
             path.begin(full_image)
-        # With the device route a checkpoint's image travels to the host while the NEXT sub-batch's photons are
-        # gathered and uploaded (the image is snapshotted on the device right after its batch, so what is saved is
-        # exactly the state after that batch); the file is written once the upload has been queued.
+        # The device route is software-pipelined against the interpreter.  The gather + upload of sub-batch s runs on
+        # a helper thread while this loop builds the stamps of sub-batch s + 1; the fused launch of s is queued when
+        # that upload has finished (``drain``), right before the upload of s + 1 (whose pointer tables are ready by then) starts.  A checkpoint's image is
+        # snapshotted on the device right after the last launch of its batch -- what is saved is exactly the state
+        # after that batch -- travels to the host on a side stream and is written to the file while the next
+        # upload runs (``flush_pending``).  The order of the device work is the reference's.
         pending = None  # batch number whose checkpoint awaits its image
+        inflight = None  # [resume, recalc, batch number to checkpoint after this launch or None]
         image_current = False  # full_image.array holds the final pixels already
+        import os as _os
+        import time as _time
+
+        prof = {} if _os.environ.get("B2_PLUGIN_PROFILE") else None  # host seconds per phase of the loop
+
+        def lap(name, t0):
+            if prof is not None:
+                prof[name] = prof.get(name, 0.0) + _time.perf_counter() - t0
+            return _time.perf_counter()
 
         def flush_pending():
             nonlocal pending
@@ -279,6 +292,25 @@ class B200PhotonPoolingImageBuilder(_ImsimPoolingBuilder):
                                      book["obj_nums"], pending)
                 pending = None
 
+        def drain():
+            nonlocal inflight, pending, image_current
+            if inflight is None:
+                return
+            resume_, recalc_, closes = inflight
+            inflight = None
+            t = _time.perf_counter()
+            path.add_wait()
+            t = lap("wait for the upload", t)
+            path.step(resume=resume_, recalc=recalc_)
+            t = lap("launch", t)
+            image_current = False
+            if closes is not None:
+                flush_pending()  # (only if a batch had no sub-batch after it to do this)
+                t = _time.perf_counter()
+                path.snapshot_begin()
+                pending = closes
+                lap("snapshot_begin", t)
+
         for batch_num, batch in enumerate(batches, start=done):
             if not batch:
                 continue
@@ -286,15 +318,23 @@ class B200PhotonPoolingImageBuilder(_ImsimPoolingBuilder):
                 logger.warning("Starting photon batch %d/%d.", batch_num + 1, nbatch)
             base['index_key'] = 'image_num'
             for sub_num, sub in enumerate(self.make_photon_subbatches(batch, nsub)):
+                t = _time.perf_counter()
                 stamps, current_vars = self.build_stamps(base, logger, sub)
+                t = lap("build_stamps", t)
                 resume = batch_num > done or sub_num > 0
                 recalc = sub_num == 0
                 if path is not None:
-                    path.add([stamp.photons for stamp in stamps])
+                    t = _time.perf_counter()
+                    path.add_prepare([stamp.photons for stamp in stamps])  # while the previous upload runs
                     del stamps
+                    lap("add_prepare", t)
+                    drain()
+                    t = _time.perf_counter()
+                    path.add_start()
+                    t = lap("add_start", t)
                     flush_pending()
-                    path.step(resume=resume, recalc=recalc)
-                    image_current = False
+                    lap("checkpoint (image to host + save)", t)
+                    inflight = [resume, recalc, None]
                 else:
                     photons = self.merge_photon_arrays(stamps)
                     del stamps
@@ -305,18 +345,22 @@ class B200PhotonPoolingImageBuilder(_ImsimPoolingBuilder):
                 book["vars"].extend(v for v in current_vars if v != 0)
             if self.checkpoint is not None:
                 if path is not None:
-                    path.snapshot_begin()
-                    pending = batch_num + 1
+                    if inflight is not None:
+                        inflight[2] = batch_num + 1
                 else:
                     self.save_checkpoint(self.checkpoint, chk_name, base, full_image, book["stamps"], book["vars"],
                                          book["obj_nums"], batch_num + 1)
         if path is not None:
+            drain()
             if pending is not None:
                 flush_pending()
                 image_current = True  # the last checkpoint's image is the final one
             if not image_current:
                 path.read_back(full_image)
             self.last_pooled_photons, self.last_h2d_bytes = path.photons, path.h2d_bytes
+            if prof is not None:
+                logger.warning("pooled device route, host seconds: %s", {k: round(v, 4) for k, v in prof.items()})
+                self.last_profile = prof
 
         current_var = galsim.config.FlattenNoiseVariance(base, full_image, book["stamps"], tuple(book["vars"]), logger)
         return full_image, current_var

@@ -432,7 +432,8 @@ class PooledDevicePath:
       returns None for anything else -- the caller then keeps the reference's host loop;
     * ``begin(full_image)`` uploads the image as it stands (FFT objects already drawn, a restored checkpoint);
     * ``add(photon_arrays)`` gathers the stamps' pageable arrays into one device pool (``b2_photons_upload``: the
-      merge happens in the pinned ring, no host-side copy of the pool);
+      merge happens in the pinned ring, no host-side copy of the pool); ``add_begin`` / ``add_wait`` are its two
+      halves, the upload running on a helper thread in between;
     * ``step(resume, recalc)`` is one ``b2_pool_step``; ``read_back(full_image)`` copies the image to the host
       (checkpoints, the return of ``buildImage``).
     """
@@ -444,6 +445,8 @@ class PooledDevicePath:
         self.image = None
         self.photons = 0
         self.h2d_bytes = 0
+        self._worker = None
+        self._upload = None
 
     @classmethod
     def recognise(cls, photon_ops, sensor, local_wcs=None, seed=None):
@@ -503,11 +506,24 @@ class PooledDevicePath:
 
     def add(self, photon_arrays):
         """The photons of a sub-batch: a list of (GalSim) PhotonArrays with x, y, flux and wavelengths."""
-        import ctypes as C  # noqa: PLC0415
+        n = self.add_begin(photon_arrays)
+        self.add_wait()
+        return n
 
+    def add_begin(self, photon_arrays):
+        """``add_prepare`` + ``add_start``."""
+        n = self.add_prepare(photon_arrays)
+        self.add_start()
+        return n
+
+    def add_prepare(self, photon_arrays):
+        """First half of an upload, host work only: the device pool is allocated and the table of the stamps' array
+        pointers is built.  May be called while the previous sub-batch is still uploading / waiting for its launch
+        (its pool is a different allocation).  The arrays must stay untouched until ``add_wait`` has returned (they
+        are kept referenced here)."""
         arrays = [pa for pa in photon_arrays if pa is not None and len(pa) > 0]
         n = int(sum(len(pa) for pa in arrays))
-        self.dp = None
+        self._prepared = None
         if n == 0:
             return 0
         fields = ("x", "y", "flux", "wavelength")
@@ -518,7 +534,7 @@ class PooledDevicePath:
         nseg = len(arrays)
         # pointer table [field][stamp] without a ctypes object per array
         ptrs = np.empty((len(fields), nseg), dtype=np.uint64)
-        keep = []
+        keep = [arrays]
         for f, name in enumerate(fields):
             row = ptrs[f]
             for g, pa in enumerate(arrays):
@@ -529,13 +545,45 @@ class PooledDevicePath:
                 row[g] = a.__array_interface__["data"][0]
         lens = np.fromiter((len(pa) for pa in arrays), dtype=np.int64, count=nseg)
         dst = np.array([getattr(dp, name).data_ptr() for name in fields], dtype=np.uint64)
-        _lib.check(_lib.load().b2_photons_upload(self.ctx.handle, len(fields), nseg, ptrs.ctypes.data, lens.ctypes.data,
-                                                 dst.ctypes.data))
-        dp._has.update(wavelength=True)
-        self.dp = dp
+        keep += [ptrs, lens, dst]
+        lib, handle, nf = _lib.load(), self.ctx.handle, len(fields)
+
+        def upload():
+            # ctypes drops the GIL for the duration of the call: the host copy threads and the DMA run while the
+            # interpreter builds the next stamps
+            return lib.b2_photons_upload(handle, nf, nseg, ptrs.ctypes.data, lens.ctypes.data, dst.ctypes.data)
+
+        self._prepared = (upload, dp, keep)
         self.photons += n
         self.h2d_bytes += n * 8 * len(fields)
         return n
+
+    def add_start(self):
+        """Second half: start gathering the prepared sub-batch into its device pool on a helper thread and return at
+        once; the caller goes on with its own host work and calls ``add_wait`` before ``step``.  Call it after the
+        previous sub-batch's ``step``: the upload is ordered on the stream behind what has been queued so far."""
+        self.dp = None
+        self._upload = None
+        prepared, self._prepared = getattr(self, "_prepared", None), None
+        if prepared is None:
+            return
+        upload, dp, keep = prepared
+        if self._worker is None:
+            from concurrent.futures import ThreadPoolExecutor  # noqa: PLC0415
+
+            self._worker = ThreadPoolExecutor(max_workers=1, thread_name_prefix="b2-upload")
+        self._upload = (self._worker.submit(upload), dp, keep)
+
+    def add_wait(self):
+        """Wait for the upload started by ``add_begin``; the pool is then ready for ``step``."""
+        up, self._upload = getattr(self, "_upload", None), None
+        if up is None:
+            return
+        fut, dp, keep = up
+        _lib.check(fut.result())
+        keep.clear()
+        dp._has.update(wavelength=True)
+        self.dp = dp
 
     def step(self, resume: bool, recalc: bool):
         """SiliconSensor.accumulate(resume, recalc) of the uploaded pool after the pooled ops, one fused launch."""
