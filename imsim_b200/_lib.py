@@ -75,6 +75,8 @@ _SIGNATURES = {
     "b2_ctx_synchronize": (C.c_int, [vp]),
     "b2_fma_peak": (C.c_int, [vp, C.c_int32, dp]),
     "b2_copy_through_ring": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int32]),
+    "b2_segments_constant": (C.c_int, [C.c_int64, vp, vp, vp, vp]),
+    "b2_fill_segments": (C.c_int, [vp, C.c_int64, vp, vp, vp]),
     "b2_test_round_f32": (C.c_int, [vp, C.c_int64, dp, dp]),
     "b2_timing_report": (C.c_int, [C.c_char_p, C.c_int64]),
     "b2_ctx_record_kernel_events": (C.c_int, [vp, C.c_int32]),

@@ -82,6 +82,7 @@ extern "C" int b2_ctx_destroy(b2_ctx* ctx) {
     }
     if (ctx->scratch.ptr) cudaFree(ctx->scratch.ptr);
     if (ctx->stats.ptr) cudaFree(ctx->stats.ptr);
+    if (ctx->fill_scratch.ptr) cudaFree(ctx->fill_scratch.ptr);
     delete ctx;
     return 0;
 }

@@ -144,6 +144,7 @@ struct b2_ctx {
     } extras[B2_DEV_MAX_SURF];
     Scratch scratch;         // staging for B2_HOST calls
     Scratch stats;           // small device buffer for counters
+    Scratch fill_scratch;    // segment tables of b2_fill_segments
     B2TanSip img_host, field_host;
     // live timing of the dominant kernel (bench.py roofline): event pairs around each launch
     bool record_events = false;

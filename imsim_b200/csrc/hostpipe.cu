@@ -355,3 +355,40 @@ extern "C" int b2_host_memcpy(void* dst, const void* src, int64_t bytes) {
     pool().run(pieces);
     return 0;
 }
+
+// Is every segment a constant array?  GalSim's shooters give all photons of an object the same flux, so the flux
+// field of a pooled upload is one number per stamp: reading it once (host threads, no writes) is cheaper than copying
+// it into the ring and over PCIe.  value[g] = first element of segment g (0 for an empty one); *all_constant = 1 iff
+// every element of every segment equals its segment's first.
+extern "C" int b2_segments_constant(int64_t nseg, const double* const* seg, const int64_t* seg_len, double* value,
+                                    int32_t* all_constant) {
+    B2_REQUIRE(nseg >= 0 && (nseg == 0 || (seg && seg_len && value)) && all_constant, "b2_segments_constant: null argument");
+    std::atomic<int> ok{1};
+    std::atomic<int64_t> next{0};
+    auto work = [&] {
+        for (;;) {
+            const int64_t g = next.fetch_add(1);
+            if (g >= nseg) break;
+            const double* a = seg[g];
+            const int64_t m = seg_len[g];
+            const double v = m > 0 ? a[0] : 0.0;
+            value[g] = v;
+            if (!ok.load(std::memory_order_relaxed)) continue;  // values are still wanted
+            // bitwise comparison in blocks: any difference (a NaN included) makes the segment non-constant
+            uint64_t vb, acc = 0;
+            memcpy(&vb, &v, 8);
+            const uint64_t* b = reinterpret_cast<const uint64_t*>(a);
+            for (int64_t i = 0; i < m; ++i) acc |= b[i] ^ vb;
+            if (acc) ok.store(0);
+        }
+    };
+    long total = 0;
+    for (int64_t g = 0; g < nseg; ++g) total += (long)seg_len[g];
+    int nth = (int)std::min<long>(pool().threads(), std::max<long>(1, total >> 20));
+    std::vector<std::thread> th;
+    for (int i = 1; i < nth; ++i) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    *all_constant = ok.load();
+    return 0;
+}

@@ -1449,3 +1449,38 @@ extern "C" int b2_copy_through_ring(b2_ctx* ctx, void* host, void* device, int64
     const double* dout[1] = {(const double*)device};
     return b2_pipe_run(ctx, bytes / 8, 0, nullptr, nullptr, 1, hout, dout, nullptr);
 }
+
+// dst[start[g] .. start[g+1]) = value[g]: a per-stamp constant field of a pooled upload written on the device
+__global__ void k_fill_segments(int64_t n, int64_t nseg, const int64_t* __restrict__ start, const double* __restrict__ value,
+                                double* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t lo = 0, hi = nseg;  // start[lo] <= i < start[hi]
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(start + mid) <= i) lo = mid; else hi = mid;
+    }
+    dst[i] = __ldg(value + lo);
+}
+
+extern "C" int b2_fill_segments(b2_ctx* ctx, int64_t nseg, const int64_t* seg_len, const double* value, double* dst) {
+    B2_REQUIRE(ctx && nseg >= 0 && (nseg == 0 || (seg_len && value && dst)), "b2_fill_segments: null argument");
+    if (nseg == 0) return 0;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    std::vector<int64_t> start((size_t)nseg + 1, 0);
+    for (int64_t g = 0; g < nseg; ++g) {
+        B2_REQUIRE(seg_len[g] >= 0, "b2_fill_segments: negative segment length");
+        start[g + 1] = start[g] + seg_len[g];
+    }
+    const int64_t n = start[nseg];
+    if (n == 0) return 0;
+    // the two small tables go to a scratch buffer of the context (stream-ordered: a later call may reuse it)
+    const size_t sb = ((size_t)nseg + 1) * sizeof(int64_t), vb = (size_t)nseg * sizeof(double);
+    if (b2_scratch_reserve(ctx, ctx->fill_scratch, sb + vb)) return 1;
+    char* d = (char*)ctx->fill_scratch.ptr;
+    B2_CUDA(cudaMemcpyAsync(d, start.data(), sb, cudaMemcpyHostToDevice, ctx->stream));
+    B2_CUDA(cudaMemcpyAsync(d + sb, value, vb, cudaMemcpyHostToDevice, ctx->stream));
+    k_fill_segments<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, nseg, (const int64_t*)d, (const double*)(d + sb), dst);
+    B2_CHECK_LAUNCH();
+    return 0;
+}

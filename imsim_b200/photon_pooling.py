@@ -18,8 +18,10 @@ Two layers:
 """
 from __future__ import annotations
 
+import ctypes as C
 import dataclasses
 import itertools
+import os
 import warnings
 from dataclasses import dataclass
 from enum import Enum, auto
@@ -447,6 +449,8 @@ class PooledDevicePath:
         self.h2d_bytes = 0
         self._worker = None
         self._upload = None
+        #: stamps whose photons all carry the same flux send one number instead of the array (B2_FLUX_ARRAYS=1: off)
+        self.constant_flux_shortcut = not os.environ.get("B2_FLUX_ARRAYS")
 
     @classmethod
     def recognise(cls, photon_ops, sensor, local_wcs=None, seed=None):
@@ -544,18 +548,36 @@ class PooledDevicePath:
                     keep.append(a)
                 row[g] = a.__array_interface__["data"][0]
         lens = np.fromiter((len(pa) for pa in arrays), dtype=np.int64, count=nseg)
+        lib, handle = _lib.load(), self.ctx.handle
+        # GalSim's shooters give every photon of an object the same flux: if that holds for all stamps (one read of
+        # the flux arrays on the copy threads, bit for bit), the field is written on the device from one number per
+        # stamp instead of crossing PCIe
+        fill = None
+        if self.constant_flux_shortcut:
+            fi = fields.index("flux")
+            values = np.empty(nseg, dtype=np.float64)
+            flag = C.c_int32(0)
+            _lib.check(lib.b2_segments_constant(nseg, ptrs[fi].ctypes.data, lens.ctypes.data, values.ctypes.data,
+                                                C.addressof(flag)))
+            if flag.value:
+                fill = (values, dp.flux.data_ptr())
+                ptrs = np.ascontiguousarray(np.delete(ptrs, fi, axis=0))
+                fields = tuple(f for f in fields if f != "flux")
         dst = np.array([getattr(dp, name).data_ptr() for name in fields], dtype=np.uint64)
         keep += [ptrs, lens, dst]
-        lib, handle, nf = _lib.load(), self.ctx.handle, len(fields)
+        nf = len(fields)
 
         def upload():
             # ctypes drops the GIL for the duration of the call: the host copy threads and the DMA run while the
             # interpreter builds the next stamps
-            return lib.b2_photons_upload(handle, nf, nseg, ptrs.ctypes.data, lens.ctypes.data, dst.ctypes.data)
+            rc = lib.b2_photons_upload(handle, nf, nseg, ptrs.ctypes.data, lens.ctypes.data, dst.ctypes.data)
+            if rc == 0 and fill is not None:
+                rc = lib.b2_fill_segments(handle, nseg, lens.ctypes.data, fill[0].ctypes.data, fill[1])
+            return rc
 
         self._prepared = (upload, dp, keep)
         self.photons += n
-        self.h2d_bytes += n * 8 * len(fields)
+        self.h2d_bytes += n * 8 * nf + (8 * nseg if fill is not None else 0)
         return n
 
     def add_start(self):

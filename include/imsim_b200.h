@@ -510,6 +510,13 @@ int b2_photons_upload(b2_ctx* ctx, int32_t nfields, int64_t nseg, const double* 
    (the full image of the classic pipeline, imsim/lsst_image.py:359-368).  bytes must be a multiple of 8.  Returns once
    the host array has been read / written. */
 int b2_copy_through_ring(b2_ctx* ctx, void* host, void* device, int64_t bytes, int32_t to_device);
+/* A pooled field that is one number per stamp (GalSim's shooters give every photon of an object the same flux) need
+   not cross PCIe: b2_segments_constant reads the stamps' HOST arrays once on the copy threads (value[g] = first element
+   of segment g, *all_constant = 1 iff every segment is constant, compared bit for bit), b2_fill_segments writes
+   dst[sum(seg_len[:g]) ...] = value[g] on the DEVICE in stream order.  Same bits as uploading the arrays. */
+int b2_segments_constant(int64_t nseg, const double* const* seg, const int64_t* seg_len, double* value,
+                         int32_t* all_constant);
+int b2_fill_segments(b2_ctx* ctx, int64_t nseg, const int64_t* seg_len, const double* value, double* dst);
 /* host-to-host copy on the library's copy threads (B2_HOST_THREADS): used to hand a pinned snapshot of the image to
    the caller's pageable array when a checkpoint is written while the next batch is already uploading */
 int b2_host_memcpy(void* dst, const void* src, int64_t bytes);

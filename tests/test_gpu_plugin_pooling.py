@@ -69,7 +69,8 @@ def test_pooled_builder_takes_the_device_route_and_matches_the_host_loop():
     cat = _catalog(rng, 40, su.detector.nx, su.detector.ny)
     total = sum(c["flux"] for c in cat)
     img_d, b = _run("device", cat, su)
-    assert b.last_pooled_photons == total and b.last_h2d_bytes == 32 * total
+    # x, y, wavelength as arrays; the flux, constant per stamp, as one number per stamp and batch
+    assert b.last_pooled_photons == total and 24 * total < b.last_h2d_bytes < 24.1 * total
     img_h, _ = _run("host", cat, su)
     a, h = img_d.array.astype(np.float64), img_h.array.astype(np.float64)
     assert a.shape == (su.detector.ny, su.detector.nx)
@@ -132,3 +133,45 @@ def test_checkpoints_hold_the_image_after_their_batch():
     builder2.setup(cfg2, base2, 0, 0, [], pc.Quiet())
     image2, _ = builder2.buildImage(cfg2, base2, 0, 0, pc.Quiet())
     np.testing.assert_array_equal(image2.array, image.array)
+
+
+def test_constant_flux_stamps_send_one_number_each(monkeypatch):
+    """Stamps whose photons all carry the same flux are written on the device from one value per stamp; a stamp with
+    varying fluxes switches the whole field back to the upload.  Same pool either way, bit for bit."""
+    import torch
+
+    from imsim_b200 import OpticsContext
+    from imsim_b200.photon_array import PhotonArray
+    from imsim_b200.photon_pooling import PhotonPool, PooledDevicePath
+    from imsim_b200.sensor import SiliconSensor
+
+    ctx = OpticsContext(device=0, stream=torch.cuda.current_stream())
+    cfg, dat = helpers.sensor_model("lsst_itl_50_4")
+    sensor = SiliconSensor(config=cfg, vertex_data=dat, nrecalc=0, rng=1, absorption_table=helpers.absorption(), context=ctx)
+    rng = np.random.default_rng(0)
+
+    def stamps(vary):
+        out = []
+        for k, n in enumerate((700_000, 3, 250_000, 1)):
+            f = np.full(n, 0.25 * (k + 1))
+            if vary and k == 2:
+                f[n // 2] = 7.0
+            out.append(PhotonArray(n, x=rng.uniform(0, 100, n), y=rng.uniform(0, 100, n), flux=f,
+                                   wavelength=rng.uniform(500, 700, n)))
+        return out
+
+    for vary in (False, True):
+        arrays = stamps(vary)
+        want = np.concatenate([a.flux for a in arrays])
+        got = {}
+        for shortcut in (True, False):
+            path = PooledDevicePath(PhotonPool(ctx, sensor), sensor)
+            path.constant_flux_shortcut = shortcut
+            n = path.add(arrays)
+            torch.cuda.synchronize()
+            assert n == want.size
+            got[shortcut] = (path.dp.flux.cpu().numpy(), path.dp.x.cpu().numpy(), path.h2d_bytes)
+        np.testing.assert_array_equal(got[True][0], want)
+        np.testing.assert_array_equal(got[False][0], want)
+        np.testing.assert_array_equal(got[True][1], got[False][1])
+        assert (got[True][2] < got[False][2]) == (not vary)  # fewer bytes only when every stamp is constant
