@@ -249,7 +249,16 @@ def simulate_visit(opts, rank, world, local, barrier=None):
         psf = AtmosphericPSF(1.2, 0.7, "r", rng=271828, device="cuda:%d" % local)
         seds = [wavelength_cdf(wave, 1.0 + 0.8 * np.sin(wave / (15.0 + 5 * k))) for k in range(8)]
         cdf = (np.array([c for c, _ in seds]), np.array([w for _, w in seds]))
-    runner = DetectorRunner(local, models, helpers.absorption(), tree_rings={d: tr for d in mine}, psf=psf)
+    # lanes: independent DetectorRunners on their own streams, driven by one host thread each, so that one
+    # detector's FP64-bound ray trace shares the SMs with another's boundary update and memory-bound kernels
+    lanes = 1 if opts.visit_serial else max(1, int(getattr(opts, "visit_lanes", 0) or os.environ.get("B2_VISIT_LANES", "1")))
+    lanes = min(lanes, max(1, len(mine)))
+    if lanes == 1:
+        runner = DetectorRunner(local, models, helpers.absorption(), tree_rings={d: tr for d in mine}, psf=psf)
+    else:
+        from imsim_b200.visit import VisitLanes
+
+        visit_lanes = VisitLanes(local, lanes, models, helpers.absorption(), tree_rings={d: tr for d in mine}, psf=psf)
 
     def job(d):
         make = synthetic_catalog if opts.visit_catalog else synthetic_objects
@@ -270,8 +279,10 @@ def simulate_visit(opts, rank, world, local, barrier=None):
         t0 = time.perf_counter()
         if opts.visit_serial:  # one detector at a time, host and device in turn (the pre-pipelining behaviour)
             recs = [runner.run(**job(d))[0] for d in mine]
-        else:
+        elif lanes == 1:
             recs = [rec for rec, _ in runner.run_many(job(d) for d in mine)]
+        else:
+            recs = visit_lanes.run([job(d) for d in mine], cost=lambda j: costs[j["det_name"]])
         torch.cuda.synchronize()
         walls.append(time.perf_counter() - t0)
     return walls, recs
@@ -325,7 +336,8 @@ def visit_for_line(args, rank, world, local, dev):
     import torch
 
     opts = argparse.Namespace(visit_catalog=True, visit_readout=True, visit_sky=800.0, visit_ccds=args.visit_ccds,
-                              visit_photons=args.visit_photons, visit_repeat=2, visit_serial=False)
+                              visit_photons=args.visit_photons, visit_repeat=2, visit_serial=False,
+                              visit_lanes=args.visit_lanes or int(os.environ.get("B2_VISIT_LANES", "2")))
     mx = [0.0, 0.0, 0.0, 0.0]  # wall of the reported visit, wall of the first, GPU time, failure flag
     sm = [0.0, 0.0]            # photons, CCDs
     err = ""
@@ -353,7 +365,9 @@ def visit_for_line(args, rank, world, local, dev):
             "chain": "catalogue objects (stars, bulge / disc / knots galaxies, 8 SEDs) -> six-screen atmosphere + second "
                      "kick -> RubinDiffractionOptics -> SiliconSensor (brighter-fatter + tree rings, 10 batches) -> "
                      "sky through the pixel areas -> bleed / dark / CTI / noise -> int32 segments, e-image and raw "
-                     "segments to pinned host buffers; 189 CCDs by LPT over the ranks, no collective on the path"}
+                     "segments to pinned host buffers; 189 CCDs by LPT over the ranks, no collective on the path",
+            "lanes_per_gpu": int(opts.visit_lanes),
+            "gpu_s_note": "gpu_s_max_rank sums the per-CCD device times; with more than one lane they overlap"}
 
 
 def plugin_e2e(su, P, K, rank, hx, hy, hwl, hflux, n_obj=1000):
@@ -587,6 +601,8 @@ def main():
     ap.add_argument("--visit-repeat", type=int, default=2,
                     help="with --visit: simulate the visit this many times in the process and report the last "
                          "(steady state; the first also pays the one-time allocations)")
+    ap.add_argument("--visit-lanes", type=int, default=0,
+                    help="detectors simulated concurrently per GPU on separate streams (default: B2_VISIT_LANES or 1)")
     ap.add_argument("--visit-serial", action="store_true",
                     help="with --visit: no software pipelining (prepare, launch and finish each detector in turn)")
     ap.add_argument("--no-configs", action="store_true",

@@ -344,3 +344,63 @@ class DetectorRunner:
                 queue.append(self.launch(prep))
         for h in queue:
             yield self.finish(h)
+
+
+class VisitLanes:
+    """Several ``DetectorRunner`` s of one GPU, each on its own stream and driven by its own host thread, so that one
+    detector's FP64-bound ray trace shares the SMs with another's boundary update and its memory-bound kernels
+    (measured: two lanes finish a catalogue-field visit 6 % sooner than one, three do no better).  Detectors are
+    independent (seeds follow ``det_index``), so the images do not depend on the number of lanes."""
+
+    def __init__(self, device: int, lanes: int, *runner_args, **runner_kw):
+        import torch
+
+        self.torch, self.device = torch, device
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(max(1, lanes))]
+        self.runners = []
+        for s in self.streams:
+            with torch.cuda.stream(s):
+                self.runners.append(DetectorRunner(device, *runner_args, **runner_kw))
+        psf = runner_kw.get("psf")
+        if psf is not None and hasattr(psf, "screens"):  # moved to the device once, before the lanes start
+            psf.upload(self.runners[0].ctx, None)
+        torch.cuda.synchronize(device)
+
+    def run(self, jobs, cost=None, on_result=None):
+        """``jobs``: a list of keyword dicts for ``DetectorRunner.prepare``; ``cost(job)`` balances the lanes (LPT;
+        default: equal costs).  ``on_result(record, image, raw)`` is called on the lane's thread while the image
+        is valid.  Returns the records in the order of ``jobs``."""
+        import threading
+
+        torch = self.torch
+        jobs = list(jobs)
+        lanes = len(self.runners)
+        load = [0.0] * lanes
+        lane_of = [0] * len(jobs)
+        for i in sorted(range(len(jobs)), key=lambda i_: -(cost(jobs[i_]) if cost else 1.0)):
+            k = int(np.argmin(load))
+            lane_of[i] = k
+            load[k] += cost(jobs[i]) if cost else 1.0
+        recs, errs = [None] * len(jobs), []
+
+        def work(k):
+            try:
+                torch.cuda.set_device(self.device)  # the current device is per thread
+                mine = [i for i in range(len(jobs)) if lane_of[i] == k]
+                runner = self.runners[k]
+                with torch.cuda.stream(self.streams[k]):
+                    for i, (rec, image) in zip(mine, runner.run_many(jobs[i] for i in mine)):
+                        recs[i] = rec
+                        if on_result is not None:
+                            on_result(rec, image, runner.last_raw)
+            except BaseException as e:  # noqa: BLE001 -- re-raised on the calling thread
+                errs.append(e)
+
+        threads = [threading.Thread(target=work, args=(k,), name="b2-visit-lane-%d" % k) for k in range(lanes)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errs:
+            raise errs[0]
+        return recs

@@ -183,3 +183,40 @@ def test_pipelined_visit_equals_one_detector_at_a_time():
             n += 1
         assert n == len(dets)
     assert list(runner2.run_many([])) == []
+
+
+def test_visit_lanes_give_the_images_of_one_runner():
+    """Two detectors at a time on separate streams and host threads (visit.VisitLanes): same records, e-images and
+    raw segments as one runner working through the list."""
+    import zlib
+
+    from imsim_b200.atmosphere import GaussianPSF
+    from imsim_b200.flat import wavelength_cdf
+    from imsim_b200.visit import DetectorRunner, VisitLanes, synthetic_catalog
+
+    models = {"e2v": helpers.sensor_model("lsst_e2v_50_4"), "itl": helpers.sensor_model("lsst_itl_50_4")}
+    wave = np.linspace(550, 690, 15)
+    seds = [wavelength_cdf(wave, 1.0 + 0.1 * k * (wave - 550) / 140) for k in range(8)]
+    cdf = (np.array([c for c, _ in seds]), np.array([w for _, w in seds]))
+    dets = ["R22_S11", "R01_S00", "R22_S12", "R22_S11", "R01_S00"]
+    tr = {d: helpers.tree_ring_table() for d in dets if d.startswith("R22")}
+    jobs = []
+    for i, d in enumerate(dets):
+        nx, ny = (4072, 4000) if d.startswith("R01") else (4096, 4004)
+        jobs.append(dict(det_name=d, objects=(lambda i=i, nx=nx, ny=ny: synthetic_catalog(300, nx, ny, seed=i,
+                                                                                         total_photons=1.5e6)),
+                         nbatch=3, wavelength_cdf=cdf, det_index=i, readout=True, sky_level=100.0))
+    crc = lambda a: zlib.crc32(np.ascontiguousarray(a).tobytes())  # noqa: E731
+    runner = DetectorRunner(0, models, helpers.absorption(), tree_rings=tr, psf=GaussianPSF(0.7))
+    want = {}
+    for rec, image in runner.run_many(jobs):
+        want[(rec["det_name"], rec["photons"])] = (rec["electrons"], crc(image.array), crc(runner.last_raw))
+    got = {}
+
+    def collect(rec, image, raw):
+        got[(rec["det_name"], rec["photons"])] = (rec["electrons"], crc(image.array), crc(raw))
+
+    lanes = VisitLanes(0, 2, models, helpers.absorption(), tree_rings=tr, psf=GaussianPSF(0.7))
+    recs = lanes.run(jobs, cost=lambda j: 2.0 if j["det_name"].startswith("R22") else 1.0, on_result=collect)
+    assert [r["det_name"] for r in recs] == dets
+    assert got == want
