@@ -268,7 +268,9 @@ k_update_distortions(const __grid_constant__ DevSensor s, const CT* __restrict__
 // Arithmetic per visited pixel is identical to k_update_distortions (bit-identical results).
 // The running points are float-valued doubles.  MODE 0: float tables, GalSim's conversions (3 conversions + 2 FP64
 // operations per term); 1: double tables, rounding on the FP64 adder (bf_term: 4 FP64 + 2 integer); 2: double tables,
-// rounding by the narrowing / widening conversion pair (2 + 2: both pipes share the term).  Same bits in all three.
+// rounding by the narrowing / widening conversion pair (2 + 2: both pipes share the term); 3: as 2 with the tables
+// staged in shared memory, entries padded by one point so that the per-lane reads of a warp (every lane another
+// entry) spread over the banks -- the same reads through L1 cost a wavefront per distinct line.  Same bits in all.
 template <typename CT, int NV, int MODE>
 __global__ void __launch_bounds__(256)
 k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __restrict__ charge,
@@ -310,6 +312,15 @@ k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __rest
     }
     if (!__syncthreads_or(any_local)) return;  // no charge within reach of this tile
     const int cxk = (s.nx9 - 1) / 2, cyk = (s.ny9 - 1) / 2;
+    constexpr int SH = NV + 3, SV = NV + 1;  // padded entry lengths of the shared-memory tables [double2]
+    double2* sKH = reinterpret_cast<double2*>(rowbits + MAXHR);
+    double2* sKV = sKH + (MODE == 3 ? s.nx9 * s.ny9 * SH : 0);
+    if (MODE == 3) {
+        const int nent = s.nx9 * s.ny9;
+        for (int k = tid; k < nent * (NV + 2); k += TX * TY) sKH[(k / (NV + 2)) * SH + k % (NV + 2)] = KH[k];
+        for (int k = tid; k < nent * NV; k += TX * TY) sKV[(k / NV) * SV + k % NV] = KV[k];
+        // (visible to every thread after the barriers of the slot sort below)
+    }
     // Each slot's window of charged pixels is packed once into one 64-bit word, 8 bits per halo row (qdist <= 3:
     // at most 8 rows of at most 8 columns), lowest bit = first pixel in the reference's (row, column) order, so
     // the loop below visits exactly the charged pixels with one find-first-set each and no per-row scanning.
@@ -396,6 +407,10 @@ k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __rest
                             const double2 d = __ldg(KH + kk + k);
                             bf_term(hx[k], d.x, c);
                             bf_term(hy[k], d.y, c);
+                        } else if (MODE == 3) {
+                            const double2 d = sKH[(kk / (NV + 2)) * SH + k];
+                            hx[k] = (double)(float)__dadd_rn(hx[k], __dmul_rn(d.x, c));
+                            hy[k] = (double)(float)__dadd_rn(hy[k], __dmul_rn(d.y, c));
                         } else if (MODE == 2) {
                             const double2 d = __ldg(KH + kk + k);
                             hx[k] = (double)(float)__dadd_rn(hx[k], __dmul_rn(d.x, c));
@@ -432,6 +447,10 @@ k_update_distortions_tiled(const __grid_constant__ DevSensor s, const CT* __rest
                             const double2 d = __ldg(KV + kk + k);
                             bf_term(vx[k], d.x, c);
                             bf_term(vy[k], d.y, c);
+                        } else if (MODE == 3) {
+                            const double2 d = sKV[(kk / NV) * SV + k];
+                            vx[k] = (double)(float)__dadd_rn(vx[k], __dmul_rn(d.x, c));
+                            vy[k] = (double)(float)__dadd_rn(vy[k], __dmul_rn(d.y, c));
                         } else if (MODE == 2) {
                             const double2 d = __ldg(KV + kk + k);
                             vx[k] = (double)(float)__dadd_rn(vx[k], __dmul_rn(d.x, c));
@@ -1018,16 +1037,23 @@ static int launch_update_tiled(b2_sensor* s, const CT* charge) {
     size_t smem = (size_t)24 * 64 * sizeof(double) + 24 * sizeof(unsigned long long);
     dim3 block(32, 8, 1);
     dim3 grid((d.nx + 1 + 31) / 32, (d.ny + 1 + 7) / 8, 1);
-    static const int mode = getenv("B2_UPDATE_MODE") ? atoi(getenv("B2_UPDATE_MODE")) : 2;
-    if (d.nv == 4) {
-        if (mode == 1) k_update_distortions_tiled<CT, 4, 1><<<grid, block, smem, st>>>(d, charge, s->changed);
-        else if (mode == 2) k_update_distortions_tiled<CT, 4, 2><<<grid, block, smem, st>>>(d, charge, s->changed);
-        else k_update_distortions_tiled<CT, 4, 0><<<grid, block, smem, st>>>(d, charge, s->changed);
-    } else {
-        if (mode == 1) k_update_distortions_tiled<CT, 8, 1><<<grid, block, smem, st>>>(d, charge, s->changed);
-        else if (mode == 2) k_update_distortions_tiled<CT, 8, 2><<<grid, block, smem, st>>>(d, charge, s->changed);
-        else k_update_distortions_tiled<CT, 8, 0><<<grid, block, smem, st>>>(d, charge, s->changed);
+    static const int mode = getenv("B2_UPDATE_MODE") ? atoi(getenv("B2_UPDATE_MODE")) : 3;
+    const size_t smem3 = smem + (size_t)d.nx9 * d.ny9 * ((d.nv + 3) + (d.nv + 1)) * sizeof(double2);
+#define B2_TILED(NVV, MM, SM)                                                                                          \
+    {                                                                                                                 \
+        if ((SM) > 48 * 1024)                                                                                         \
+            B2_CUDA(cudaFuncSetAttribute(k_update_distortions_tiled<CT, NVV, MM>,                                      \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM)));                    \
+        k_update_distortions_tiled<CT, NVV, MM><<<grid, block, (SM), st>>>(d, charge, s->changed);                    \
     }
+    if (d.nv == 4) {
+        if (mode == 1) B2_TILED(4, 1, smem) else if (mode == 2) B2_TILED(4, 2, smem) else if (mode == 3) B2_TILED(4, 3, smem3)
+        else B2_TILED(4, 0, smem)
+    } else {
+        if (mode == 1) B2_TILED(8, 1, smem) else if (mode == 2) B2_TILED(8, 2, smem) else if (mode == 3) B2_TILED(8, 3, smem3)
+        else B2_TILED(8, 0, smem)
+    }
+#undef B2_TILED
     B2_CHECK_LAUNCH();
     return 0;
 }
