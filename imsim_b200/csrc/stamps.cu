@@ -160,6 +160,8 @@ __device__ __forceinline__ unsigned row_bits(const StampBits& cb, int j, int i1,
     return (unsigned)v & (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
 }
 
+#define ST_SH(nv) ((nv) + 3)  // padded lengths [double2] of a table entry in shared memory: horizontal, vertical
+#define ST_SV(nv) ((nv) + 1)
 #define ST_QMAX 3  // the list path is written for qdist = 3 (GalSim's default, what imSim's models use): 8 x 8 windows
 
 // q == 3: the window of slot (x, y) is 8 rows x 8 columns, one 64-bit word, bit 8 r + c = pixel (x - 4 + c, y - 4 + r)
@@ -211,7 +213,7 @@ __device__ __forceinline__ void stamp_slot_apply(const DevSensor& s, const doubl
             const double c = __ldcg(charge + (size_t)j * nx + i);
             if (c == 0.0) continue;
             any = true;
-            const double2* kh = KH + ((y - j + cyk) * s.nx9 + (x - i + cxk)) * (NV + 2);
+            const double2* kh = KH + ((y - j + cyk) * s.nx9 + (x - i + cxk)) * ST_SH(NV);
 #pragma unroll
             for (int k = 0; k <= NV + 1; ++k) {
                 const double2 d = kh[k];
@@ -243,7 +245,7 @@ __device__ __forceinline__ void stamp_slot_apply(const DevSensor& s, const doubl
             const double c = __ldcg(charge + (size_t)j * nx + i);
             if (c == 0.0) continue;
             any = true;
-            const double2* kv = KV + ((y - j + cyk) * s.nx9 + (x - i + cxk)) * NV;
+            const double2* kv = KV + ((y - j + cyk) * s.nx9 + (x - i + cxk)) * ST_SV(NV);
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
                 const double2 d = kv[k];
@@ -324,9 +326,11 @@ k_stamp_jobs(const __grid_constant__ DevSensor base, const B2StampJob* __restric
     const unsigned rank = T::rank();
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int gtid = (int)rank * ST_THREADS + tid;
-    const int nKH = base.nx9 * base.ny9 * (NV + 2), nKV = base.nx9 * base.ny9 * NV;
-    for (int k = tid; k < nKH; k += ST_THREADS) sK[k] = base.KHd[k];
-    for (int k = tid; k < nKV; k += ST_THREADS) sK[nKH + k] = base.KVd[k];
+    // entries padded by one point: the lanes of a warp read different entries, which then spread over the banks
+    const int nent = base.nx9 * base.ny9;
+    const int nKH = nent * ST_SH(NV), nKV = nent * ST_SV(NV);
+    for (int k = tid; k < nent * (NV + 2); k += ST_THREADS) sK[(k / (NV + 2)) * ST_SH(NV) + k % (NV + 2)] = base.KHd[k];
+    for (int k = tid; k < nent * NV; k += ST_THREADS) sK[nKH + (k / NV) * ST_SV(NV) + k % NV] = base.KVd[k];
     const double2* KH = sK;
     const double2* KV = sK + nKH;
     SlowRec* slow = slow_scratch + (size_t)blockIdx.x * ST_TILE;
@@ -915,7 +919,7 @@ extern "C" int b2_sensor_accumulate_stamps(b2_sensor* s, int32_t njobs, const B2
     B2_CUDA(cudaMemcpyAsync(dorder, order.data(), (size_t)njobs * sizeof(int), cudaMemcpyHostToDevice, st));
     const StampPhotons ph{x, y, dxdz, dydz, wl, flux, rand4, n, seed, offset};
     const FullImage full{full_pixels, full_xmin, full_ymin, full_nx, full_ny, dtype_bytes};
-    const size_t smem_k = (size_t)s->d.nx9 * s->d.ny9 * (2 * nv + 2) * sizeof(double2);
+    const size_t smem_k = (size_t)s->d.nx9 * s->d.ny9 * (ST_SH(nv) + ST_SV(nv)) * sizeof(double2);
     // occupancy bitmap of the stamp in flight in shared memory: two blocks per SM share ~220 KB
     size_t bit_words = 0;
     for (int j = 0; j < njobs; ++j)
