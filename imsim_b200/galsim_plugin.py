@@ -34,6 +34,8 @@ a real GalSim.
 """
 from __future__ import annotations
 
+import os
+
 import galsim
 import numpy as np
 from galsim.config import (GetAllParams, GetInputObj, InputLoader, PhotonOpBuilder, RegisterInputType,
@@ -90,12 +92,19 @@ _N_GPUS = None
 
 
 def _device(base):
-    """One GPU per worker process: det_num % n_gpus (GalSim forks workers per output file)."""
+    """One GPU per worker process.  A launcher that pins one process per GPU says which (``LOCAL_RANK`` of torchrun /
+    srun wrappers, or ``b2_device`` in the config's base dict); otherwise det_num % n_gpus: GalSim forks its
+    workers per output file, i.e. per detector."""
     global _N_GPUS
     if _N_GPUS is None:
         import torch
 
         _N_GPUS = max(torch.cuda.device_count(), 1)  # asked once: the NVML query costs ~20 ms a call
+    if "b2_device" in base:
+        return int(base["b2_device"]) % _N_GPUS
+    local_rank = os.environ.get("LOCAL_RANK")
+    if local_rank is not None and local_rank.lstrip("-").isdigit():
+        return int(local_rank) % _N_GPUS
     return int(base.get("det_num", base.get("file_num", 0))) % _N_GPUS
 
 

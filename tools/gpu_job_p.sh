@@ -1,12 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out/r02
-for n in 8; do
-  timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2953$n \
-    bench.py --gpus $n --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r02/bench_n${n}_lanes.json 2> gpurun_out/r02/bench_n${n}_lanes.err
-  echo "N=$n rc=$?"; tail -c 300 gpurun_out/r02/bench_n${n}_lanes.err
+for n in 4 2; do
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2955$n \
+    bench.py --gpus $n --steps 5 --warmup 3 --no-cpu-baseline --no-visit-line > gpurun_out/r02/bench_n${n}_fixed.json 2>/dev/null
   python - <<P
 import json
-d=json.loads(open('gpurun_out/r02/bench_n${n}_lanes.json').read().strip().splitlines()[-1])
-print('value %.3e e2e %.3e visit %s' % (d['value'], d['e2e']['value'], {k: d['visit'].get(k) for k in ('visits_per_hour','wall_s_max_rank','note','error','lanes_per_gpu')}))
+d=json.loads(open('gpurun_out/r02/bench_n${n}_fixed.json').read().strip().splitlines()[-1])
+print('N=$n value %.3e e2e %.3e pinned %.3e' % (d['value'], d['e2e']['value'], d['e2e']['pinned_route']['value']))
 P
 done
