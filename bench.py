@@ -337,7 +337,7 @@ def visit_for_line(args, rank, world, local, dev):
 
     opts = argparse.Namespace(visit_catalog=True, visit_readout=True, visit_sky=800.0, visit_ccds=args.visit_ccds,
                               visit_photons=args.visit_photons, visit_repeat=2, visit_serial=False,
-                              visit_lanes=args.visit_lanes or int(os.environ.get("B2_VISIT_LANES", "2")))
+                              visit_lanes=getattr(args, "visit_lanes", 0) or int(os.environ.get("B2_VISIT_LANES", "2")))
     mx = [0.0, 0.0, 0.0, 0.0]  # wall of the reported visit, wall of the first, GPU time, failure flag
     sm = [0.0, 0.0]            # photons, CCDs
     err = ""
