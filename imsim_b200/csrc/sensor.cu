@@ -494,13 +494,14 @@ k_update_bounds(const __grid_constant__ DevSensor s, const uint8_t* __restrict__
         oymin = fmin(oymin, py);
         oymax = fmax(oymax, py);
     });
-    double cx = (oxmin + oxmax) / 2.0, cy = (oymin + oymax) / 2.0;
-    double ixmin = oxmin, ixmax = oxmax, iymin = oymin, iymax = oymax;
-    walk_polygon(s, x, y, [&](double px, double py, double, double) {
-        if (px - cx >= fabs(py - cy) && px < ixmax) ixmax = px;
-        if (px - cx <= -fabs(py - cy) && px > ixmin) ixmin = px;
-        if (py - cy >= fabs(px - cx) && py < iymax) iymax = py;
-        if (py - cy <= -fabs(px - cx) && py > iymin) iymin = py;
+    // the "trivially inside" box, inscribed by construction: the innermost vertex of each edge, corners counting for
+    // both edges they end (oracle_sensor.c: update_bounds)
+    double ixmin = -INFINITY, ixmax = INFINITY, iymin = -INFINITY, iymax = INFINITY;
+    walk_polygon(s, x, y, [&](double px, double py, double ex, double ey) {
+        if (ex == 0.0 && px > ixmin) ixmin = px;
+        if (ex == 1.0 && px < ixmax) ixmax = px;
+        if (ey == 0.0 && py > iymin) iymin = py;
+        if (ey == 1.0 && py < iymax) iymax = py;
     });
     *reinterpret_cast<double4*>(s.outer + pix * 4) = make_double4(oxmin, oxmax, oymin, oymax);
     *reinterpret_cast<double4*>(s.inner + pix * 4) = make_double4(ixmin, ixmax, iymin, iymax);
@@ -550,23 +551,12 @@ k_update_bounds_t(const __grid_constant__ DevSensor s, const uint8_t* __restrict
     const double oxmax = fmax((double)fmaxf(fmaxf(bx1, tx1), lx1), (double)rx1 + 1.0);
     const double oymin = fmin((double)fminf(fminf(by0, ly0), ry0), (double)ty0 + 1.0);
     const double oymax = fmax((double)fmaxf(fmaxf(by1, ly1), ry1), (double)ty1 + 1.0);
-    const double cx = (oxmin + oxmax) / 2.0, cy = (oymin + oymax) / 2.0;
-    double ixmin = oxmin, ixmax = oxmax, iymin = oymin, iymax = oymax;
-    auto inner = [&](double px, double py) {
-        if (px - cx >= fabs(py - cy) && px < ixmax) ixmax = px;
-        if (px - cx <= -fabs(py - cy) && px > ixmin) ixmin = px;
-        if (py - cy >= fabs(px - cx) && py < iymax) iymax = py;
-        if (py - cy <= -fabs(px - cx) && py > iymin) iymin = py;
-    };
-    // same order as walk_polygon (the updates are order independent minima / maxima, kept for clarity)
-#pragma unroll
-    for (int k = 0; k < NV + 2; ++k) inner((double)B[k].x, (double)B[k].y);
-#pragma unroll
-    for (int k = 0; k < NV; ++k) inner((double)R[k].x + 1.0, (double)R[k].y);
-#pragma unroll
-    for (int k = NV + 1; k >= 0; --k) inner((double)T[k].x, (double)T[k].y + 1.0);
-#pragma unroll
-    for (int k = NV - 1; k >= 0; --k) inner((double)L[k].x, (double)L[k].y);
+    // inner box: the innermost vertex of each edge, corners counting for both edges they end -- the per-edge
+    // extrema are at hand already (conversion and the +1 offsets are monotone, as for the outer box)
+    const double ixmin = (double)fmaxf(fmaxf(lx1, B[0].x), T[0].x);
+    const double ixmax = fmin((double)rx0 + 1.0, (double)fminf(B[NV + 1].x, T[NV + 1].x));
+    const double iymin = (double)by1;
+    const double iymax = (double)ty0 + 1.0;
     *reinterpret_cast<double4*>(s.outer + pix * 4) = make_double4(oxmin, oxmax, oymin, oymax);
     *reinterpret_cast<double4*>(s.inner + pix * 4) = make_double4(ixmin, ixmax, iymin, iymax);
 }

@@ -63,13 +63,12 @@ __device__ __forceinline__ void stamp_bounds_pixel(const DevSensor& s, int x, in
         oymin = fmin(oymin, py);
         oymax = fmax(oymax, py);
     });
-    double cx = (oxmin + oxmax) / 2.0, cy = (oymin + oymax) / 2.0;
-    double ixmin = oxmin, ixmax = oxmax, iymin = oymin, iymax = oymax;
-    walk_polygon<NV>(s, x, y, [&](double px, double py, double, double) {
-        if (px - cx >= fabs(py - cy) && px < ixmax) ixmax = px;
-        if (px - cx <= -fabs(py - cy) && px > ixmin) ixmin = px;
-        if (py - cy >= fabs(px - cx) && py < iymax) iymax = py;
-        if (py - cy <= -fabs(px - cx) && py > iymin) iymin = py;
+    double ixmin = -INFINITY, ixmax = INFINITY, iymin = -INFINITY, iymax = INFINITY;
+    walk_polygon<NV>(s, x, y, [&](double px, double py, double ex, double ey) {
+        if (ex == 0.0 && px > ixmin) ixmin = px;
+        if (ex == 1.0 && px < ixmax) ixmax = px;
+        if (ey == 0.0 && py > iymin) iymin = py;
+        if (ey == 1.0 && py < iymax) iymax = py;
     });
     size_t pix = (size_t)y * s.nx + x;
     *reinterpret_cast<double4*>(s.outer + pix * 4) = make_double4(oxmin, oxmax, oymin, oymax);
