@@ -1,8 +1,7 @@
 #!/bin/bash
-# ncu --set full of the boundary update inside a catalogue-field visit CCD, both arithmetic variants
-mkdir -p gpurun_out/r02
-for a in 1 0; do
-  B2_UPDATE_ADDER=$a timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_update_distortions_tiled -s 6 -c 1 \
-    -o gpurun_out/r02/prof_update_dense_adder$a -f python tools/visit_kernel_breakdown.py --catalog > gpurun_out/r02/ncu_update_dense_$a.log 2>&1
-  echo "adder=$a rc=$?"; tail -3 gpurun_out/r02/ncu_update_dense_$a.log | cut -c1-300
+# stage 1: blocks per SM held by the register allocation (B2_STAGE1_OCC 4 / 5 / 6 / 8), per-kernel time in a catalogue-field CCD
+for o in 4 5 6 8 4 6; do
+  echo "== B2_STAGE1_OCC=$o"
+  B2_STAGE1_OCC=$o timeout 600 python tools/visit_kernel_breakdown.py --catalog 2>&1 | grep "^R22" | tail -1 | grep -o "'k_stage1_photons': ([0-9]*, [0-9.]*)"
 done
+B2_STAGE1_OCC=6 timeout 600 python -m pytest tests/test_gpu_stage1.py -q -x 2>&1 | tail -1
