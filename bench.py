@@ -736,7 +736,7 @@ def main():
 
     # ---- end-to-end steps through the public host-facing API: pinned host batches -> H2D (double
     # buffered on a copy stream) -> b2_pool_step -> D2H of the image after every batch ----
-    e2e_K = int(os.environ.get("B2_E2E_STEPS", "0")) or max(3, min(K, 6))  # (longer for PCIe counter sampling)
+    e2e_K = int(os.environ.get("B2_E2E_STEPS", "0")) or max(3, min(K, 20))  # (B2_E2E_STEPS: longer, for PCIe counter sampling)
     host_batches = [pinned] * e2e_K
     pool.run_host_batches(host_batches[:2], image, first_resume=True)  # warm the pipeline
     barrier()
