@@ -300,7 +300,9 @@ def test_annular_zernike_basis_is_orthonormal():
 # tests/test_sensor_models.py:13-37: Mxx, Myy of a 1e6 e-, sigma = 1 px Gaussian on 17 x 17, one GalSim RNG stream
 _REG = {"none": (1.0814199384960002, 1.0829925551110002),
         "lsst_itl_50_4": (1.2904056635999999, 1.2986653947160003), "lsst_itl_50_8": (1.2903588210709998, 1.298329443484),
-        "lsst_e2v_50_4": (1.305061712704, 1.321133490204), "lsst_e2v_50_8": (1.3052209484710002, 1.319877330876)}
+        "lsst_itl_50_32": (1.290387793884, 1.298246399375),
+        "lsst_e2v_50_4": (1.305061712704, 1.321133490204), "lsst_e2v_50_8": (1.3052209484710002, 1.319877330876),
+        "lsst_e2v_50_32": (1.3050858704, 1.319152136959)}
 
 
 def _moments(a):
@@ -347,10 +349,20 @@ def test_sensor_moment_differences_between_models():
     They test what depends on the model: the strength of brighter-fatter (e2v against ITL) and the handling of
     coarse pixel polygons (4 against 8 vertices per edge), i.e. the corner regions.  With the inscribed
     "trivially inside" box (oracle_sensor.c: update_bounds) the oracle gives, minus the reference,
-    e2v_4 - itl_4: x -0.0006, y -0.0010;  itl_4 - itl_8: y +0.0002;  e2v_4 - e2v_8: y +0.0001;
+    e2v_4 - itl_4: x -0.0006, y -0.0008;  e2v_32 - itl_32: -0.0003, -0.0003;  itl_4 - itl_8: y +0.0002;  e2v_4 - e2v_8:
+    y +0.0001;  itl_8 - itl_32: y +0.0004;  e2v_8 - e2v_32: y -0.0000;
     with a box built from GalSim-style 45-degree wedges it was x -0.0012, y -0.0020; -0.0003; -0.0005."""
     models = ["lsst_itl_50_4", "lsst_itl_50_8", "lsst_e2v_50_4", "lsst_e2v_50_8"]
     loaded = {m: helpers.sensor_model(m) for m in models}
+    # the two 32-vertex models (tests/golden/make_golden_sensor_models_32.py): polygons fine enough for the shape of
+    # the trivially-inside box not to matter
+    g32 = helpers.golden("sensor_models_32.npz")
+    for m in ("lsst_itl_50_32", "lsst_e2v_50_32"):
+        cfg = {str(k): (int(v) if str(k) in ("NumVertices", "PixelBoundaryNx", "PixelBoundaryNy", "NumPhases",
+                                              "CollectingPhases") else float(v))
+               for k, v in zip(g32["cfg_keys"], g32[m + "_cfg"])}
+        loaded[m] = (cfg, np.ascontiguousarray(g32[m + "_dat"]))
+        models.append(m)
     acc = {m: np.zeros(2) for m in models}
     nseed = 3
     for seed in range(nseed):
@@ -377,3 +389,7 @@ def test_sensor_moment_differences_between_models():
     for sensor in ("itl", "e2v"):
         d = excess("lsst_%s_50_4" % sensor, "lsst_%s_50_8" % sensor)
         assert abs(d[0]) < 0.0004 and abs(d[1]) < 0.0005, (sensor, d)
+        d = excess("lsst_%s_50_8" % sensor, "lsst_%s_50_32" % sensor)  # measured: itl y +0.0004, e2v y -0.0000 (x -0.0002)
+        assert abs(d[0]) < 0.0004 and abs(d[1]) < 0.0006, (sensor, d)
+    d = excess("lsst_e2v_50_32", "lsst_itl_50_32")  # brighter-fatter strength without polygon coarseness: x -0.0003, y -0.0003
+    assert abs(d[0]) < 0.0008 and abs(d[1]) < 0.0012, d
