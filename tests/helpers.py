@@ -85,3 +85,16 @@ def test_photon_arrays(n=10000, t=0.0, seed=42, wavelength=577.6, center=(0.0, 0
                 time=np.full(n, t))
 
 
+
+
+_package_sensor_model = sensor_model
+
+
+def sensor_model(name="lsst_itl_50_4"):  # noqa: F811
+    """The package's four sensor models, plus the reference's two 32-vertex ones from tests/golden."""
+    if not name.endswith("_32"):
+        return _package_sensor_model(name)
+    g = golden("sensor_models_32.npz")
+    ints = ("NumVertices", "PixelBoundaryNx", "PixelBoundaryNy", "NumPhases", "CollectingPhases")
+    cfg = {str(k): (int(v) if str(k) in ints else float(v)) for k, v in zip(g["cfg_keys"], g[name + "_cfg"])}
+    return cfg, np.ascontiguousarray(g[name + "_dat"])

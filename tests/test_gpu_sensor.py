@@ -100,9 +100,10 @@ def test_boundaries_match_oracle_with_tree_rings():
     assert np.array_equal(gi.array, ci)
 
 
-@pytest.mark.parametrize("model", ["lsst_itl_50_4", "lsst_e2v_50_8"])
+@pytest.mark.parametrize("model", ["lsst_itl_50_4", "lsst_e2v_50_8", "lsst_itl_50_32"])
 def test_bf_on_matches_oracle(model):
-    """Brighter-fatter on, boundary updates every nrecalc electrons in photon order."""
+    """Brighter-fatter on, boundary updates every nrecalc electrons in photon order (32 vertices per edge: the
+    generic kernels, 4 and 8 the specialised ones)."""
     gpu, cpu = _sensors(model=model, treerings=True, strength=1.0, nrecalc=10000)
     rng = np.random.default_rng(3)
     pa, rand4 = _photons(300000, 33, 33, rng, kind="star", wavelengths=False, angles=False)

@@ -356,12 +356,8 @@ def test_sensor_moment_differences_between_models():
     loaded = {m: helpers.sensor_model(m) for m in models}
     # the two 32-vertex models (tests/golden/make_golden_sensor_models_32.py): polygons fine enough for the shape of
     # the trivially-inside box not to matter
-    g32 = helpers.golden("sensor_models_32.npz")
     for m in ("lsst_itl_50_32", "lsst_e2v_50_32"):
-        cfg = {str(k): (int(v) if str(k) in ("NumVertices", "PixelBoundaryNx", "PixelBoundaryNy", "NumPhases",
-                                              "CollectingPhases") else float(v))
-               for k, v in zip(g32["cfg_keys"], g32[m + "_cfg"])}
-        loaded[m] = (cfg, np.ascontiguousarray(g32[m + "_dat"]))
+        loaded[m] = helpers.sensor_model(m)
         models.append(m)
     acc = {m: np.zeros(2) for m in models}
     nseed = 3
